@@ -1,0 +1,157 @@
+/*
+ * vrod_knn.h -- C ABI of the B200-native exact k-nearest-neighbour scan that fills vRod's SEARCH
+ * hot path.  Plain C: opaque handles, pointers and sizes only; no C++ exception crosses it.
+ *
+ * Reference interfaces these entry points stand behind (paths relative to the vRod repo):
+ *   - src/command/types.rs:5-7      trait Command { fn execute(&self); }          (call shape)
+ *   - src/command/types.rs:114-119  SearchCommand::execute  -- EMPTY body; vrod_collection_search
+ *                                   is what a maintainer would call from it
+ *   - src/command/types.rs:14-19    CreateCollectionCommand::execute -> vrod_collection_create
+ *   - src/command/types.rs:27-32    DropCollectionCommand::execute   -> vrod_collection_drop
+ *   - src/command/types.rs:38-43    ListCollectionsCommand::execute  -> vrod_collection_list
+ *   - src/command/types.rs:62-67, 75-80  Insert/BulkInsertCommand::execute -> vrod_collection_insert
+ *   - src/database/mod.rs:6-10      struct Database (collections are a TODO) -> vrod_ctx owns them
+ *   - src/utils/embeddings.rs:29-31 Vec<Vec<f32>> rows: element type f32, one dimension per set
+ * The reference has no FFI of its own; INTEGRATION.md shows the Rust
+ * `extern "C"` block and the command bodies that bind these symbols.
+ *
+ * Rules: the caller owns every host buffer; the library copies in/out and retains no pointer.
+ * Handles are freed only by vrod_ctx_destroy / vrod_collection_drop.  One calling thread per
+ * vrod_ctx (the reference's Rc<RefCell<Database>> is !Send + !Sync, types.rs:10).  Every function
+ * returns a vrod_status; vrod_last_error() gives the thread-local message of the last failure.
+ * There is no CPU fallback: without a CUDA device vrod_ctx_create fails with VROD_ENOGPU.
+ *
+ * Search semantics (DESIGN.md "Search semantics"; parity is unpinned by the reference):
+ *   Euclidean  dist = (f32) sqrt( SUM_j (x_j - q_j)^2 )
+ *   Cosine     dist = (f32) (1 - dot / (sqrt(nx) sqrt(nq))),  dist = 1 if nx == 0 or nq == 0
+ *   sums in f64 with fma in the fixed 128-way interleaved order + adjacent-pair tree,
+ *   results ordered by (f32 dist ascending, id ascending), ids = insertion index (u64) from 0,
+ *   slots beyond min(k, N) padded with id = UINT64_MAX, dist = +inf.
+ *   Non-finite inputs are rejected with VROD_EINVAL.
+ */
+#ifndef VROD_KNN_H
+#define VROD_KNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VROD_API __attribute__((visibility("default")))
+#else
+#define VROD_API
+#endif
+
+typedef struct vrod_ctx vrod_ctx;               /* device, stream, NCCL communicator, collections */
+typedef struct vrod_collection vrod_collection; /* this rank's row shard: rows, norms, scratch     */
+
+typedef enum {
+    VROD_OK = 0,
+    VROD_EINVAL = 1,    /* bad argument, non-finite input, dimension mismatch, k out of range */
+    VROD_ENOTFOUND = 2, /* no collection of that name */
+    VROD_EEXISTS = 3,   /* collection name already taken */
+    VROD_ENOMEM = 4,    /* host or device allocation failed, or capacity exceeded */
+    VROD_ECUDA = 5,     /* CUDA runtime error */
+    VROD_ENCCL = 6,     /* NCCL error or NCCL library not loadable */
+    VROD_ENOGPU = 7     /* no usable CUDA device: there is no CPU path */
+} vrod_status;
+
+typedef enum { VROD_EUCLIDEAN = 0, VROD_COSINE = 1 } vrod_metric;
+
+#define VROD_MAX_K 1024u          /* largest k a search accepts */
+#define VROD_COMM_ID_BYTES 128u   /* size of the opaque communicator id (an ncclUniqueId) */
+#define VROD_PAD_ID UINT64_MAX
+
+/* Counters of one context, for benches and tests (monotonic since ctx creation). */
+typedef struct {
+    uint64_t searches;         /* queries answered */
+    uint64_t kernel_launches;  /* CUDA kernels this library launched */
+    uint64_t fast_scans;       /* queries answered by the f32 scan + exact rerank */
+    uint64_t exact_rescans;    /* queries whose guard failed and were re-answered by the f64 scan */
+    uint64_t batched_tiles;    /* tensor-core tiles issued by the batched path */
+    uint64_t h2d_bytes;        /* bytes copied host->device by search calls */
+    uint64_t d2h_bytes;        /* bytes copied device->host by search calls */
+} vrod_stats;
+
+/* ---- context -------------------------------------------------------------------------- */
+
+/* One GPU, no sharding.  `device` is a CUDA ordinal. */
+VROD_API vrod_status vrod_ctx_create(int device, vrod_ctx **out);
+
+/* Fill `out` (VROD_COMM_ID_BYTES) with a fresh communicator id; rank 0 calls it and ships the
+ * bytes to the other ranks by any means (the benches use torch.distributed). */
+VROD_API vrod_status vrod_comm_unique_id(void *out);
+
+/* One process per GPU: this rank holds shard `rank` of `world` of every collection (contiguous row
+ * ranges).  Collective: all ranks call it with the same id.  Searches
+ * merge the per-rank top-k lists with one ncclAllGather on the context's stream. */
+VROD_API vrod_status vrod_ctx_create_sharded(int device, int rank, int world, const void *comm_id,
+                                             vrod_ctx **out);
+
+VROD_API void vrod_ctx_destroy(vrod_ctx *ctx);
+VROD_API vrod_status vrod_ctx_synchronize(vrod_ctx *ctx);
+/* The cudaStream_t every kernel and copy of this context is issued on (for event timing). */
+VROD_API void *vrod_ctx_stream(vrod_ctx *ctx);
+VROD_API vrod_status vrod_ctx_stats(vrod_ctx *ctx, vrod_stats *out);
+VROD_API int vrod_ctx_rank(vrod_ctx *ctx);
+VROD_API int vrod_ctx_world(vrod_ctx *ctx);
+
+/* ---- collections (Database surface) ---------------------------------------------------- */
+
+/* CREATE: `capacity_rows` is the GLOBAL row capacity; a sharded context keeps ceil(capacity/world)
+ * rows per rank.  dim >= 1. */
+VROD_API vrod_status vrod_collection_create(vrod_ctx *ctx, const char *name, uint32_t dim, vrod_metric metric,
+                                            uint64_t capacity_rows, vrod_collection **out);
+VROD_API vrod_status vrod_collection_get(vrod_ctx *ctx, const char *name, vrod_collection **out);
+VROD_API vrod_status vrod_collection_drop(vrod_ctx *ctx, const char *name);
+/* LISTCOLLECTIONS: writes the names, '\n'-separated and NUL-terminated, into buf (cap bytes);
+ * *needed receives the size required including the NUL. */
+VROD_API vrod_status vrod_collection_list(vrod_ctx *ctx, char *buf, size_t cap, size_t *needed);
+
+VROD_API vrod_status vrod_collection_info(vrod_collection *c, uint32_t *dim, vrod_metric *metric,
+                                          uint64_t *count, uint64_t *capacity);
+
+/* INSERT / BULKINSERT: append n rows (row-major n x dim f32).  Ids are insertion indices; the id of
+ * the first appended row is written to *first_id (may be NULL).  In a sharded context every rank
+ * passes the same rows and keeps the part that falls into its range. */
+VROD_API vrod_status vrod_collection_insert(vrod_collection *c, const float *rows, uint64_t n, uint64_t *first_id);
+
+/* Append n synthetic rows generated ON THE DEVICE: element (i, j) of a collection is
+ * u2f(philox4x32_10(counter = (i*dim + j) >> 2, key = seed)[(i*dim + j) & 3]), uniform [-1, 1);
+ * i is the global row index.  The CPU oracle replays it bit for bit. */
+VROD_API vrod_status vrod_collection_fill_synthetic(vrod_collection *c, uint64_t n, uint64_t seed);
+
+/* Copy rows [row0, row0+n) of THIS RANK's shard (local indices) back to the host (n x dim). */
+VROD_API vrod_status vrod_collection_read_rows(vrod_collection *c, uint64_t row0, uint64_t n, float *out);
+/* Global id of this rank's local row 0 and the number of rows it holds. */
+VROD_API vrod_status vrod_collection_shard(vrod_collection *c, uint64_t *id_base, uint64_t *local_rows);
+
+/* ---- SEARCH ----------------------------------------------------------------------------- */
+
+/* Exact top-k of b queries (row-major b x dim f32, host memory).  out_ids / out_dist: b x k, host.
+ * Synchronous: results are in the out buffers on return.  1 <= k <= VROD_MAX_K.  In a sharded
+ * context it is collective (same queries on every rank) and every rank receives the global result. */
+VROD_API vrod_status vrod_collection_search(vrod_collection *c, const float *queries, uint32_t b, uint32_t k,
+                                            uint64_t *out_ids, float *out_dist);
+
+/* Same, with queries and outputs already resident in device memory of the context's GPU.  The work
+ * is enqueued on vrod_ctx_stream() and the call returns without synchronising; queries must have
+ * been validated (finite) by the caller. */
+VROD_API vrod_status vrod_collection_search_device(vrod_collection *c, const float *d_queries, uint32_t b,
+                                                   uint32_t k, uint64_t *d_out_ids, float *d_out_dist);
+
+/* Force a path for tests and benches: 0 = automatic (default), 1 = f32 scan + rerank only where the
+ * guard holds else exact (same as auto but never the batched path), 2 = always the exact f64 scan,
+ * 3 = always the tensor-core batched path. */
+VROD_API vrod_status vrod_collection_set_path(vrod_collection *c, int path);
+
+VROD_API const char *vrod_last_error(void);
+VROD_API const char *vrod_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VROD_KNN_H */

@@ -1,0 +1,217 @@
+// knn_device.cuh -- device helpers shared by the kNN scan kernels (sm_100a).
+//
+// Hot path of vRod's SEARCH command (call site: reference src/command/types.rs:114-119, empty body).
+// Nothing here has a reference counterpart; the semantics are DESIGN.md "Search semantics".
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vrod {
+
+constexpr int kScanThreads = 256;  // 8 warps per CTA
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint64_t kKeyMax = 0xFFFFFFFFFFFFFFFFull;
+
+// ---- order-preserving float <-> uint32 (so (value, row) packs into one comparable u64) --------
+__device__ __forceinline__ uint32_t f2ord(float v) {
+    uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+    uint32_t b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t make_key(float v, uint32_t row) {
+    return ((uint64_t)f2ord(v) << 32) | row;
+}
+
+// ---- streaming 128-bit load: read-only path, no L1 allocation (each byte is used once) --------
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(p));
+    return r;
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), the library's own statement of the generator -------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+    uint32_t c2 = 0, c3 = 0;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ float word_to_unit(uint32_t w) {
+    return (float)((int32_t)(w >> 8) - (1 << 23)) * 0x1p-23f;
+}
+
+// ---- multi-row butterfly reduction --------------------------------------------------------------
+// Each lane holds N partial sums (one per row slot).  After the call every lane holds the full sum
+// of ONE row slot (returned; its index is added to rsel), replicated over the lanes that differ in
+// the bits not used for slot selection.  N row slots cost N-1 + log2(LPR/N) shuffles instead of
+// N*log2(LPR).  ASC = true walks lane offsets 1,2,4,.. (the canonical adjacent-pair order of the
+// exact f64 sums); ASC = false walks LPR/2,..,1.
+template <typename T, int N, int OFF, int LPR, bool ASC>
+struct RowsReduce {
+    static __device__ __forceinline__ T run(T *p, int lane, int &rsel, int weight) {
+        constexpr bool live = ASC ? (OFF < LPR) : (OFF >= 1);
+        if constexpr (!live) {
+            static_assert(N == 1, "more row slots than lanes per row");
+            return p[0];
+        } else {
+            constexpr int NEXT = ASC ? OFF * 2 : OFF / 2;
+            if constexpr (N > 1) {
+                constexpr int H = N / 2;
+                const bool up = (lane & OFF) != 0;
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    const T send = up ? p[j] : p[j + H];
+                    const T keep = up ? p[j + H] : p[j];
+                    p[j] = keep + __shfl_xor_sync(kFull, send, OFF);
+                }
+                if (up) rsel += H;
+                return RowsReduce<T, H, NEXT, LPR, ASC>::run(p, lane, rsel, weight);
+            } else {
+                p[0] = p[0] + __shfl_xor_sync(kFull, p[0], OFF);
+                return RowsReduce<T, 1, NEXT, LPR, ASC>::run(p, lane, rsel, weight);
+            }
+        }
+    }
+};
+
+// ---- per-CTA candidate store ----------------------------------------------------------------------
+// A CTA keeps the best `kprime` keys it has seen in shared memory.  Warps append keys that beat the
+// current threshold; when the store passes its high-water mark a warp raises prune_req and every
+// warp joins a block-wide sort at its next iteration boundary.
+struct CandCtl {
+    unsigned long long thrkey;  // kprime-th best key so far (kKeyMax until kprime keys are held)
+    float thr_f;                // its value part, for the cheap per-row test
+    int cnt;                    // keys in the store
+    int prune_req;
+    int overflow;               // store overran its capacity (cannot happen by construction; checked)
+    int done_warps;
+    int all_done;
+    int is_last;
+    double nq;                  // canonical sum q_j^2 (cosine rerank)
+    float u_val;                // value part of the kprime-th approximate key (guard)
+    int ncand;
+};
+
+__device__ __forceinline__ void cand_reset(CandCtl *ctl) {
+    ctl->thrkey = kKeyMax;
+    ctl->thr_f = __int_as_float(0x7f800000);
+    ctl->cnt = 0;
+    ctl->prune_req = 0;
+    ctl->done_warps = 0;
+    ctl->all_done = 0;
+}
+
+__device__ __forceinline__ void cand_append(CandCtl *ctl, unsigned long long *buf, unsigned long long key, int cap,
+                                            int water) {
+    if (key < *(volatile unsigned long long *)&ctl->thrkey) {
+        const int pos = atomicAdd(&ctl->cnt, 1);
+        if (pos < cap) buf[pos] = key;
+        else ctl->overflow = 1;
+        if (pos >= water) *(volatile int *)&ctl->prune_req = 1;
+    }
+}
+
+// Block-wide bitonic sort of P (power of two) keys in shared memory, ascending.  Caller has synced.
+__device__ __forceinline__ void block_bitonic(unsigned long long *a, int P, int tid) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < (P >> 1); i += kScanThreads) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int hi = lo | j;
+                const bool asc = (lo & k) == 0;
+                const unsigned long long x = a[lo], y = a[hi];
+                if ((x > y) == asc) { a[lo] = y; a[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Keep the best kprime keys (sorted ascending in buf[0..cnt)), refresh the threshold.  All threads of
+// the CTA call it right after a __syncthreads().
+__device__ __forceinline__ void block_prune(CandCtl *ctl, unsigned long long *buf, int kprime, int cap, int tid) {
+    int cnt = ctl->cnt;
+    if (cnt > cap) cnt = cap;
+    int P = 32;
+    while (P < cnt) P <<= 1;
+    for (int i = cnt + tid; i < P; i += kScanThreads) buf[i] = kKeyMax;
+    __syncthreads();
+    block_bitonic(buf, P, tid);
+    if (tid == 0) {
+        const int nc = cnt < kprime ? cnt : kprime;
+        ctl->cnt = nc;
+        if (nc == kprime) {
+            ctl->thrkey = buf[kprime - 1];
+            ctl->thr_f = ord2f((uint32_t)(buf[kprime - 1] >> 32));
+        } else {
+            ctl->thrkey = kKeyMax;
+            ctl->thr_f = __int_as_float(0x7f800000);
+        }
+        ctl->prune_req = 0;
+        ctl->all_done = (ctl->done_warps == kScanWarps);
+    }
+    __syncthreads();
+}
+
+// ---- canonical f64 sums (bit-identical to oracle/knn_oracle.c by construction of the order) --------
+// partial[j mod 128] accumulates element j with fma; lane l owns partials 4l..4l+3; the adjacent-pair
+// tree is (p0+p1)+(p2+p3) inside the lane, then lanes xor 1,2,4,8,16.
+template <bool COS>
+__device__ __forceinline__ void canon_accum(const float4 x, const float4 q, double (&p)[4]) {
+    if constexpr (COS) {
+        p[0] = fma((double)x.x, (double)q.x, p[0]);
+        p[1] = fma((double)x.y, (double)q.y, p[1]);
+        p[2] = fma((double)x.z, (double)q.z, p[2]);
+        p[3] = fma((double)x.w, (double)q.w, p[3]);
+    } else {
+        const double a = __dsub_rn((double)x.x, (double)q.x), b = __dsub_rn((double)x.y, (double)q.y);
+        const double c = __dsub_rn((double)x.z, (double)q.z), d = __dsub_rn((double)x.w, (double)q.w);
+        p[0] = fma(a, a, p[0]);
+        p[1] = fma(b, b, p[1]);
+        p[2] = fma(c, c, p[2]);
+        p[3] = fma(d, d, p[3]);
+    }
+}
+__device__ __forceinline__ double canon_lane_fold(const double (&p)[4]) {
+    return __dadd_rn(__dadd_rn(p[0], p[1]), __dadd_rn(p[2], p[3]));
+}
+__device__ __forceinline__ double canon_warp_tree(double v) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) v = __dadd_rn(v, __shfl_xor_sync(kFull, v, off));
+    return v;
+}
+
+// One warp computes the canonical sum over a row of `ld4` float4 chunks.  MODE 0: SUM (x-q)^2,
+// MODE 1: SUM x*q, MODE 2: SUM x*x.
+template <int MODE>
+__device__ __forceinline__ double canon_row_sum(const float4 *x, const float4 *q, int ld4, int lane) {
+    double p[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = lane; c < ld4; c += 32) {
+        const float4 xv = __ldg(x + c);
+        if constexpr (MODE == 0) canon_accum<false>(xv, __ldg(q + c), p);
+        else if constexpr (MODE == 1) canon_accum<true>(xv, __ldg(q + c), p);
+        else canon_accum<true>(xv, xv, p);
+    }
+    return canon_warp_tree(canon_lane_fold(p));
+}
+
+__device__ __forceinline__ float canon_l2_dist(double sq) { return __double2float_rn(__dsqrt_rn(sq)) + 0.0f; }
+__device__ __forceinline__ float canon_cos_dist(double dot, double nx, double nq) {
+    if (nx == 0.0 || nq == 0.0) return 1.0f;
+    const double den = __dmul_rn(__dsqrt_rn(nx), __dsqrt_rn(nq));
+    return __double2float_rn(__dsub_rn(1.0, __ddiv_rn(dot, den))) + 0.0f;
+}
+
+}  // namespace vrod

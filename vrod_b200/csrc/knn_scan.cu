@@ -1,0 +1,677 @@
+// knn_scan.cu -- single-query exact top-k scan kernels for sm_100a.
+//
+// The work vRod's SearchCommand::execute would do (reference src/command/types.rs:114-119, empty
+// body) over the rows of a Database collection (reference src/database/mod.rs:6-10, TODO).
+//
+//   fast_scan_kernel   HBM-bound pass over the shard's f32 rows: per-row f32 distance surrogate
+//                      (L2: SUM (x-q)^2, cosine: -dot * 1/||x|| with the precomputed inverse norm),
+//                      multi-row butterfly reduction, per-CTA candidate store (threshold filter +
+//                      shared-memory bitonic prune), last-CTA merge of all CTA lists, exact f64
+//                      rerank of the kprime survivors in the canonical order and a guard that
+//                      PROVES no dropped row can belong to the top k (else status = 1).
+//   exact_scan_kernel  the same scan with every row evaluated in canonical f64; answers the
+//                      queries whose guard failed (and path = 2).
+//   row_norms / fill_synthetic / pad_queries / merge_hits  small helpers around them.
+#include "knn_device.cuh"
+#include "knn_scan.cuh"
+
+#include <math.h>
+
+namespace vrod {
+
+// -------------------------------------------------------------------------------------------------
+struct ScanParams {
+    const float4 *rows4;
+    const float *inv_norm;
+    const float4 *q4;
+    uint32_t n, ld4;
+    unsigned long long id_base;
+    uint32_t k;
+    int kprime, cap, water;
+    uint32_t iters;
+    unsigned long long *blk_cand;
+    unsigned int *ticket;
+    int *status;
+    unsigned long long *counters;
+    const int *only_if;
+    Hit *out;
+    double eps;
+};
+
+constexpr int kCtlBytes = 128;
+static_assert(sizeof(CandCtl) <= kCtlBytes, "CandCtl must fit its slot");
+
+// Finish protocol of a scanning CTA + cross-CTA merge by the last CTA to finish.
+// Returns true in the last CTA, with the grid's best <= kprime keys sorted in buf[0..ctl->cnt).
+__device__ __forceinline__ bool finish_and_merge(CandCtl *ctl, unsigned long long *buf, const ScanParams &p, int tid) {
+    const int lane = tid & 31;
+    if (lane == 0) atomicAdd(&ctl->done_warps, 1);
+    // Warps that are done wait here; a straggler joins either to prune or because it is done too.
+    while (true) {
+        __syncthreads();
+        block_prune(ctl, buf, p.kprime, p.cap, tid);
+        if (ctl->all_done) break;
+    }
+    const int cnt = ctl->cnt;
+    unsigned long long *mine = p.blk_cand + (size_t)blockIdx.x * p.kprime;
+    for (int i = tid; i < p.kprime; i += kScanThreads) __stcg(mine + i, i < cnt ? buf[i] : kKeyMax);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(p.ticket, 1u);
+        ctl->is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!ctl->is_last) return false;
+    __threadfence();
+
+    // ---- last CTA: merge gridDim.x sorted lists, walking them by depth ----
+    if (tid == 0) {
+        const int ov = ctl->overflow;
+        cand_reset(ctl);
+        ctl->overflow = ov;
+        *p.ticket = 0;  // self-reset for the next launch
+    }
+    __syncthreads();
+    const int nlists = gridDim.x;
+    const int water = p.cap - nlists;
+    unsigned int active = 0xffffffffu;  // bit li <-> list tid + li*kScanThreads (nlists <= 32*kScanThreads)
+    for (int depth = 0; depth < p.kprime; ++depth) {
+        int any = 0;
+        int li = 0;
+        for (int b = tid; b < nlists; b += kScanThreads, ++li) {
+            if (active & (1u << li)) {
+                const unsigned long long key = __ldcg(p.blk_cand + (size_t)b * p.kprime + depth);
+                if (key < *(volatile unsigned long long *)&ctl->thrkey) {
+                    const int pos = atomicAdd(&ctl->cnt, 1);
+                    if (pos < p.cap) buf[pos] = key;
+                    else ctl->overflow = 1;
+                    any = 1;
+                } else {
+                    active &= ~(1u << li);
+                }
+            }
+        }
+        if (!__syncthreads_or(any)) break;
+        if (ctl->cnt > water || ctl->cnt > p.kprime * 2) {  // uniform: cnt is stable after the barrier
+            block_prune(ctl, buf, p.kprime, p.cap, tid);
+        }
+    }
+    __syncthreads();
+    block_prune(ctl, buf, p.kprime, p.cap, tid);
+    return true;
+}
+
+// Write the final k hits from sorted exact keys in buf[0..ncand).
+__device__ __forceinline__ void write_hits(const unsigned long long *buf, int ncand, const ScanParams &p, int tid) {
+    for (int i = tid; i < (int)p.k; i += kScanThreads) {
+        Hit h;
+        if (i < ncand) {
+            h.id = p.id_base + (uint32_t)buf[i];
+            h.dist = ord2f((uint32_t)(buf[i] >> 32));
+        } else {
+            h.id = kKeyMax;
+            h.dist = __int_as_float(0x7f800000);
+        }
+        h.pad = 0;
+        p.out[i] = h;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Fast scan.  LPR lanes cooperate on one row (32/LPR rows per 128-bit load instruction), CH float4
+// chunks per lane per row (CH == 0: run-time chunk loop), RB row slots in flight per iteration.
+// -------------------------------------------------------------------------------------------------
+template <bool COS>
+__device__ __forceinline__ float chunk_acc(const float4 x, const float4 q, float acc) {
+    if constexpr (COS) {
+        acc = fmaf(x.x, q.x, acc);
+        acc = fmaf(x.y, q.y, acc);
+        acc = fmaf(x.z, q.z, acc);
+        acc = fmaf(x.w, q.w, acc);
+    } else {
+        const float a = x.x - q.x, b = x.y - q.y, c = x.z - q.z, d = x.w - q.w;
+        acc = fmaf(a, a, acc);
+        acc = fmaf(b, b, acc);
+        acc = fmaf(c, c, acc);
+        acc = fmaf(d, d, acc);
+    }
+    return acc;
+}
+
+template <int LPR, int CH, int RB, bool COS>
+__global__ void __launch_bounds__(kScanThreads, 2) fast_scan_kernel(const ScanParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    CandCtl *ctl = reinterpret_cast<CandCtl *>(smem);
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem + kCtlBytes);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int RPL = 32 / LPR;    // rows per load instruction
+    constexpr int ROWS = RB * RPL;   // rows per warp iteration
+    constexpr int REP = LPR / RB;    // lanes holding the same row total after the reduction
+    constexpr int CHR = CH > 0 ? CH : 1;
+    const int sub = lane / LPR, ls = lane % LPR;
+    const int rsel = ls / REP;
+    const bool owner = (ls % REP) == 0;
+
+    if (tid == 0) {
+        cand_reset(ctl);
+        ctl->overflow = 0;
+    }
+    float4 qv[CHR];
+    if constexpr (CH > 0) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) qv[c] = __ldg(p.q4 + ls + LPR * c);
+    }
+    __syncthreads();
+
+    const int water = p.water;
+    const uint32_t total_warps = gridDim.x * kScanWarps;
+    const uint32_t gw = blockIdx.x * kScanWarps + warp;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (uint32_t it = 0; it < p.iters; ++it) {
+        if (*(volatile int *)&ctl->prune_req) {
+            __syncthreads();
+            block_prune(ctl, buf, p.kprime, p.cap, tid);
+        }
+        const unsigned long long row0 = ((unsigned long long)it * total_warps + gw) * ROWS;
+        const unsigned long long myrow = row0 + (unsigned)(rsel * RPL + sub);
+        const bool myok = myrow < p.n;
+        float part[RB];
+        if constexpr (CH > 0) {
+            float4 v[RB][CHR];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const unsigned long long row = row0 + (unsigned)(r * RPL + sub);
+                const bool ok = row < p.n;
+                const float4 *src = p.rows4 + row * p.ld4 + ls;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) v[r][c] = ok ? ldg_stream(src + LPR * c) : (COS ? zero4 : qv[c]);
+            }
+            float inv = 1.0f;
+            if (COS && myok) inv = __ldg(p.inv_norm + myrow);
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) acc = chunk_acc<COS>(v[r][c], qv[c], acc);
+                part[r] = acc;
+            }
+            int slot = 0;
+            float tot = RowsReduce<float, RB, LPR / 2, LPR, false>::run(part, lane, slot, 0);
+            if constexpr (COS) tot = -tot * inv;
+            const float thr = *(volatile float *)&ctl->thr_f;
+            if (myok && owner && !(tot > thr)) cand_append(ctl, buf, make_key(tot, (uint32_t)myrow), p.cap, water);
+        } else {
+            // generic dimension: run-time chunk loop, q from L1
+            float inv = 1.0f;
+            if (COS && myok) inv = __ldg(p.inv_norm + myrow);
+#pragma unroll
+            for (int r = 0; r < RB; ++r) part[r] = 0.f;
+            for (uint32_t c = ls; c < p.ld4; c += 4 * LPR) {
+                float4 v[RB][4];
+                float4 q[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t cc = c + u * LPR;
+                    q[u] = cc < p.ld4 ? __ldg(p.q4 + cc) : zero4;
+                }
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const unsigned long long row = row0 + (unsigned)(r * RPL + sub);
+                    const bool ok = row < p.n;
+                    const float4 *src = p.rows4 + row * p.ld4;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t cc = c + u * LPR;
+                        v[r][u] = (ok && cc < p.ld4) ? ldg_stream(src + cc) : (COS ? zero4 : q[u]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < RB; ++r)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) part[r] = chunk_acc<COS>(v[r][u], q[u], part[r]);
+            }
+            int slot = 0;
+            float tot = RowsReduce<float, RB, LPR / 2, LPR, false>::run(part, lane, slot, 0);
+            if constexpr (COS) tot = -tot * inv;
+            const float thr = *(volatile float *)&ctl->thr_f;
+            if (myok && owner && !(tot > thr)) cand_append(ctl, buf, make_key(tot, (uint32_t)myrow), p.cap, water);
+        }
+    }
+
+    if (!finish_and_merge(ctl, buf, p, tid)) return;
+
+    // ---- last CTA: exact rerank of the survivors in canonical f64, guard, output ----
+    const int ncand = ctl->cnt;
+    if (tid == 0) {
+        ctl->ncand = ncand;
+        ctl->u_val = ncand > 0 ? ord2f((uint32_t)(buf[ncand - 1] >> 32)) : 0.f;
+    }
+    if (COS && warp == 0) {
+        const double nq = canon_row_sum<2>(p.q4, p.q4, (int)p.ld4, lane);
+        if (lane == 0) ctl->nq = nq;
+    }
+    __syncthreads();
+    for (int c = warp; c < ncand; c += kScanWarps) {
+        const uint32_t row = (uint32_t)buf[c];
+        const float4 *x = p.rows4 + (size_t)row * p.ld4;
+        float dist;
+        if constexpr (COS) {
+            const double nx = canon_row_sum<2>(x, x, (int)p.ld4, lane);
+            const double dot = canon_row_sum<1>(x, p.q4, (int)p.ld4, lane);
+            dist = canon_cos_dist(dot, nx, ctl->nq);
+        } else {
+            dist = canon_l2_dist(canon_row_sum<0>(x, p.q4, (int)p.ld4, lane));
+        }
+        __syncwarp();
+        if (lane == 0) buf[c] = make_key(dist, row);
+    }
+    __syncthreads();
+    {
+        int P = 32;
+        while (P < ncand) P <<= 1;
+        for (int i = ncand + tid; i < P; i += kScanThreads) buf[i] = kKeyMax;
+        __syncthreads();
+        block_bitonic(buf, P, tid);
+    }
+    write_hits(buf, ncand, p, tid);
+    if (tid == 0) {
+        int bad = ctl->overflow;
+        if (p.n > (uint32_t)ncand) {
+            // rows were dropped: every dropped row has surrogate >= u_val.  Bound its exact distance
+            // from below and require it to be strictly above the k-th exact distance.
+            const int kk = (int)p.k < ncand ? (int)p.k : ncand;
+            const float T = ord2f((uint32_t)(buf[kk - 1] >> 32));
+            double u = (double)ctl->u_val;
+            if (!(u == u)) bad = 1;  // NaN surrogate
+            if (u > 3.4028234663852886e38) u = 3.4028234663852886e38;
+            float lb;
+            if constexpr (COS) {
+                const double nqs = __dsqrt_rn(ctl->nq);
+                if (nqs > 0.0) {
+                    const double d = 1.0 + u / nqs - p.eps;
+                    lb = __double2float_rd(d - 4.0e-16 * (1.0 + fabs(u / nqs)));
+                } else {
+                    lb = -1.0f;  // zero query: every distance is 1, the scan cannot rank; rescan exactly
+                }
+            } else {
+                double s = u * (1.0 - p.eps) - (double)p.ld4 * 4.0 * 1.0e-44;
+                if (s < 0.0) s = 0.0;
+                lb = __double2float_rd(__dsqrt_rd(s));
+            }
+            if (!(lb > T)) bad = 1;
+            if (kk < (int)p.k) bad = 1;
+        }
+        *p.status = bad ? 1 : 0;
+        if (bad && p.counters) atomicAdd(p.counters, 1ull);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Exact scan: every row in canonical f64 (warp per row, RB rows in flight).
+// -------------------------------------------------------------------------------------------------
+template <int RB, bool COS>
+__global__ void __launch_bounds__(kScanThreads, 2) exact_scan_kernel(const ScanParams p) {
+    if (p.only_if != nullptr && *p.only_if == 0) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    CandCtl *ctl = reinterpret_cast<CandCtl *>(smem);
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem + kCtlBytes);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        cand_reset(ctl);
+        ctl->overflow = 0;
+    }
+    if (COS && warp == 0) {
+        const double nq = canon_row_sum<2>(p.q4, p.q4, (int)p.ld4, lane);
+        if (lane == 0) ctl->nq = nq;
+    }
+    __syncthreads();
+    const double nq = COS ? ctl->nq : 0.0;
+
+    // slot owned after the ascending butterfly: bit-reversed low lane bits
+    int rsel = 0;
+    {
+        int n = RB, off = 1;
+        while (n > 1) {
+            if (lane & off) rsel += n / 2;
+            n >>= 1;
+            off <<= 1;
+        }
+    }
+    constexpr int REPMASK = ~(RB - 1) & 31;  // lanes with these bits clear own a distinct slot copy
+    const bool owner = (lane & REPMASK) == 0;
+
+    const int water = p.water;
+    const uint32_t total_warps = gridDim.x * kScanWarps;
+    const uint32_t gw = blockIdx.x * kScanWarps + warp;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (uint32_t it = 0; it < p.iters; ++it) {
+        if (*(volatile int *)&ctl->prune_req) {
+            __syncthreads();
+            block_prune(ctl, buf, p.kprime, p.cap, tid);
+        }
+        const unsigned long long row0 = ((unsigned long long)it * total_warps + gw) * RB;
+        double acc[RB][4], accx[COS ? RB : 1][4];
+#pragma unroll
+        for (int r = 0; r < RB; ++r)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[r][e] = 0.0;
+                if constexpr (COS) accx[r][e] = 0.0;
+            }
+        for (uint32_t c = lane; c < p.ld4; c += 32) {
+            const float4 q = __ldg(p.q4 + c);
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const unsigned long long row = row0 + r;
+                const float4 x = row < p.n ? ldg_stream(p.rows4 + row * p.ld4 + c) : (COS ? zero4 : q);
+                canon_accum<COS>(x, q, acc[r]);
+                if constexpr (COS) canon_accum<true>(x, x, accx[r]);
+            }
+        }
+        double part[RB], partx[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            part[r] = canon_lane_fold(acc[r]);
+            if constexpr (COS) partx[r] = canon_lane_fold(accx[r]);
+        }
+        int slot = 0;
+        const double tot = RowsReduce<double, RB, 1, 32, true>::run(part, lane, slot, 0);
+        float dist;
+        if constexpr (COS) {
+            int slot2 = 0;
+            const double nx = RowsReduce<double, RB, 1, 32, true>::run(partx, lane, slot2, 0);
+            dist = canon_cos_dist(tot, nx, nq);
+        } else {
+            dist = canon_l2_dist(tot);
+        }
+        const unsigned long long myrow = row0 + (unsigned)rsel;
+        const float thr = *(volatile float *)&ctl->thr_f;
+        if (myrow < p.n && owner && !(dist > thr)) cand_append(ctl, buf, make_key(dist, (uint32_t)myrow), p.cap, water);
+    }
+
+    if (!finish_and_merge(ctl, buf, p, tid)) return;
+    write_hits(buf, ctl->cnt, p, tid);
+}
+
+// -------------------------------------------------------------------------------------------------
+// helpers
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_norms_kernel(const float4 *rows4, uint32_t row0, uint32_t n, uint32_t ld4,
+                                                        float *inv_norm, float *sq_norm, int *flags) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = w; r < n; r += nw) {
+        const float4 *x = rows4 + (size_t)(row0 + r) * ld4;
+        double p[4] = {0.0, 0.0, 0.0, 0.0};
+        int bad = 0;
+        for (uint32_t c = lane; c < ld4; c += 32) {
+            const float4 v = ldg_stream(x + c);
+            const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+            if (!(m <= 3.4028234663852886e38f) || v.x != v.x || v.y != v.y || v.z != v.z || v.w != v.w) bad |= 1;
+            if (m > 0x1p40f) bad |= 2;
+            canon_accum<true>(v, v, p);
+        }
+        const double nx = canon_warp_tree(canon_lane_fold(p));
+        if (nx > 0.0 && (nx < 0x1p-80 || nx > 0x1p100)) bad |= 2;
+        bad = __reduce_or_sync(kFull, bad);
+        if (lane == 0) {
+            inv_norm[row0 + r] = nx > 0.0 ? __double2float_rn(1.0 / sqrt(nx)) : 0.f;
+            sq_norm[row0 + r] = __double2float_rn(nx);
+            if (bad) atomicOr(flags, bad);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_synthetic_kernel(float4 *rows4, uint32_t row0, uint32_t n, uint32_t dim,
+                                                             uint32_t ld4, unsigned long long g0, uint32_t k0,
+                                                             uint32_t k1) {
+    const unsigned long long total = (unsigned long long)n * ld4;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const uint32_t r = (uint32_t)(t / ld4), c = (uint32_t)(t % ld4);
+        const unsigned long long e = (g0 + r) * dim + 4ull * c;  // first element of this float4
+        float v[4];
+        if ((dim & 3u) == 0) {
+            const uint4 w = philox4x32_10((uint32_t)(e >> 2), (uint32_t)(e >> 34), k0, k1);
+            v[0] = word_to_unit(w.x); v[1] = word_to_unit(w.y); v[2] = word_to_unit(w.z); v[3] = word_to_unit(w.w);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (4 * c + j < dim) {
+                    const unsigned long long ee = e + j;
+                    const uint4 w = philox4x32_10((uint32_t)(ee >> 2), (uint32_t)(ee >> 34), k0, k1);
+                    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+                    v[j] = word_to_unit(ws[ee & 3]);
+                } else {
+                    v[j] = 0.f;
+                }
+            }
+        }
+        rows4[(size_t)(row0 + r) * ld4 + c] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__global__ void pad_queries_kernel(const float *src, float *dst, uint32_t b, uint32_t dim, uint32_t ld) {
+    const uint32_t total = b * ld;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const uint32_t r = t / ld, c = t % ld;
+        dst[t] = c < dim ? src[(size_t)r * dim + c] : 0.f;
+    }
+}
+
+// One CTA per query: sort g*k (dist, shard, slot) keys; shards hold ascending id ranges and each list
+// is already (dist, id)-sorted, so (dist, shard, slot) order IS (dist, id) order.
+__global__ void __launch_bounds__(kScanThreads) merge_hits_kernel(const Hit *lists, uint32_t g, uint32_t b, uint32_t k,
+                                                                  unsigned long long *out_ids, float *out_dist) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem);
+    const int tid = threadIdx.x;
+    const uint32_t qi = blockIdx.x;
+    const int total = (int)(g * k);
+    int P = 32;
+    while (P < total) P <<= 1;
+    for (int i = tid; i < P; i += kScanThreads) {
+        unsigned long long key = kKeyMax;
+        if (i < total) {
+            const uint32_t s = i / k, j = i % k;
+            const Hit h = lists[((size_t)s * b + qi) * k + j];
+            if (h.id != kKeyMax) key = ((unsigned long long)f2ord(h.dist) << 32) | (s << 16) | j;
+        }
+        buf[i] = key;
+    }
+    __syncthreads();
+    block_bitonic(buf, P, tid);
+    for (int i = tid; i < (int)k; i += kScanThreads) {
+        const unsigned long long key = buf[i];
+        unsigned long long id = kKeyMax;
+        float dist = __int_as_float(0x7f800000);
+        if (key != kKeyMax) {
+            const uint32_t s = ((uint32_t)key >> 16) & 0xffffu, j = (uint32_t)key & 0xffffu;
+            const Hit h = lists[((size_t)s * b + qi) * k + j];
+            id = h.id;
+            dist = h.dist;
+        }
+        out_ids[(size_t)qi * k + i] = id;
+        out_dist[(size_t)qi * k + i] = dist;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+int scan_sm_count(int device) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    return sms;
+}
+
+namespace {
+
+struct Variant {
+    uint32_t ld4;
+    int rows;  // rows per warp iteration
+    void (*l2)(const ScanParams);
+    void (*cs)(const ScanParams);
+};
+
+#define VROD_VARIANT(LD4, LPR, CH, RB) \
+    { LD4, RB *(32 / LPR), fast_scan_kernel<LPR, CH, RB, false>, fast_scan_kernel<LPR, CH, RB, true> }
+
+const Variant kVariants[] = {
+    VROD_VARIANT(8, 8, 1, 8),      // d = 32
+    VROD_VARIANT(16, 16, 1, 8),    // d = 64
+    VROD_VARIANT(32, 32, 1, 8),    // d = 128
+    VROD_VARIANT(64, 32, 2, 4),    // d = 256
+    VROD_VARIANT(96, 32, 3, 4),    // d = 384
+    VROD_VARIANT(128, 32, 4, 2),   // d = 512
+    VROD_VARIANT(192, 32, 6, 2),   // d = 768
+    VROD_VARIANT(256, 32, 8, 1),   // d = 1024
+    VROD_VARIANT(384, 32, 12, 1),  // d = 1536
+};
+const Variant kGeneric = VROD_VARIANT(0, 32, 0, 2);
+
+const Variant &pick_variant(uint32_t ld4) {
+    for (const Variant &v : kVariants)
+        if (v.ld4 == ld4) return v;
+    return kGeneric;
+}
+
+constexpr int kExactRBL2 = 4, kExactRBCos = 2;
+
+int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+ScanPlan make_scan_plan(const ShardView &s, uint32_t k, int sm_count, bool exact) {
+    ScanPlan pl{};
+    const uint32_t ld4 = s.ld / 4;
+    int rows;
+    const void *fn;
+    if (exact) {
+        rows = s.metric ? kExactRBCos : kExactRBL2;
+        fn = s.metric ? (const void *)exact_scan_kernel<kExactRBCos, true> : (const void *)exact_scan_kernel<kExactRBL2, false>;
+        pl.kprime = (int)k;
+    } else {
+        const Variant &v = pick_variant(ld4);
+        rows = v.rows;
+        fn = s.metric ? (const void *)v.cs : (const void *)v.l2;
+        pl.kprime = next_pow2((int)k + 16);
+        if (pl.kprime < 32) pl.kprime = 32;
+    }
+    // capacity first (it sets the shared memory, which sets occupancy), grid second
+    int max_grid = sm_count * 8;
+    pl.cap = next_pow2(pl.kprime + max_grid + 64);
+    if (pl.cap < 2 * pl.kprime) pl.cap = 2 * pl.kprime;
+    if (pl.cap < 512) pl.cap = 512;
+    pl.smem = kCtlBytes + (size_t)pl.cap * sizeof(unsigned long long);
+    int bps = 1;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, kScanThreads, pl.smem) != cudaSuccess || bps < 1) bps = 1;
+    if (bps > 8) bps = 8;
+    long long want = ((long long)s.n + (long long)rows * kScanWarps - 1) / ((long long)rows * kScanWarps);
+    if (want < 1) want = 1;
+    long long grid = (long long)sm_count * bps;
+    if (grid > want) grid = want;
+    pl.grid = (int)grid;
+    // error bound of the f32 pass (DESIGN.md "Guard"): each term carries <= 2 roundings, the per-lane
+    // chain is (ld/LPR) fmas long and the butterfly adds log2(LPR) more; 1.5x safety.
+    const double u = ldexp(1.0, -24);
+    const double chain = (double)((s.ld + 31) / 32 * 4 + 12);
+    pl.eps = 1.5 * chain * u + (double)s.ld * ldexp(1.0, -50);  // + slack for the f64 sums' own rounding
+    if (s.metric) pl.eps += 4.0 * u;
+    return pl;
+}
+
+size_t scan_cand_bytes(int sm_count) { return (size_t)sm_count * 8 * 2048 * sizeof(unsigned long long); }
+
+static ScanParams make_params(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan, const ScanScratch &scr,
+                              int rows_per_iter) {
+    ScanParams p{};
+    p.rows4 = reinterpret_cast<const float4 *>(s.rows);
+    p.inv_norm = s.inv_norm;
+    p.q4 = reinterpret_cast<const float4 *>(q);
+    p.n = s.n;
+    p.ld4 = s.ld / 4;
+    p.id_base = s.id_base;
+    p.k = k;
+    p.kprime = plan.kprime;
+    p.cap = plan.cap;
+    // prune trigger of the scanning phase: early enough that the threshold starts filtering after a
+    // few hundred rows, late enough that a CTA sorts only a handful of times per query
+    p.water = 4 * plan.kprime > 256 ? 4 * plan.kprime : 256;
+    if (p.water > plan.cap - kScanWarps * 32) p.water = plan.cap - kScanWarps * 32;
+    const unsigned long long batches = ((unsigned long long)s.n + rows_per_iter - 1) / rows_per_iter;
+    const unsigned long long tw = (unsigned long long)plan.grid * kScanWarps;
+    p.iters = (uint32_t)((batches + tw - 1) / tw);
+    p.blk_cand = scr.blk_cand;
+    p.ticket = scr.ticket;
+    p.counters = scr.counters;
+    p.eps = plan.eps;
+    return p;
+}
+
+cudaError_t launch_fast_scan(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan, const ScanScratch &scr,
+                             int *status, Hit *out, cudaStream_t st) {
+    const Variant &v = pick_variant(s.ld / 4);
+    ScanParams p = make_params(s, q, k, plan, scr, v.rows);
+    p.status = status;
+    p.out = out;
+    (s.metric ? v.cs : v.l2)<<<plan.grid, kScanThreads, plan.smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exact_scan(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan, const ScanScratch &scr,
+                              const int *only_if_flag, Hit *out, cudaStream_t st) {
+    ScanParams p = make_params(s, q, k, plan, scr, s.metric ? kExactRBCos : kExactRBL2);
+    p.only_if = only_if_flag;
+    p.out = out;
+    if (s.metric) exact_scan_kernel<kExactRBCos, true><<<plan.grid, kScanThreads, plan.smem, st>>>(p);
+    else exact_scan_kernel<kExactRBL2, false><<<plan.grid, kScanThreads, plan.smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_row_norms(const float *rows, uint32_t row0, uint32_t n, uint32_t ld, float *inv_norm, float *sq_norm,
+                             int *flags, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    long long blocks = ((long long)n + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    row_norms_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(rows), row0, n, ld / 4, inv_norm,
+                                                  sq_norm, flags);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_synthetic(float *rows, uint32_t row0, uint32_t n, uint32_t dim, uint32_t ld, uint64_t g0,
+                                  uint64_t seed, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    fill_synthetic_kernel<<<148 * 16, 256, 0, st>>>(reinterpret_cast<float4 *>(rows), row0, n, dim, ld / 4, g0,
+                                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pad_queries(const float *src, float *dst, uint32_t b, uint32_t dim, uint32_t ld, cudaStream_t st) {
+    if (b == 0) return cudaSuccess;
+    pad_queries_kernel<<<64, 256, 0, st>>>(src, dst, b, dim, ld);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_hits(const Hit *lists, uint32_t g, uint32_t b, uint32_t k, unsigned long long *out_ids,
+                              float *out_dist, cudaStream_t st) {
+    if (b == 0) return cudaSuccess;
+    size_t smem = (size_t)next_pow2((int)(g * k) < 32 ? 32 : (int)(g * k)) * sizeof(unsigned long long);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(merge_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    merge_hits_kernel<<<b, kScanThreads, smem, st>>>(lists, g, b, k, out_ids, out_dist);
+    return cudaGetLastError();
+}
+
+}  // namespace vrod

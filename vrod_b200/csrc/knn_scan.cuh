@@ -1,0 +1,65 @@
+// knn_scan.cuh -- host-visible launch interface of the scan kernels (knn_scan.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vrod {
+
+struct ShardView {
+    const float *rows;       // n x ld f32, row-major, rows zero-padded from dim to ld (ld % 4 == 0)
+    const float *inv_norm;   // n f32: 1/||x|| (0 for a zero row)               [cosine fast scan]
+    const float *sq_norm;    // n f32: ||x||^2                                  [batched L2 path]
+    uint32_t n;              // local rows (< 2^32)
+    uint32_t dim, ld;
+    int metric;              // 0 Euclidean, 1 cosine
+    uint64_t id_base;        // global id of local row 0
+};
+
+// Per-launch scratch owned by the collection (sized by scan_scratch_bytes()).
+struct ScanScratch {
+    unsigned long long *blk_cand;  // [max_grid][kprime] per-CTA best keys
+    unsigned int *ticket;          // self-resetting last-CTA ticket
+    int *status;                   // [b] 0 = answered exactly, 1 = guard failed -> exact rescan needed
+    unsigned long long *counters;  // [0] += 1 per query whose guard failed
+};
+
+struct ScanPlan {
+    int grid;        // CTAs
+    int kprime;      // candidates kept by the f32 scan (>= k + 16, power of two)
+    int cap;         // candidate store capacity (keys) per CTA
+    size_t smem;     // dynamic shared memory per CTA
+    double eps;      // error bound of the f32 pass (relative for L2, absolute on cos-sim for cosine)
+};
+
+// Result entry exchanged between ranks: 16 bytes.
+struct Hit {
+    unsigned long long id;
+    float dist;
+    uint32_t pad;
+};
+
+int scan_sm_count(int device);
+ScanPlan make_scan_plan(const ShardView &s, uint32_t k, int sm_count, bool exact);
+size_t scan_cand_bytes(int sm_count);
+
+// f32 scan + exact rerank + guard of ONE query (q: ld floats, device).  Writes k hits to `out`.
+cudaError_t launch_fast_scan(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan,
+                             const ScanScratch &scr, int *status, Hit *out, cudaStream_t st);
+// exact f64 scan of ONE query; if only_if_flag != nullptr the grid returns at once unless *only_if_flag != 0.
+cudaError_t launch_exact_scan(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan,
+                              const ScanScratch &scr, const int *only_if_flag, Hit *out, cudaStream_t st);
+
+// rows [row0, row0+n) of the shard: inv_norm / sq_norm, and flags[0] |= 1 if a value is not finite,
+// |= 2 if a value or norm is outside the range the f32 scan's error bound covers.
+cudaError_t launch_row_norms(const float *rows, uint32_t row0, uint32_t n, uint32_t ld, float *inv_norm,
+                             float *sq_norm, int *flags, cudaStream_t st);
+// synthetic rows (global row index g0 + local) into rows[row0 ..]
+cudaError_t launch_fill_synthetic(float *rows, uint32_t row0, uint32_t n, uint32_t dim, uint32_t ld, uint64_t g0,
+                                  uint64_t seed, cudaStream_t st);
+// [b x dim] -> [b x ld] zero padded
+cudaError_t launch_pad_queries(const float *src, float *dst, uint32_t b, uint32_t dim, uint32_t ld, cudaStream_t st);
+// merge g lists of [b][k] hits (layout [g][b][k]) into ids/dist [b][k] by (dist, id)
+cudaError_t launch_merge_hits(const Hit *lists, uint32_t g, uint32_t b, uint32_t k, unsigned long long *out_ids,
+                              float *out_dist, cudaStream_t st);
+
+}  // namespace vrod

@@ -1,0 +1,611 @@
+// vrod_capi.cu -- the C ABI (include/vrod_knn.h): contexts, collections, SEARCH.
+//
+// Stands behind the reference's command bodies (all empty today): CreateCollectionCommand
+// (src/command/types.rs:14-19), InsertCommand / BulkInsertCommand (:62-67, :75-80), SearchCommand
+// (:114-119), and plays the part of the collections the reference's Database never got
+// (src/database/mod.rs:6-10).  No CPU fallback: every entry point needs the CUDA device.
+#include "../../include/vrod_knn.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "knn_batched.cuh"
+#include "knn_scan.cuh"
+
+using namespace vrod;
+
+// -------------------------------------------------------------------------------------------------
+// errors
+// -------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static vrod_status fail(vrod_status st, const std::string &msg) {
+    g_last_error = msg;
+    return st;
+}
+#define VROD_CUDA(expr)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(e__ == cudaErrorMemoryAllocation ? VROD_ENOMEM : VROD_ECUDA,                      \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                             \
+    } while (0)
+
+// -------------------------------------------------------------------------------------------------
+// NCCL, loaded on first use (a single-GPU context never touches it)
+// -------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static vrod_status nccl_load() {
+    if (g_nccl.lib) return VROD_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *lib = nullptr;
+    for (const char *n : names) {
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return fail(VROD_ENCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+    NcclApi a;
+    a.lib = lib;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(lib, "ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(lib, "ncclCommDestroy");
+    a.AllGather = (decltype(a.AllGather))dlsym(lib, "ncclAllGather");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.GetErrorString)
+        return fail(VROD_ENCCL, "libnccl.so.2 lacks a required symbol");
+    g_nccl = a;
+    return VROD_OK;
+}
+#define VROD_NCCL(expr)                                                                                   \
+    do {                                                                                                  \
+        ncclResult_t r__ = (expr);                                                                        \
+        if (r__ != ncclSuccess) return fail(VROD_ENCCL, std::string(#expr) + ": " + g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+// -------------------------------------------------------------------------------------------------
+// handles
+// -------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+struct vrod_ctx {
+    int device = 0, rank = 0, world = 1, sms = 0;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+    std::map<std::string, vrod_collection *> colls;
+    // scratch shared by every collection of the context
+    DevBuf blk_cand, small, q_pad, q_dev, hits_local, hits_all, out_ids, out_dist, batched;
+    PinBuf q_host, ids_host, dist_host;
+    unsigned long long *dev_counters = nullptr;  // [0] exact rescans (counted on the device)
+    vrod_stats stats{};
+};
+
+struct vrod_collection {
+    vrod_ctx *ctx = nullptr;
+    std::string name;
+    uint32_t dim = 0, ld = 0;
+    vrod_metric metric = VROD_EUCLIDEAN;
+    uint64_t capacity = 0;    // global
+    uint64_t shard_rows = 0;  // rows per rank (capacity split)
+    uint64_t id_base = 0;     // first global id of this rank's range
+    uint64_t count = 0;       // global rows inserted
+    uint64_t local = 0;       // rows held by this rank
+    float *rows = nullptr, *inv_norm = nullptr, *sq_norm = nullptr;
+    int *flags = nullptr;     // device: bit0 non-finite value seen, bit1 value outside the f32 scan's safe range
+    bool fast_ok = true;
+    int path = 0;
+};
+
+static int *ctx_ticket(vrod_ctx *c) { return reinterpret_cast<int *>(c->small.p); }
+static int *ctx_status(vrod_ctx *c) { return reinterpret_cast<int *>(c->small.p) + 64; }
+constexpr uint32_t kMaxBatch = 1u << 16;
+
+static vrod_status ctx_init(vrod_ctx *c, int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(VROD_ENOGPU, "no CUDA device: vrod_knn has no CPU path");
+    if (device < 0 || device >= ndev) return fail(VROD_EINVAL, "device ordinal out of range");
+    VROD_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VROD_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(VROD_ENOGPU, "vrod_knn is built for sm_100a (B200) only");
+    c->device = device;
+    c->sms = prop.multiProcessorCount;
+    VROD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    VROD_CUDA(c->blk_cand.ensure(scan_cand_bytes(c->sms)));
+    VROD_CUDA(c->small.ensure(256 + sizeof(int) * kMaxBatch + 64));
+    VROD_CUDA(cudaMemsetAsync(c->small.p, 0, c->small.bytes, c->stream));
+    VROD_CUDA(cudaMalloc(&c->dev_counters, 64));
+    VROD_CUDA(cudaMemsetAsync(c->dev_counters, 0, 64, c->stream));
+    VROD_CUDA(cudaStreamSynchronize(c->stream));
+    return VROD_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// context API
+// -------------------------------------------------------------------------------------------------
+extern "C" vrod_status vrod_ctx_create(int device, vrod_ctx **out) {
+    if (!out) return fail(VROD_EINVAL, "out is NULL");
+    *out = nullptr;
+    std::unique_ptr<vrod_ctx> c(new (std::nothrow) vrod_ctx());
+    if (!c) return fail(VROD_ENOMEM, "host allocation failed");
+    vrod_status st = ctx_init(c.get(), device);
+    if (st != VROD_OK) return st;
+    *out = c.release();
+    return VROD_OK;
+}
+
+extern "C" vrod_status vrod_comm_unique_id(void *out) {
+    if (!out) return fail(VROD_EINVAL, "out is NULL");
+    vrod_status st = nccl_load();
+    if (st != VROD_OK) return st;
+    static_assert(sizeof(ncclUniqueId) == VROD_COMM_ID_BYTES, "communicator id size");
+    ncclUniqueId id;
+    VROD_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out, &id, sizeof(id));
+    return VROD_OK;
+}
+
+extern "C" vrod_status vrod_ctx_create_sharded(int device, int rank, int world, const void *comm_id, vrod_ctx **out) {
+    if (!out) return fail(VROD_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (world < 1 || world > 256 || rank < 0 || rank >= world) return fail(VROD_EINVAL, "bad rank/world");
+    if (world > 1 && !comm_id) return fail(VROD_EINVAL, "comm_id is NULL");
+    std::unique_ptr<vrod_ctx> c(new (std::nothrow) vrod_ctx());
+    if (!c) return fail(VROD_ENOMEM, "host allocation failed");
+    vrod_status st = ctx_init(c.get(), device);
+    if (st != VROD_OK) return st;
+    c->rank = rank;
+    c->world = world;
+    if (world > 1) {
+        st = nccl_load();
+        if (st != VROD_OK) return st;
+        ncclUniqueId id;
+        memcpy(&id, comm_id, sizeof(id));
+        VROD_NCCL(g_nccl.CommInitRank(&c->comm, world, id, rank));
+    }
+    *out = c.release();
+    return VROD_OK;
+}
+
+static void collection_free(vrod_collection *c) {
+    if (!c) return;
+    cudaFree(c->rows);
+    cudaFree(c->inv_norm);
+    cudaFree(c->sq_norm);
+    cudaFree(c->flags);
+    delete c;
+}
+
+extern "C" void vrod_ctx_destroy(vrod_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->colls) collection_free(kv.second);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    DevBuf *dev[] = {&ctx->blk_cand, &ctx->small, &ctx->q_pad, &ctx->q_dev, &ctx->hits_local,
+                     &ctx->hits_all, &ctx->out_ids, &ctx->out_dist, &ctx->batched};
+    for (DevBuf *b : dev) b->release();
+    PinBuf *pin[] = {&ctx->q_host, &ctx->ids_host, &ctx->dist_host};
+    for (PinBuf *b : pin) b->release();
+    cudaFree(ctx->dev_counters);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" vrod_status vrod_ctx_synchronize(vrod_ctx *ctx) {
+    if (!ctx) return fail(VROD_EINVAL, "ctx is NULL");
+    VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VROD_OK;
+}
+extern "C" void *vrod_ctx_stream(vrod_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int vrod_ctx_rank(vrod_ctx *ctx) { return ctx ? ctx->rank : -1; }
+extern "C" int vrod_ctx_world(vrod_ctx *ctx) { return ctx ? ctx->world : -1; }
+
+extern "C" vrod_status vrod_ctx_stats(vrod_ctx *ctx, vrod_stats *out) {
+    if (!ctx || !out) return fail(VROD_EINVAL, "NULL argument");
+    VROD_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long dc[2] = {0, 0};
+    VROD_CUDA(cudaMemcpyAsync(dc, ctx->dev_counters, sizeof(dc), cudaMemcpyDeviceToHost, ctx->stream));
+    VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.exact_rescans = dc[0];
+    *out = ctx->stats;
+    return VROD_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// collections
+// -------------------------------------------------------------------------------------------------
+extern "C" vrod_status vrod_collection_create(vrod_ctx *ctx, const char *name, uint32_t dim, vrod_metric metric,
+                                              uint64_t capacity_rows, vrod_collection **out) {
+    if (out) *out = nullptr;
+    if (!ctx || !name || !*name) return fail(VROD_EINVAL, "ctx/name is NULL or empty");
+    if (dim == 0 || dim > (1u << 20)) return fail(VROD_EINVAL, "dim must be in [1, 2^20]");
+    if (metric != VROD_EUCLIDEAN && metric != VROD_COSINE) return fail(VROD_EINVAL, "unknown metric");
+    if (capacity_rows == 0) return fail(VROD_EINVAL, "capacity_rows must be > 0");
+    if (ctx->colls.count(name)) return fail(VROD_EEXISTS, std::string("collection '") + name + "' already exists");
+    VROD_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<vrod_collection> c(new (std::nothrow) vrod_collection());
+    if (!c) return fail(VROD_ENOMEM, "host allocation failed");
+    c->ctx = ctx;
+    c->name = name;
+    c->dim = dim;
+    c->ld = (dim + 3u) & ~3u;
+    c->metric = metric;
+    c->capacity = capacity_rows;
+    c->shard_rows = (capacity_rows + ctx->world - 1) / ctx->world;
+    if (c->shard_rows >= 0xFFFFFFFFull) return fail(VROD_EINVAL, "more than 2^32-1 rows per GPU");
+    c->id_base = c->shard_rows * (uint64_t)ctx->rank;
+    const size_t row_bytes = (size_t)c->shard_rows * c->ld * sizeof(float);
+    cudaError_t e = cudaMalloc(&c->rows, row_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&c->inv_norm, (size_t)c->shard_rows * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->sq_norm, (size_t)c->shard_rows * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->flags, 64);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->flags, 0, 64, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(c->rows); cudaFree(c->inv_norm); cudaFree(c->sq_norm); cudaFree(c->flags);
+        return fail(e == cudaErrorMemoryAllocation ? VROD_ENOMEM : VROD_ECUDA,
+                    std::string("allocating the collection: ") + cudaGetErrorString(e));
+    }
+    vrod_collection *raw = c.release();
+    ctx->colls[name] = raw;
+    if (out) *out = raw;
+    return VROD_OK;
+}
+
+extern "C" vrod_status vrod_collection_get(vrod_ctx *ctx, const char *name, vrod_collection **out) {
+    if (!ctx || !name || !out) return fail(VROD_EINVAL, "NULL argument");
+    auto it = ctx->colls.find(name);
+    if (it == ctx->colls.end()) {
+        *out = nullptr;
+        return fail(VROD_ENOTFOUND, std::string("no collection '") + name + "'");
+    }
+    *out = it->second;
+    return VROD_OK;
+}
+
+extern "C" vrod_status vrod_collection_drop(vrod_ctx *ctx, const char *name) {
+    if (!ctx || !name) return fail(VROD_EINVAL, "NULL argument");
+    auto it = ctx->colls.find(name);
+    if (it == ctx->colls.end()) return fail(VROD_ENOTFOUND, std::string("no collection '") + name + "'");
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    collection_free(it->second);
+    ctx->colls.erase(it);
+    return VROD_OK;
+}
+
+extern "C" vrod_status vrod_collection_list(vrod_ctx *ctx, char *buf, size_t cap, size_t *needed) {
+    if (!ctx) return fail(VROD_EINVAL, "ctx is NULL");
+    std::string s;
+    for (auto &kv : ctx->colls) {
+        if (!s.empty()) s += '\n';
+        s += kv.first;
+    }
+    if (needed) *needed = s.size() + 1;
+    if (buf && cap > 0) {
+        const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return VROD_OK;
+}
+
+extern "C" vrod_status vrod_collection_info(vrod_collection *c, uint32_t *dim, vrod_metric *metric, uint64_t *count,
+                                            uint64_t *capacity) {
+    if (!c) return fail(VROD_EINVAL, "collection is NULL");
+    if (dim) *dim = c->dim;
+    if (metric) *metric = c->metric;
+    if (count) *count = c->count;
+    if (capacity) *capacity = c->capacity;
+    return VROD_OK;
+}
+
+extern "C" vrod_status vrod_collection_shard(vrod_collection *c, uint64_t *id_base, uint64_t *local_rows) {
+    if (!c) return fail(VROD_EINVAL, "collection is NULL");
+    if (id_base) *id_base = c->id_base;
+    if (local_rows) *local_rows = c->local;
+    return VROD_OK;
+}
+
+extern "C" vrod_status vrod_collection_set_path(vrod_collection *c, int path) {
+    if (!c || path < 0 || path > 3) return fail(VROD_EINVAL, "bad path");
+    c->path = path;
+    return VROD_OK;
+}
+
+// rows [g0, g0+n) of the global sequence: which part lands on this rank?  Returns local start / count / source offset.
+static void shard_overlap(const vrod_collection *c, uint64_t g0, uint64_t n, uint64_t *loc0, uint64_t *cnt, uint64_t *src_off) {
+    const uint64_t lo = c->id_base, hi = c->id_base + c->shard_rows;
+    const uint64_t a = g0 > lo ? g0 : lo;
+    const uint64_t b = (g0 + n) < hi ? (g0 + n) : hi;
+    if (b <= a) {
+        *loc0 = 0; *cnt = 0; *src_off = 0;
+        return;
+    }
+    *loc0 = a - lo;
+    *cnt = b - a;
+    *src_off = a - g0;
+}
+
+// after new rows landed in [loc0, loc0+cnt): norms + validation
+static vrod_status finish_append(vrod_collection *c, uint64_t loc0, uint64_t cnt, bool check_flags) {
+    vrod_ctx *ctx = c->ctx;
+    VROD_CUDA(launch_row_norms(c->rows, (uint32_t)loc0, (uint32_t)cnt, c->ld, c->inv_norm, c->sq_norm, c->flags, ctx->stream));
+    if (cnt) ctx->stats.kernel_launches++;
+    if (check_flags) {
+        int fl = 0;
+        VROD_CUDA(cudaMemcpyAsync(&fl, c->flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (fl & 1) {
+            VROD_CUDA(cudaMemsetAsync(c->flags, 0, sizeof(int), ctx->stream));
+            return fail(VROD_EINVAL, "rows contain NaN or infinity");
+        }
+        if (fl & 2) c->fast_ok = false;
+    }
+    return VROD_OK;
+}
+
+extern "C" vrod_status vrod_collection_insert(vrod_collection *c, const float *rows, uint64_t n, uint64_t *first_id) {
+    if (!c) return fail(VROD_EINVAL, "collection is NULL");
+    if (n == 0) {
+        if (first_id) *first_id = c->count;
+        return VROD_OK;
+    }
+    if (!rows) return fail(VROD_EINVAL, "rows is NULL");
+    if (c->count + n > c->capacity) return fail(VROD_ENOMEM, "collection capacity exceeded");
+    vrod_ctx *ctx = c->ctx;
+    VROD_CUDA(cudaSetDevice(ctx->device));
+    uint64_t loc0, cnt, off;
+    shard_overlap(c, c->count, n, &loc0, &cnt, &off);
+    if (cnt) {
+        const float *src = rows + (size_t)off * c->dim;
+        float *dst = c->rows + (size_t)loc0 * c->ld;
+        if (c->ld != c->dim) VROD_CUDA(cudaMemsetAsync(dst, 0, (size_t)cnt * c->ld * sizeof(float), ctx->stream));
+        VROD_CUDA(cudaMemcpy2DAsync(dst, (size_t)c->ld * sizeof(float), src, (size_t)c->dim * sizeof(float),
+                                    (size_t)c->dim * sizeof(float), (size_t)cnt, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    vrod_status st = finish_append(c, loc0, cnt, true);
+    if (st != VROD_OK) return st;  // rejected rows are not counted: the next insert overwrites them
+    if (first_id) *first_id = c->count;
+    c->count += n;
+    c->local += cnt;
+    return VROD_OK;
+}
+
+extern "C" vrod_status vrod_collection_fill_synthetic(vrod_collection *c, uint64_t n, uint64_t seed) {
+    if (!c) return fail(VROD_EINVAL, "collection is NULL");
+    if (c->count + n > c->capacity) return fail(VROD_ENOMEM, "collection capacity exceeded");
+    vrod_ctx *ctx = c->ctx;
+    VROD_CUDA(cudaSetDevice(ctx->device));
+    uint64_t loc0, cnt, off;
+    shard_overlap(c, c->count, n, &loc0, &cnt, &off);
+    if (cnt) {
+        VROD_CUDA(launch_fill_synthetic(c->rows, (uint32_t)loc0, (uint32_t)cnt, c->dim, c->ld, c->id_base + loc0, seed,
+                                        ctx->stream));
+        ctx->stats.kernel_launches++;
+    }
+    vrod_status st = finish_append(c, loc0, cnt, false);
+    if (st != VROD_OK) return st;
+    VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+    c->count += n;
+    c->local += cnt;
+    return VROD_OK;
+}
+
+extern "C" vrod_status vrod_collection_read_rows(vrod_collection *c, uint64_t row0, uint64_t n, float *out) {
+    if (!c || (!out && n)) return fail(VROD_EINVAL, "NULL argument");
+    if (row0 + n > c->local) return fail(VROD_EINVAL, "row range outside this rank's shard");
+    if (n == 0) return VROD_OK;
+    vrod_ctx *ctx = c->ctx;
+    VROD_CUDA(cudaSetDevice(ctx->device));
+    VROD_CUDA(cudaMemcpy2DAsync(out, (size_t)c->dim * sizeof(float), c->rows + (size_t)row0 * c->ld,
+                                (size_t)c->ld * sizeof(float), (size_t)c->dim * sizeof(float), (size_t)n,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VROD_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// SEARCH
+// -------------------------------------------------------------------------------------------------
+static ShardView shard_view(const vrod_collection *c) {
+    ShardView s{};
+    s.rows = c->rows;
+    s.inv_norm = c->inv_norm;
+    s.sq_norm = c->sq_norm;
+    s.n = (uint32_t)c->local;
+    s.dim = c->dim;
+    s.ld = c->ld;
+    s.metric = (int)c->metric;
+    s.id_base = c->id_base;
+    return s;
+}
+
+// queries already on the device as [b x ld]; enqueue everything, no synchronisation
+static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t b, uint32_t k, uint64_t *d_ids,
+                                  float *d_dist, bool force_exact) {
+    vrod_ctx *ctx = c->ctx;
+    const ShardView s = shard_view(c);
+    const size_t nhits = (size_t)b * k;
+    VROD_CUDA(ctx->hits_local.ensure(nhits * sizeof(Hit)));
+    Hit *local = reinterpret_cast<Hit *>(ctx->hits_local.p);
+    ScanScratch scr{reinterpret_cast<unsigned long long *>(ctx->blk_cand.p),
+                    reinterpret_cast<unsigned int *>(ctx_ticket(ctx)), ctx_status(ctx), ctx->dev_counters};
+    const bool exact_only = force_exact || c->path == 2 || !c->fast_ok;
+    const bool batched = !exact_only && batched_supported(s, b, k) && (c->path == 3 || (c->path == 0 && b >= 64));
+    if (batched) {
+        BatchedStats bs{};
+        vrod_status st = VROD_OK;
+        cudaError_t e = launch_batched_search(s, d_q, b, k, ctx->sms, &ctx->batched.p, &ctx->batched.bytes, ctx_status(ctx),
+                                              local, ctx->stream, &bs);
+        if (e != cudaSuccess) st = fail(VROD_ECUDA, std::string("batched search: ") + cudaGetErrorString(e));
+        if (st != VROD_OK) return st;
+        ctx->stats.kernel_launches += bs.launches;
+        ctx->stats.batched_tiles += bs.tiles;
+        // queries whose guard failed are rescanned exactly, decided on the device
+        const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
+        for (uint32_t qi = 0; qi < b; ++qi) {
+            VROD_CUDA(launch_exact_scan(s, d_q + (size_t)qi * s.ld, k, xp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k,
+                                        ctx->stream));
+            ctx->stats.kernel_launches++;
+        }
+    } else if (exact_only) {
+        const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
+        for (uint32_t qi = 0; qi < b; ++qi) {
+            VROD_CUDA(launch_exact_scan(s, d_q + (size_t)qi * s.ld, k, xp, scr, nullptr, local + (size_t)qi * k, ctx->stream));
+            ctx->stats.kernel_launches++;
+        }
+        ctx->stats.exact_rescans += 0;
+    } else {
+        const ScanPlan fp = make_scan_plan(s, k, ctx->sms, false);
+        const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
+        for (uint32_t qi = 0; qi < b; ++qi) {
+            const float *q = d_q + (size_t)qi * s.ld;
+            VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, ctx->stream));
+            VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, ctx->stream));
+            ctx->stats.kernel_launches += 2;
+        }
+        ctx->stats.fast_scans += b;
+    }
+    const Hit *lists = local;
+    uint32_t g = 1;
+    if (ctx->world > 1) {
+        VROD_CUDA(ctx->hits_all.ensure(nhits * sizeof(Hit) * ctx->world));
+        VROD_NCCL(g_nccl.AllGather(local, ctx->hits_all.p, nhits * sizeof(Hit), ncclChar, ctx->comm, ctx->stream));
+        lists = reinterpret_cast<const Hit *>(ctx->hits_all.p);
+        g = (uint32_t)ctx->world;
+    }
+    VROD_CUDA(launch_merge_hits(lists, g, b, k, reinterpret_cast<unsigned long long *>(d_ids), d_dist, ctx->stream));
+    ctx->stats.kernel_launches++;
+    ctx->stats.searches += b;
+    return VROD_OK;
+}
+
+static vrod_status check_search_args(vrod_collection *c, const void *q, uint32_t b, uint32_t k, const void *ids,
+                                     const void *dist) {
+    if (!c) return fail(VROD_EINVAL, "collection is NULL");
+    if (b == 0) return VROD_OK;
+    if (!q || !ids || !dist) return fail(VROD_EINVAL, "NULL buffer");
+    if (k == 0 || k > VROD_MAX_K) return fail(VROD_EINVAL, "k must be in [1, VROD_MAX_K]");
+    if (b > kMaxBatch) return fail(VROD_EINVAL, "more than 65536 queries in one call");
+    return VROD_OK;
+}
+
+extern "C" vrod_status vrod_collection_search_device(vrod_collection *c, const float *d_queries, uint32_t b, uint32_t k,
+                                                     uint64_t *d_out_ids, float *d_out_dist) {
+    vrod_status st = check_search_args(c, d_queries, b, k, d_out_ids, d_out_dist);
+    if (st != VROD_OK || b == 0) return st;
+    vrod_ctx *ctx = c->ctx;
+    VROD_CUDA(cudaSetDevice(ctx->device));
+    const float *q = d_queries;
+    if (c->ld != c->dim) {
+        VROD_CUDA(ctx->q_pad.ensure((size_t)b * c->ld * sizeof(float)));
+        VROD_CUDA(launch_pad_queries(d_queries, reinterpret_cast<float *>(ctx->q_pad.p), b, c->dim, c->ld, ctx->stream));
+        ctx->stats.kernel_launches++;
+        q = reinterpret_cast<const float *>(ctx->q_pad.p);
+    }
+    return search_enqueue(c, q, b, k, d_out_ids, d_out_dist, false);
+}
+
+extern "C" vrod_status vrod_collection_search(vrod_collection *c, const float *queries, uint32_t b, uint32_t k,
+                                              uint64_t *out_ids, float *out_dist) {
+    vrod_status st = check_search_args(c, queries, b, k, out_ids, out_dist);
+    if (st != VROD_OK || b == 0) return st;
+    vrod_ctx *ctx = c->ctx;
+    VROD_CUDA(cudaSetDevice(ctx->device));
+    // validate + pack (zero padded to ld) into pinned staging
+    const size_t qbytes = (size_t)b * c->ld * sizeof(float);
+    VROD_CUDA(ctx->q_host.ensure(qbytes));
+    float *qh = reinterpret_cast<float *>(ctx->q_host.p);
+    bool unsafe = false;
+    for (uint32_t i = 0; i < b; ++i) {
+        const float *src = queries + (size_t)i * c->dim;
+        float *dst = qh + (size_t)i * c->ld;
+        double nq = 0.0;
+        for (uint32_t j = 0; j < c->dim; ++j) {
+            const float v = src[j];
+            if (!isfinite(v)) return fail(VROD_EINVAL, "query contains NaN or infinity");
+            if (fabsf(v) > 0x1p40f) unsafe = true;
+            nq += (double)v * (double)v;
+            dst[j] = v;
+        }
+        for (uint32_t j = c->dim; j < c->ld; ++j) dst[j] = 0.f;
+        if (nq > 0.0 && (nq < 0x1p-80 || nq > 0x1p100)) unsafe = true;
+        if (c->metric == VROD_COSINE && nq == 0.0) unsafe = true;  // all distances are 1: answered by the exact scan
+    }
+    const size_t nres = (size_t)b * k;
+    VROD_CUDA(ctx->q_dev.ensure(qbytes));
+    VROD_CUDA(ctx->out_ids.ensure(nres * sizeof(uint64_t)));
+    VROD_CUDA(ctx->out_dist.ensure(nres * sizeof(float)));
+    VROD_CUDA(ctx->ids_host.ensure(nres * sizeof(uint64_t)));
+    VROD_CUDA(ctx->dist_host.ensure(nres * sizeof(float)));
+    VROD_CUDA(cudaMemcpyAsync(ctx->q_dev.p, qh, qbytes, cudaMemcpyHostToDevice, ctx->stream));
+    st = search_enqueue(c, reinterpret_cast<const float *>(ctx->q_dev.p), b, k, reinterpret_cast<uint64_t *>(ctx->out_ids.p),
+                        reinterpret_cast<float *>(ctx->out_dist.p), unsafe);
+    if (st != VROD_OK) return st;
+    VROD_CUDA(cudaMemcpyAsync(ctx->ids_host.p, ctx->out_ids.p, nres * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    VROD_CUDA(cudaMemcpyAsync(ctx->dist_host.p, ctx->out_dist.p, nres * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_ids, ctx->ids_host.p, nres * sizeof(uint64_t));
+    memcpy(out_dist, ctx->dist_host.p, nres * sizeof(float));
+    ctx->stats.h2d_bytes += qbytes;
+    ctx->stats.d2h_bytes += nres * (sizeof(uint64_t) + sizeof(float));
+    return VROD_OK;
+}
+
+extern "C" const char *vrod_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *vrod_version(void) { return "vrod_knn_b200 0.1.0 (sm_100a)"; }
