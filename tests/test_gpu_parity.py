@@ -1,0 +1,249 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Bar: bit-exact ids AND bit-exact f32 distances (the canonical f64 order is part of
+the contract), far inside north_star's "identical ids, distances within 1e-5 relative"."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import assert_same, load_kat
+
+pytestmark = pytest.mark.gpu
+KAT = load_kat()
+_seq = [0]
+
+
+def make(ctx, rows, metric, dim=None, capacity=None):
+    from vrod_b200 import ffi  # noqa: F401
+    _seq[0] += 1
+    rows = np.asarray(rows, dtype=np.float32)
+    dim = dim or rows.shape[1]
+    c = ctx.create(f"t{_seq[0]}", dim, metric, capacity or max(1, len(rows)))
+    if len(rows):
+        c.insert(rows)
+    return c
+
+
+@pytest.mark.parametrize("path", [0, 2], ids=["auto", "exact"])
+@pytest.mark.parametrize("case", KAT, ids=[c["name"] for c in KAT])
+def test_golden_through_the_c_abi(ctx, case, path):
+    c = make(ctx, case["rows"], case["metric"], dim=len(case["query"]))
+    c.set_path(path)
+    ids, dist = c.search(case["query"], case["k"])
+    assert_same(ids[0], dist[0], case["ids"], case["dist"], case["name"])
+    ctx.drop(c.name)
+
+
+SWEEP = [(10000, 128), (1000, 64), (5000, 32), (3000, 768), (2000, 1536), (1234, 100), (777, 3), (50, 128),
+         (5, 128), (20000, 384), (60000, 256), (4096, 512), (3000, 1024), (2500, 200), (1500, 2052)]
+
+
+@pytest.mark.parametrize("metric", [0, 1], ids=["l2", "cos"])
+@pytest.mark.parametrize("n,d", SWEEP)
+def test_matches_oracle(ctx, oracle, n, d, metric):
+    c = ctx.create(f"s{n}_{d}_{metric}", d, metric, n)
+    c.fill_synthetic(n, 1000 + d)
+    X = oracle.fill(n, d, 1000 + d)
+    assert np.array_equal(c.read_rows(0, n), X), "device Philox fill differs from the oracle's"
+    Q = oracle.fill(3, d, 2000 + d)
+    for k in (1, 10, 100):
+        rid, rdist = oracle.search(X, Q, k, metric)
+        for path in (0, 2):
+            c.set_path(path)
+            ids, dist = c.search(Q, k)
+            assert_same(ids, dist, rid, rdist, f"n={n} d={d} metric={metric} k={k} path={path}")
+    ctx.drop(c.name)
+
+
+def test_config0_10k_x128_euclidean_top10(ctx, oracle):
+    """BASELINE configs[0]: the reference's own CPU-runnable case."""
+    c = ctx.create("cfg0", 128, 0, 10000)
+    c.fill_synthetic(10000, 0x5EED0001)
+    X = oracle.fill(10000, 128, 0x5EED0001)
+    Q = oracle.fill(32, 128, 0x5EED0002)
+    assert_same(*c.search(Q, 10), *oracle.search(X, Q, 10, 0))
+    # one query at a time gives the same rows as the batch
+    for i in (0, 7, 31):
+        ids, dist = c.search(Q[i], 10)
+        assert_same(ids, dist, *oracle.search(X, Q[i], 10, 0))
+    ctx.drop("cfg0")
+
+
+def test_config1_1m_x768_cosine_top10_full_size(ctx, oracle):
+    """BASELINE configs[1] at full size; the oracle needs ~0.3 s per query on 8 host threads."""
+    n, d = 1_000_000, 768
+    c = ctx.create("cfg1", d, 1, n)
+    c.fill_synthetic(n, 0x5EED0001)
+    X = oracle.fill(n, d, 0x5EED0001)
+    Q = oracle.fill(4, d, 0x5EED0002)
+    before = ctx.stats()
+    ids, dist = c.search(Q, 10)
+    assert_same(ids, dist, *oracle.search(X, Q, 10, 1))
+    after = ctx.stats()
+    assert after["fast_scans"] - before["fast_scans"] == 4
+    assert after["exact_rescans"] == before["exact_rescans"], "random data must not need the f64 rescan"
+    # k = 100 and the exact path agree too
+    assert_same(*c.search(Q[:2], 100), *oracle.search(X, Q[:2], 100, 1))
+    c.set_path(2)
+    assert_same(*c.search(Q[:1], 10), ids[:1], dist[:1])
+    ctx.drop("cfg1")
+
+
+def test_10m_x128_l2_full_size(ctx, oracle):
+    """BASELINE configs[2]'s collection (single-query path here): 10M x 128, k = 10 and 100."""
+    n, d = 10_000_000, 128
+    c = ctx.create("cfg2", d, 0, n)
+    c.fill_synthetic(n, 0x5EED0001)
+    X = oracle.fill(n, d, 0x5EED0001)
+    Q = oracle.fill(2, d, 0x5EED0002)
+    assert_same(*c.search(Q, 10), *oracle.search(X, Q, 10, 0))
+    assert_same(*c.search(Q[:1], 100), *oracle.search(X, Q[:1], 100, 0))
+    del X
+    ctx.drop("cfg2")
+
+
+@pytest.mark.skipif(os.environ.get("VROD_SKIP_100M") == "1", reason="VROD_SKIP_100M=1")
+def test_config3_100m_x128_l2_top10_full_size(ctx, oracle):
+    """BASELINE configs[3] on ONE GPU (51.2 GB).  The oracle never holds the collection: it replays
+    the Philox stream in 4M-row chunks and merges the per-chunk lists (the same (dist, id) merge)."""
+    n, d, k, chunk = 100_000_000, 128, 10, 4_000_000
+    c = ctx.create("cfg3", d, 0, n)
+    c.fill_synthetic(n, 0x5EED0001)
+    Q = oracle.fill(2, d, 0x5EED0002)
+    ids, dist = c.search(Q, k)
+    parts_i, parts_d = [], []
+    for lo in range(0, n, chunk):
+        X = oracle.fill(min(chunk, n - lo), d, 0x5EED0001, row0=lo)
+        pi, pd = oracle.search(X, Q, k, 0, id_base=lo)
+        parts_i.append(pi)
+        parts_d.append(pd)
+    assert_same(ids, dist, *oracle.merge(np.stack(parts_i), np.stack(parts_d)))
+    # size-independent properties at full size: sorted by (dist, id), ids valid and unique
+    assert np.all(np.diff(dist, axis=1) >= 0) and np.all(ids < n)
+    assert all(len(set(r)) == k for r in ids.tolist())
+    # the rows the GPU claims are nearest really sit at those distances (oracle arithmetic on just those rows)
+    for qi in range(2):
+        for j in (0, k - 1):
+            row = oracle.fill(1, d, 0x5EED0001, row0=int(ids[qi, j]))[0]
+            assert np.float32(oracle.distance(row, Q[qi], 0)) == dist[qi, j]
+    ctx.drop("cfg3")
+
+
+def test_device_api_equals_host_api(ctx, oracle):
+    import torch
+    n, d, k = 50000, 128, 10
+    c = ctx.create("dev", d, 0, n)
+    c.fill_synthetic(n, 5)
+    Q = oracle.fill(6, d, 6)
+    hid, hdist = c.search(Q, k)
+    q = torch.from_numpy(Q).cuda()
+    ids = torch.empty((6, k), dtype=torch.int64, device="cuda")
+    dist = torch.empty((6, k), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    c.search_device(q.data_ptr(), 6, k, ids.data_ptr(), dist.data_ptr())
+    ctx.synchronize()
+    assert_same(ids.cpu().numpy().astype(np.uint64), dist.cpu().numpy(), hid, hdist)
+    ctx.drop("dev")
+
+
+def test_incremental_inserts_equal_one_insert(ctx, oracle):
+    X = oracle.fill(5000, 96, 9)
+    Q = oracle.fill(2, 96, 10)
+    c = ctx.create("inc", 96, 1, 6000)
+    assert c.insert(X[:1]) == 0
+    assert c.insert(X[1:1234]) == 1
+    assert c.insert(X[1234:]) == 1234
+    assert c.info()["count"] == 5000
+    assert_same(*c.search(Q, 10), *oracle.search(X, Q, 10, 1))
+    ctx.drop("inc")
+
+
+def test_degenerate_ties_fall_back_to_the_exact_scan(ctx, oracle):
+    """All rows identical: the f32 scan cannot prove its candidates, the guard fails, and the f64 scan
+    answers -- ids are still the k smallest (tie-break by id)."""
+    row = oracle.fill(1, 128, 3)
+    X = np.repeat(row, 5000, axis=0)
+    c = make(ctx, X, 0)
+    before = ctx.stats()["exact_rescans"]
+    ids, dist = c.search(row[0], 10)
+    assert list(ids[0]) == list(range(10)) and np.all(dist == 0.0)
+    assert ctx.stats()["exact_rescans"] == before + 1
+    q = oracle.fill(1, 128, 4)
+    assert_same(*c.search(q, 10), *oracle.search(X, q, 10, 0))
+    # a block of duplicates straddling the k-th place among distinct rows
+    Y = oracle.fill(3000, 64, 8)
+    Y[100:140] = Y[50]
+    c2 = make(ctx, Y, 1)
+    assert_same(*c2.search(Y[50], 10), *oracle.search(Y, Y[50], 10, 1))
+    assert_same(*c2.search(Y[50], 64), *oracle.search(Y, Y[50], 64, 1))
+    ctx.drop(c.name)
+    ctx.drop(c2.name)
+
+
+def test_self_match_is_distance_zero(ctx, oracle):
+    X = oracle.fill(20000, 384, 13)
+    c = make(ctx, X, 0)
+    ids, dist = c.search(X[[17, 19999]], 3)
+    assert ids[0, 0] == 17 and ids[1, 0] == 19999 and dist[0, 0] == 0.0 and dist[1, 0] == 0.0
+    assert_same(ids, dist, *oracle.search(X, X[[17, 19999]], 3, 0))
+    ctx.drop(c.name)
+
+
+def test_extreme_magnitudes_use_the_exact_scan(ctx, oracle):
+    """Values outside the range the f32 pass's error bound covers are still answered exactly."""
+    X = oracle.fill(4000, 64, 14)
+    X[::7] *= np.float32(1e30)
+    X[1::7] *= np.float32(1e-30)
+    X[5] = 0.0
+    Q = oracle.fill(2, 64, 15)
+    Q[1] *= np.float32(1e25)
+    for metric in (0, 1):
+        c = make(ctx, X, metric)
+        assert_same(*c.search(Q, 10), *oracle.search(X, Q, 10, metric), f"metric={metric}")
+        ctx.drop(c.name)
+
+
+def test_argument_errors(ctx, oracle):
+    from vrod_b200 import ffi
+    X = oracle.fill(100, 16, 1)
+    c = make(ctx, X, 0, capacity=100)
+    with pytest.raises(ffi.VrodError) as e:
+        ctx.create(c.name, 16, 0, 10)
+    assert e.value.status == ffi.EEXISTS
+    with pytest.raises(ffi.VrodError) as e:
+        ctx.get("nope")
+    assert e.value.status == ffi.ENOTFOUND
+    for k in (0, ffi.MAX_K + 1):
+        with pytest.raises(ffi.VrodError) as e:
+            c.search(X[0], k)
+        assert e.value.status == ffi.EINVAL
+    bad = X[:2].copy()
+    bad[1, 3] = np.nan
+    with pytest.raises(ffi.VrodError) as e:
+        c.search(bad, 3)
+    assert e.value.status == ffi.EINVAL
+    with pytest.raises(ffi.VrodError) as e:
+        c.insert(X[:1])           # capacity 100 is full
+    assert e.value.status == ffi.ENOMEM
+    c2 = ctx.create("nanrows", 16, 0, 10)
+    bad[1, 3] = np.inf
+    with pytest.raises(ffi.VrodError) as e:
+        c2.insert(bad)
+    assert e.value.status == ffi.EINVAL and c2.info()["count"] == 0
+    assert c2.insert(X[:3]) == 0      # the rejected rows left no trace
+    assert_same(*c2.search(X[0], 2), *oracle.search(X[:3], X[0], 2, 0))
+    assert sorted(n for n in ctx.list() if n in (c.name, "nanrows")) == sorted([c.name, "nanrows"])
+    ctx.drop(c.name)
+    ctx.drop("nanrows")
+    with pytest.raises(ffi.VrodError):
+        ctx.drop("nanrows")
+
+
+def test_k_up_to_the_maximum(ctx, oracle):
+    X = oracle.fill(30000, 128, 16)
+    Q = oracle.fill(2, 128, 17)
+    for metric in (0, 1):
+        c = make(ctx, X, metric)
+        for k in (500, 1024):
+            assert_same(*c.search(Q, k), *oracle.search(X, Q, k, metric), f"k={k}")
+        ctx.drop(c.name)
