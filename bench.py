@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the exact top-k kNN scan (vRod SEARCH hot path) on 1..8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg1|cfg0|cfg2] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A step is ONE pass of the hot path over one batch of synthetic queries (batch = 1 query unless the
+workload says otherwise): f32 scan of this rank's row shard + exact f64 rerank + guard (+ NCCL
+all-gather and merge of the per-rank top-k lists when N > 1).  The default workload is BASELINE.json
+configs[3] -- 100M x 128 f32, Euclidean, top-10 -- the collection the metric "queries/sec for exact
+top-10 kNN at 1/2/4/8 B200" is quoted on; it fits one GPU (51.2 GB), and is row-sharded over the N
+ranks (strong scaling: the collection is fixed, per-GPU rows shrink as N grows).
+
+Prints ONE JSON line on rank 0 (see the task contract): value = queries/s with queries and results
+resident in HBM, timed with CUDA events on the library's stream, max over ranks; e2e = the same metric
+through the host-buffer C-ABI call (vrod_collection_search: H2D of the query and D2H of the ids and
+distances inside the timed region); roofline = the scan kernel against the measured HBM peak;
+cpu_baseline = the CPU oracle (test infrastructure, oracle/) timed on this box's host cores on a
+bounded sample of the same collection.  --impl reference times that CPU oracle as the reference arm
+(the reference itself, sekulas/vRod, has an empty SEARCH body and no toolchain here: DESIGN.md).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (rows, dim, metric, k, batch, BASELINE.json config)
+    "cfg3": (100_000_000, 128, 0, 10, 1, "configs[3]: 100Mx128 f32 L2, exact top-10, row-sharded over the GPUs"),
+    "cfg1": (1_000_000, 768, 1, 10, 1, "configs[1]: 1Mx768 f32 cosine, single-query exact top-10"),
+    "cfg0": (10_000, 128, 0, 10, 1, "configs[0]: 10kx128 f32 Euclidean, single-query exact top-10"),
+    "cfg2": (10_000_000, 128, 0, 100, 1024, "configs[2]: 10Mx128 f32 L2, 1024 queries, exact top-100"),
+}
+DATA_SEED, QUERY_SEED = 0x5EED0001, 0x5EED0002
+METRIC_NAME = "queries/sec, exact top-k kNN"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per scan launch from the committed ncu capture (profiles/roofline_traffic.json), else None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(workload)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_leg(rows, dim, metric, k, steps, warmup, budget_s=20.0):
+    """Time the CPU oracle on a bounded sample of the workload: the first `sample` rows of the same
+    seeded collection, one query per step, all host threads.  qps is scaled to the full row count."""
+    from oracle import oracle as O
+    O.build()
+    sample = min(rows, max(10_000, (1 << 30) // (dim * 4)))     # <= 1 GiB of rows on the host
+    X = O.fill(sample, dim, DATA_SEED)
+    Q = O.fill(max(steps + warmup, 1), dim, QUERY_SEED)
+    for i in range(warmup):
+        O.search(X, Q[i], k, metric)
+    t_used, times = 0.0, []
+    for i in range(steps):
+        t0 = time.perf_counter()
+        O.search(X, Q[warmup + i], k, metric)
+        dt = time.perf_counter() - t0
+        times.append(dt)
+        t_used += dt
+        if t_used > budget_s and len(times) >= 3:
+            break
+    per_query_full = statistics.mean(times) * (rows / sample)
+    return {"value": 1.0 / per_query_full, "unit": "queries/s", "cores": O.max_threads(), "kind": "port",
+            "sample": f"first {sample} of {rows} rows x {dim} (same Philox stream), {len(times)} single-query top-{k} "
+                      f"scans by oracle/knn_oracle.c (canonical f64), time scaled by {rows / sample:g} to the full collection",
+            "ms_per_step_sample": statistics.mean(times) * 1e3, "steps": len(times)}
+
+
+def run_reference(args, rank):
+    rows, dim, metric, k, batch, label = WORKLOADS[args.workload]
+    if rank != 0:
+        return
+    leg = cpu_oracle_leg(rows, dim, metric, k, args.steps, args.warmup, budget_s=60.0)
+    line = {"impl": "reference", "metric": METRIC_NAME, "value": leg["value"], "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": leg["steps"], "warmup": args.warmup, "ms_per_step": 1e3 / leg["value"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": label, "rows": rows, "dim": dim, "k": k, "batch": 1,
+                       "note": "sekulas/vRod's SEARCH body is empty (src/command/types.rs:114-119) and rustc is absent: "
+                               "the reference arm is the CPU oracle port of the written semantics, all host threads"},
+            "cpu_baseline": {k2: leg[k2] for k2 in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": leg["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="vrod_b200", choices=["vrod_b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override the row count (debugging)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.rows:
+        w = list(WORKLOADS[args.workload])
+        w[0] = args.rows
+        WORKLOADS[args.workload] = tuple(w)
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if args.gpus != 1 or world != 1:
+            raise SystemExit(f"--gpus {args.gpus} needs WORLD_SIZE={args.gpus} (launch with torch.distributed.run)")
+
+    import torch
+    import torch.distributed as dist
+    from vrod_b200 import ffi
+    from vrod_b200.dist import share_comm_id
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm_id = share_comm_id(ffi.comm_unique_id, rank, world) if world > 1 else None
+    ctx = ffi.Context(local, rank, world, comm_id)
+    stream = torch.cuda.ExternalStream(ctx.stream())
+
+    rows, dim, metric, k, batch, label = WORKLOADS[args.workload]
+    coll = ctx.create("bench", dim, metric, rows)
+    coll.fill_synthetic(rows, DATA_SEED)
+    base, local_rows = coll.shard()
+
+    # queries: one fresh Philox draw per step (never a row of X), generated by the library's own
+    # device generator in a private unsharded context so that every rank holds the same full set
+    nq = (args.steps + args.warmup) * batch
+    qctx = ffi.Context(local)
+    qcoll = qctx.create("queries", dim, 0, nq)
+    qcoll.fill_synthetic(nq, QUERY_SEED)
+    from_host = qcoll.read_rows(0, nq)
+    qctx.close()
+    q_dev = torch.from_numpy(from_host).cuda()
+    ids_dev = torch.empty((batch, k), dtype=torch.int64, device="cuda")
+    dist_dev = torch.empty((batch, k), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def step_resident(i):
+        coll.search_device(q_dev[i * batch].data_ptr(), batch, k, ids_dev.data_ptr(), dist_dev.data_ptr())
+
+    # ---- resident leg: `value` ----
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    s0 = ctx.stats()
+    ctx.profile(True)
+    ctx.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step_resident(args.warmup + i)
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    kern_ms, kern_n = ctx.profile_read()
+    ctx.profile(False)
+    s1 = ctx.stats()
+    clocks = sampler.stop() if rank == 0 else None
+    last_ids = ids_dev.cpu().numpy().astype(np.uint64)
+    last_dist = dist_dev.cpu().numpy()
+
+    # ---- e2e leg: host buffers through vrod_collection_search ----
+    q_pinned = torch.from_numpy(from_host).pin_memory()
+    q_np = q_pinned.numpy()
+    for i in range(args.warmup):
+        coll.search(q_np[i * batch:(i + 1) * batch], k)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        j = args.warmup + i
+        h_ids, h_dist = coll.search(q_np[j * batch:(j + 1) * batch], k)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert np.array_equal(h_ids, last_ids) and np.array_equal(h_dist.view(np.uint32), last_dist.view(np.uint32)), \
+        "host-buffer and resident legs disagree"
+
+    # max over ranks
+    t = torch.tensor([ms_total, e2e_s * 1e3, kern_ms / max(kern_n, 1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, kern_avg_ms = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        qps = args.steps * batch / (ms_total / 1e3)
+        algo_bytes = 4.0 * local_rows * dim                 # 4*N_local*d per pass, once per batch
+        achieved = algo_bytes / (kern_avg_ms / 1e3) / 1e9 if kern_avg_ms > 0 else None
+        traffic = ncu_traffic(args.workload if world == 1 else f"{args.workload}@{world}")
+        line = {
+            "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": label, "rows": rows, "rows_per_gpu": local_rows, "dim": dim, "k": k, "batch": batch,
+                       "metric": "cosine" if metric else "euclidean", "parallelism": f"row-shard x{world}",
+                       "data_seed": hex(DATA_SEED), "query_seed": hex(QUERY_SEED),
+                       "l2_policy": f"inputs larger than L2: {algo_bytes / 1e9:.2f} GB scanned per step per GPU vs 126 MB L2",
+                       "arithmetic": "f32 scan, exact f64 rerank + guard (bit-identical to the oracle)"},
+            "e2e": {"value": args.steps * batch / (e2e_ms / 1e3), "unit": "queries/s",
+                    "h2d_bytes_per_step": int((s1["h2d_bytes"] - s0["h2d_bytes"]) // max(args.steps, 1)) or batch * dim * 4,
+                    "d2h_bytes_per_step": batch * k * 12, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]),
+            "exact_rescans": int(s1["exact_rescans"] - s0["exact_rescans"]),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "fast_scan_kernel", "algorithmic_bytes_per_launch": algo_bytes,
+                         "kernel_ms": kern_avg_ms, "launches_timed": int(kern_n)},
+            "clocks": clocks,
+        }
+        # e2e h2d: the timed host leg ran after s1 was read; report the per-step bytes the call copies
+        line["e2e"]["h2d_bytes_per_step"] = batch * ((dim + 3) // 4 * 4) * 4
+        # cheap live check of the last answer: sorted, and the claimed rows sit at the claimed distances
+        assert np.all(np.diff(last_dist, axis=1) >= 0)
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            O.build()
+            qlast = from_host[(args.warmup + args.steps - 1) * batch]
+            for j in (0, k - 1):
+                row = O.fill(1, dim, DATA_SEED, row0=int(last_ids[0, j]))[0]
+                assert np.float32(O.distance(row, qlast, metric)) == last_dist[0, j], "distance check against the oracle failed"
+            line["cpu_baseline"] = {k2: v for k2, v in cpu_oracle_leg(rows, dim, metric, k, 12, 1).items()
+                                    if k2 in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    barrier()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

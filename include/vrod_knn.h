@@ -96,6 +96,12 @@ VROD_API vrod_status vrod_ctx_synchronize(vrod_ctx *ctx);
 /* The cudaStream_t every kernel and copy of this context is issued on (for event timing). */
 VROD_API void *vrod_ctx_stream(vrod_ctx *ctx);
 VROD_API vrod_status vrod_ctx_stats(vrod_ctx *ctx, vrod_stats *out);
+/* Kernel timing for benches: while enabled, every scan kernel launch (the f32 scan of the single-query
+ * path, the tile kernel of the batched path) is bracketed by CUDA events on the context's stream.
+ * vrod_ctx_profile_read synchronises, returns the summed device time (ms) and the number of bracketed
+ * launches since the last read, and clears both. */
+VROD_API vrod_status vrod_ctx_profile(vrod_ctx *ctx, int enable);
+VROD_API vrod_status vrod_ctx_profile_read(vrod_ctx *ctx, double *kernel_ms, uint64_t *launches);
 VROD_API int vrod_ctx_rank(vrod_ctx *ctx);
 VROD_API int vrod_ctx_world(vrod_ctx *ctx);
 

@@ -130,6 +130,18 @@ struct vrod_ctx {
     PinBuf q_host, ids_host, dist_host;
     unsigned long long *dev_counters = nullptr;  // [0] exact rescans (counted on the device)
     vrod_stats stats{};
+    // optional kernel timing (vrod_ctx_profile)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
+    size_t ev_used = 0;
+    cudaEvent_t prof_event() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e = nullptr;
+            cudaEventCreate(&e);
+            ev_pool.push_back(e);
+        }
+        return ev_pool[ev_used++];
+    }
 };
 
 struct vrod_collection {
@@ -241,6 +253,7 @@ extern "C" void vrod_ctx_destroy(vrod_ctx *ctx) {
     PinBuf *pin[] = {&ctx->q_host, &ctx->ids_host, &ctx->dist_host};
     for (PinBuf *b : pin) b->release();
     cudaFree(ctx->dev_counters);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -253,6 +266,28 @@ extern "C" vrod_status vrod_ctx_synchronize(vrod_ctx *ctx) {
 extern "C" void *vrod_ctx_stream(vrod_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 extern "C" int vrod_ctx_rank(vrod_ctx *ctx) { return ctx ? ctx->rank : -1; }
 extern "C" int vrod_ctx_world(vrod_ctx *ctx) { return ctx ? ctx->world : -1; }
+
+extern "C" vrod_status vrod_ctx_profile(vrod_ctx *ctx, int enable) {
+    if (!ctx) return fail(VROD_EINVAL, "ctx is NULL");
+    ctx->profiling = enable != 0;
+    return VROD_OK;
+}
+
+extern "C" vrod_status vrod_ctx_profile_read(vrod_ctx *ctx, double *kernel_ms, uint64_t *launches) {
+    if (!ctx) return fail(VROD_EINVAL, "ctx is NULL");
+    VROD_CUDA(cudaSetDevice(ctx->device));
+    VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+    double total = 0.0;
+    for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+        float ms = 0.f;
+        VROD_CUDA(cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
+        total += ms;
+    }
+    if (kernel_ms) *kernel_ms = total;
+    if (launches) *launches = ctx->ev_used / 2;
+    ctx->ev_used = 0;
+    return VROD_OK;
+}
 
 extern "C" vrod_status vrod_ctx_stats(vrod_ctx *ctx, vrod_stats *out) {
     if (!ctx || !out) return fail(VROD_EINVAL, "NULL argument");
@@ -515,7 +550,9 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
         for (uint32_t qi = 0; qi < b; ++qi) {
             const float *q = d_q + (size_t)qi * s.ld;
+            if (ctx->profiling) VROD_CUDA(cudaEventRecord(ctx->prof_event(), ctx->stream));
             VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, ctx->stream));
+            if (ctx->profiling) VROD_CUDA(cudaEventRecord(ctx->prof_event(), ctx->stream));
             VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, ctx->stream));
             ctx->stats.kernel_launches += 2;
         }

@@ -22,7 +22,8 @@ PATH_AUTO, PATH_SCAN, PATH_EXACT, PATH_BATCHED = 0, 1, 2, 3
 # every symbol include/vrod_knn.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "vrod_ctx_create", "vrod_comm_unique_id", "vrod_ctx_create_sharded", "vrod_ctx_destroy",
-    "vrod_ctx_synchronize", "vrod_ctx_stream", "vrod_ctx_stats", "vrod_ctx_rank", "vrod_ctx_world",
+    "vrod_ctx_synchronize", "vrod_ctx_stream", "vrod_ctx_stats", "vrod_ctx_profile", "vrod_ctx_profile_read",
+    "vrod_ctx_rank", "vrod_ctx_world",
     "vrod_collection_create", "vrod_collection_get", "vrod_collection_drop", "vrod_collection_list",
     "vrod_collection_info", "vrod_collection_insert", "vrod_collection_fill_synthetic",
     "vrod_collection_read_rows", "vrod_collection_shard", "vrod_collection_search",
@@ -64,6 +65,8 @@ def lib():
         L.vrod_ctx_stream.argtypes = [vp]
         L.vrod_ctx_stream.restype = vp
         L.vrod_ctx_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.vrod_ctx_profile.argtypes = [vp, i32]
+        L.vrod_ctx_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
         L.vrod_ctx_rank.argtypes = [vp]
         L.vrod_ctx_world.argtypes = [vp]
         L.vrod_collection_create.argtypes = [vp, C.c_char_p, u32, i32, u64, C.POINTER(vp)]
@@ -188,6 +191,15 @@ class Context:
         s = Stats()
         _check(lib().vrod_ctx_stats(self.h, C.byref(s)))
         return s.as_dict()
+
+    def profile(self, enable):
+        _check(lib().vrod_ctx_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        """(summed kernel ms, bracketed launches) since the last read."""
+        ms, n = C.c_double(), C.c_uint64()
+        _check(lib().vrod_ctx_profile_read(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def create(self, name, dim, metric, capacity):
         h = C.c_void_p()
