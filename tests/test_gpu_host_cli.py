@@ -1,0 +1,65 @@
+"""GPU test of the caller side of the boundary: CREATE / BULKINSERT / INSERT / SEARCH / LISTCOLLECTIONS /
+DROP through the `vrod` CLI (C++ mirror of the reference's command layer), answers against the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.util import assert_same
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "vrod_b200", "host", "vrod")
+
+
+def fmt(v):
+    return ",".join(repr(float(np.float32(x))) if np.float32(float(repr(float(np.float32(x))))) == np.float32(x) else "%.9g" % x
+                    for x in v)
+
+
+def parse_hits(lines):
+    ids, dist, words = [], [], []
+    for ln in lines:
+        rank, i, d, w = ln.split("\t")
+        ids.append(int(i))
+        dist.append(np.float32(float(d)))
+        words.append(w)
+    return np.array(ids, dtype=np.uint64), np.array(dist, dtype=np.float32), words
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+def test_cli_end_to_end(tmp_path, oracle, metric):
+    n, d, k = 500, 24, 7
+    X = oracle.fill(n + 1, d, 99)
+    words = [f"w{i}" for i in range(n + 1)]
+    path = tmp_path / "alice_embeddings.txt"
+    with open(path, "w") as f:                      # the reference's record format, embeddings.rs:61
+        for i in range(n):
+            f.write("%s;%s\n" % (",".join("%.9g" % x for x in X[i]), words[i]))
+    q = oracle.fill(1, d, 100)[0]
+    script = "\n".join([
+        f"CREATE - words;;{metric}",                # dimension fixed by the first insert
+        f"BULKINSERT words {path}",
+        "INSERT words %s;%s" % (",".join("%.9g" % x for x in X[n]), words[n]),
+        "SEARCH words %d;%s" % (k, ",".join("%.9g" % x for x in q)),
+        "LISTCOLLECTIONS",
+        "SEARCH words 2000;%s" % ",".join("%.9g" % x for x in q),
+        "SEARCH words 3;1,2,3",
+        "SEARCH nope 3;1,2,3",
+        "DROP - words",
+        "LISTCOLLECTIONS",
+    ]) + "\n"
+    r = subprocess.run([CLI, "--script", "-"], input=script, capture_output=True, text=True, timeout=300)
+    out = r.stdout.splitlines()
+    assert out[0] == "created words" and out[1] == f"inserted {n} records, first id 0" and out[2] == f"inserted id {n}", r.stderr
+    ids, dist, ws = parse_hits(out[3:3 + k])
+    rid, rdist = oracle.search(X, q, k, 0 if metric == "euclidean" else 1)
+    assert_same(ids, dist, rid[0], rdist[0], "CLI SEARCH")
+    assert ws == [words[int(i)] for i in rid[0]]
+    assert out[3 + k] == "words"
+    assert out[4 + k:] == ["dropped words"]
+    assert r.returncode == 1                          # some commands failed, as intended:
+    assert "k must be an integer in [1, 1024]" in r.stderr
+    assert "query has 3 components, collection has 24" in r.stderr
+    assert "no collection 'nope'" in r.stderr

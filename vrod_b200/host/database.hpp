@@ -1,0 +1,60 @@
+// database.hpp -- host-side mirror of the reference's Database (src/database/mod.rs:6-22), C++17.
+//
+// The reference struct holds only a path; its collections are a TODO (mod.rs:8).  Here the Database
+// owns the C-ABI context (include/vrod_knn.h) whose collections live in GPU memory, plus the text
+// payload of every record (the word after ';' in the reference's record format,
+// src/utils/embeddings.rs:52-62), which search results print next to the id.
+#pragma once
+#include <cstdint>
+#include <filesystem>
+#include <map>
+#include <optional>
+#include <string>
+#include <vector>
+
+#include "../../include/vrod_knn.h"
+
+namespace vrod {
+
+// What a command leaves behind: `trait Command::execute(&self)` returns nothing and has no error
+// channel (src/command/types.rs:5-7), so results and failures leave through the Database.
+struct CommandResult {
+    bool ok = true;
+    std::string error;                 // empty when ok
+    std::vector<uint64_t> ids;         // SEARCH: k ids
+    std::vector<float> dist;           // SEARCH: k distances
+    std::vector<std::string> payload;  // SEARCH: payload of each hit ("" if none)
+    std::vector<std::string> names;    // LISTCOLLECTIONS
+    uint64_t first_id = 0, inserted = 0;
+};
+
+struct CollectionSpec {   // CREATE before the first INSERT fixes the dimension
+    std::optional<uint32_t> dim;
+    vrod_metric metric = VROD_EUCLIDEAN;
+    uint64_t capacity = 1u << 20;
+};
+
+class Database {
+  public:
+    // Database::new(path, name) (mod.rs:13-17): creates path/name with empty vr_config and vr_wal,
+    // io error AlreadyExists if the directory exists (src/database/setup.rs:3-26).
+    static Database create(const std::filesystem::path &path, const std::string &name);
+    // An in-memory database on one GPU (collections are not persisted: SURVEY.md 8(f) N4).
+    explicit Database(int device = 0) : device_(device) {}
+    ~Database();
+    Database(Database &&o) noexcept;
+    Database(const Database &) = delete;
+
+    vrod_ctx *ctx();  // created on first use; throws std::runtime_error without a GPU (no CPU path)
+
+    std::map<std::string, CollectionSpec> pending;                 // created, not yet materialised
+    std::map<std::string, std::vector<std::string>> payloads;      // collection -> payload by id
+    CommandResult last;                                            // result of the last command
+    std::filesystem::path path;
+
+  private:
+    int device_ = 0;
+    vrod_ctx *ctx_ = nullptr;
+};
+
+}  // namespace vrod
