@@ -123,7 +123,10 @@ __device__ __forceinline__ void cand_append(CandCtl *ctl, unsigned long long *bu
     }
 }
 
-// Block-wide bitonic sort of P (power of two) keys in shared memory, ascending.  Caller has synced.
+// Block-wide bitonic sort of P (power of two, >= 64) keys in shared memory, ascending.  Caller has synced.
+// Pair i of a stage touches elements inside one 64-key block whenever the partner distance j <= 32, and
+// pairs [32w, 32w+32) (+ multiples of kScanThreads) belong to warp w, so those stages only need a warp
+// barrier; a block barrier is needed only around the stages with j >= 64.
 __device__ __forceinline__ void block_bitonic(unsigned long long *a, int P, int tid) {
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -134,7 +137,9 @@ __device__ __forceinline__ void block_bitonic(unsigned long long *a, int P, int 
                 const unsigned long long x = a[lo], y = a[hi];
                 if ((x > y) == asc) { a[lo] = y; a[hi] = x; }
             }
-            __syncthreads();
+            const int next_j = j > 1 ? (j >> 1) : k;   // first distance of the next merge level is k
+            if (j >= 64 || next_j >= 64 || (j == 1 && k == P)) __syncthreads();
+            else __syncwarp();
         }
     }
 }
@@ -144,7 +149,7 @@ __device__ __forceinline__ void block_bitonic(unsigned long long *a, int P, int 
 __device__ __forceinline__ void block_prune(CandCtl *ctl, unsigned long long *buf, int kprime, int cap, int tid) {
     int cnt = ctl->cnt;
     if (cnt > cap) cnt = cap;
-    int P = 32;
+    int P = 64;
     while (P < cnt) P <<= 1;
     for (int i = cnt + tid; i < P; i += kScanThreads) buf[i] = kKeyMax;
     __syncthreads();

@@ -35,6 +35,8 @@ struct ScanParams {
     unsigned long long *counters;
     const int *only_if;
     Hit *out;
+    unsigned long long *out_ids;  // optional: final [k] ids / distances of this query (single-GPU contexts
+    float *out_dist;              // skip the merge kernel)
     double eps;
 };
 
@@ -115,6 +117,10 @@ __device__ __forceinline__ void write_hits(const unsigned long long *buf, int nc
         }
         h.pad = 0;
         p.out[i] = h;
+        if (p.out_ids) {
+            p.out_ids[i] = h.id;
+            p.out_dist[i] = h.dist;
+        }
     }
 }
 
@@ -619,20 +625,25 @@ static ScanParams make_params(const ShardView &s, const float *q, uint32_t k, co
 }
 
 cudaError_t launch_fast_scan(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan, const ScanScratch &scr,
-                             int *status, Hit *out, cudaStream_t st) {
+                             int *status, Hit *out, unsigned long long *out_ids, float *out_dist, cudaStream_t st) {
     const Variant &v = pick_variant(s.ld / 4);
     ScanParams p = make_params(s, q, k, plan, scr, v.rows);
     p.status = status;
     p.out = out;
+    p.out_ids = out_ids;
+    p.out_dist = out_dist;
     (s.metric ? v.cs : v.l2)<<<plan.grid, kScanThreads, plan.smem, st>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_exact_scan(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan, const ScanScratch &scr,
-                              const int *only_if_flag, Hit *out, cudaStream_t st) {
+                              const int *only_if_flag, Hit *out, unsigned long long *out_ids, float *out_dist,
+                              cudaStream_t st) {
     ScanParams p = make_params(s, q, k, plan, scr, s.metric ? kExactRBCos : kExactRBL2);
     p.only_if = only_if_flag;
     p.out = out;
+    p.out_ids = out_ids;
+    p.out_dist = out_dist;
     if (s.metric) exact_scan_kernel<kExactRBCos, true><<<plan.grid, kScanThreads, plan.smem, st>>>(p);
     else exact_scan_kernel<kExactRBL2, false><<<plan.grid, kScanThreads, plan.smem, st>>>(p);
     return cudaGetLastError();

@@ -42,12 +42,15 @@ int scan_sm_count(int device);
 ScanPlan make_scan_plan(const ShardView &s, uint32_t k, int sm_count, bool exact);
 size_t scan_cand_bytes(int sm_count);
 
-// f32 scan + exact rerank + guard of ONE query (q: ld floats, device).  Writes k hits to `out`.
+// f32 scan + exact rerank + guard of ONE query (q: ld floats, device).  Writes k hits to `out` and, when
+// out_ids/out_dist are not null, the final ids / distances as well (single-GPU: no merge kernel needed).
 cudaError_t launch_fast_scan(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan,
-                             const ScanScratch &scr, int *status, Hit *out, cudaStream_t st);
+                             const ScanScratch &scr, int *status, Hit *out, unsigned long long *out_ids, float *out_dist,
+                             cudaStream_t st);
 // exact f64 scan of ONE query; if only_if_flag != nullptr the grid returns at once unless *only_if_flag != 0.
 cudaError_t launch_exact_scan(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan,
-                              const ScanScratch &scr, const int *only_if_flag, Hit *out, cudaStream_t st);
+                              const ScanScratch &scr, const int *only_if_flag, Hit *out, unsigned long long *out_ids,
+                              float *out_dist, cudaStream_t st);
 
 // rows [row0, row0+n) of the shard: inv_norm / sq_norm, and flags[0] |= 1 if a value is not finite,
 // |= 2 if a value or norm is outside the range the f32 scan's error bound covers.

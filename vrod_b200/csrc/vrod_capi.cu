@@ -521,6 +521,10 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
     ScanScratch scr{reinterpret_cast<unsigned long long *>(ctx->blk_cand.p),
                     reinterpret_cast<unsigned int *>(ctx_ticket(ctx)), ctx_status(ctx), ctx->dev_counters};
     const bool exact_only = force_exact || c->path == 2 || !c->fast_ok;
+    // single GPU: the scan kernels write the final arrays themselves, no merge launch
+    const bool direct = ctx->world == 1;
+    auto oid = [&](uint32_t qi) { return direct ? reinterpret_cast<unsigned long long *>(d_ids) + (size_t)qi * k : nullptr; };
+    auto odd = [&](uint32_t qi) { return direct ? d_dist + (size_t)qi * k : nullptr; };
     const bool batched = !exact_only && batched_supported(s, b, k) && (c->path == 3 || (c->path == 0 && b >= 64));
     if (batched) {
         BatchedStats bs{};
@@ -535,13 +539,14 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
         for (uint32_t qi = 0; qi < b; ++qi) {
             VROD_CUDA(launch_exact_scan(s, d_q + (size_t)qi * s.ld, k, xp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k,
-                                        ctx->stream));
+                                        oid(qi), odd(qi), ctx->stream));
             ctx->stats.kernel_launches++;
         }
     } else if (exact_only) {
         const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
         for (uint32_t qi = 0; qi < b; ++qi) {
-            VROD_CUDA(launch_exact_scan(s, d_q + (size_t)qi * s.ld, k, xp, scr, nullptr, local + (size_t)qi * k, ctx->stream));
+            VROD_CUDA(launch_exact_scan(s, d_q + (size_t)qi * s.ld, k, xp, scr, nullptr, local + (size_t)qi * k, oid(qi), odd(qi),
+                                        ctx->stream));
             ctx->stats.kernel_launches++;
         }
         ctx->stats.exact_rescans += 0;
@@ -551,9 +556,11 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         for (uint32_t qi = 0; qi < b; ++qi) {
             const float *q = d_q + (size_t)qi * s.ld;
             if (ctx->profiling) VROD_CUDA(cudaEventRecord(ctx->prof_event(), ctx->stream));
-            VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, ctx->stream));
+            VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, oid(qi), odd(qi),
+                                       ctx->stream));
             if (ctx->profiling) VROD_CUDA(cudaEventRecord(ctx->prof_event(), ctx->stream));
-            VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, ctx->stream));
+            VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, oid(qi), odd(qi),
+                                        ctx->stream));
             ctx->stats.kernel_launches += 2;
         }
         ctx->stats.fast_scans += b;
@@ -566,8 +573,10 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         lists = reinterpret_cast<const Hit *>(ctx->hits_all.p);
         g = (uint32_t)ctx->world;
     }
-    VROD_CUDA(launch_merge_hits(lists, g, b, k, reinterpret_cast<unsigned long long *>(d_ids), d_dist, ctx->stream));
-    ctx->stats.kernel_launches++;
+    if (!direct || batched) {
+        VROD_CUDA(launch_merge_hits(lists, g, b, k, reinterpret_cast<unsigned long long *>(d_ids), d_dist, ctx->stream));
+        ctx->stats.kernel_launches++;
+    }
     ctx->stats.searches += b;
     return VROD_OK;
 }
