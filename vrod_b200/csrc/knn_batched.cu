@@ -1,14 +1,626 @@
-// knn_batched.cu -- batched-query path.  Not built yet in this revision: batched_supported() says no
-// and every batch is answered by per-query scans (knn_scan.cu).
+// knn_batched.cu -- batched-query path on the 5th-gen tensor cores (sm_100a: tcgen05 + TMEM + TMA).
+//
+// For a batch of queries the scan IS a dense contraction: S = X . Q^T (rows x queries).  One CTA per SM
+// owns a fixed group of BN = 256 queries (resident in shared memory, 128B-swizzled, loaded once by TMA)
+// and streams its share of the collection's row tiles (BM = 128 rows) through a multi-stage TMA ->
+// mbarrier -> tcgen05.mma (kind::tf32, operands are the stored f32 rows, no second copy) pipeline into a
+// double-buffered TMEM accumulator (2 x 256 columns).  Four epilogue warps read the accumulator with
+// tcgen05.ld and NEVER materialise the rows x queries score matrix: each score is turned into a
+// surrogate v (L2: ||x||^2/2 - dot, cosine: -dot/||x||), compared against the query's running threshold,
+// and the rare survivors are appended to a per-(CTA, query) candidate list in global memory.  When a
+// list nears capacity the epilogue warps prune it (sample-sort-count selection in registers) and tighten
+// the threshold.  batched_finish_kernel then merges the lists of all CTAs of a query, re-evaluates the
+// best k' candidates in canonical f64 (the same arithmetic as the oracle), sorts them by (dist, id) and
+// PROVES with the tf32 error bound that no dropped row can belong to the top k; a query whose proof
+// fails is flagged and answered by the single-query scan (knn_scan.cu).
+//
+// Stands for the reference's SearchCommand::execute (src/command/types.rs:114-119, empty) when the
+// argument carries many queries; nothing of it exists upstream.
 #include "knn_batched.cuh"
+
+#include <cuda.h>
+#include <math.h>
+
+#include "knn_device.cuh"
 
 namespace vrod {
 
-bool batched_supported(const ShardView &, uint32_t, uint32_t) { return false; }
+namespace {
 
-cudaError_t launch_batched_search(const ShardView &, const float *, uint32_t, uint32_t, int, void **, size_t *, int *,
-                                  Hit *, cudaStream_t, BatchedStats *) {
-    return cudaErrorNotSupported;
+constexpr int BM = 128;          // collection rows per tile  (UMMA M, TMEM lanes)
+constexpr int BN = 256;          // queries per CTA           (UMMA N, TMEM columns per accumulator stage)
+constexpr int KS = 32;           // f32 elements per K slab = one 128-byte swizzle row
+constexpr int UMMA_K = 8;        // tf32
+constexpr int CAP = 1024;        // candidate keys per (CTA, query)
+constexpr int PRUNE_AT = CAP - 2 * BM;
+constexpr int kThreads = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int SLAB_A_BYTES = BM * KS * 4;   // 16 KB
+constexpr int SLAB_B_BYTES = BN * KS * 4;   // 32 KB
+constexpr int MAX_SLABS = 4;                // dim <= 128: the query group stays resident (128 KB)
+
+struct BatchedParams {
+    const float *sq_norm, *inv_norm;
+    uint32_t n, b, nslab, stages;
+    uint32_t qgroups, cpg, ntiles;
+    unsigned long long *cand;   // [grid][BN][CAP]
+    int *cnt_out;               // [grid][BN]
+    int *qflags;                // [b] |= 1 when a list could not be pruned (query is rescanned)
+    int kprime;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (1).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;             // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset
+    d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+    return d;
+}
+// kind::tf32, f32 accumulate, A and B K-major, M = 128, N = 256
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct BatchCtl {
+    uint64_t full[8], empty[8], tfull[2], tempty[2], qfull;
+    uint32_t tmem_base;
+    int flag;
+    float thr[BN];
+    int cnt[BN];
+};
+
+// ---- epilogue: prune one (CTA, query) list with one warp ------------------------------------------
+// Keep the entries <= t where t is the smallest sampled key with at least kprime entries at or below
+// it (verified by an exact count), compact them to the front, tighten the threshold.
+__device__ __forceinline__ void prune_list(unsigned long long *cq, int q, BatchCtl *ctl, int kprime, int lane, int *fail) {
+    const int c = ctl->cnt[q];
+    if (c <= kprime) return;
+    unsigned long long key[CAP / 32];
+#pragma unroll
+    for (int i = 0; i < CAP / 32; ++i) {
+        const int idx = lane + 32 * i;
+        key[i] = idx < c ? __ldcg(cq + idx) : kKeyMax;
+    }
+    unsigned long long s = key[0];   // 32 samples (arrival order is unrelated to value), sorted across the warp
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(kFull, s, j);
+            const bool up = (lane & k2) == 0, low = (lane & j) == 0;
+            s = (low == up) ? (s < o ? s : o) : (s < o ? o : s);
+        }
+    int j = (kprime * 32 + c - 1) / c;
+    if (j > 31) j = 31;
+    unsigned long long t;
+    int count;
+    while (true) {
+        t = __shfl_sync(kFull, s, j);
+        count = 0;
+#pragma unroll
+        for (int i = 0; i < CAP / 32; ++i) count += key[i] <= t ? 1 : 0;
+        count = __reduce_add_sync(kFull, count);
+        if (count >= kprime || j == 31) break;
+        ++j;
+    }
+    if (count < kprime) {   // pathological arrival order: give the query up, the scan path answers it
+        if (lane == 0) {
+            *fail = 1;
+            ctl->cnt[q] = 0;
+            ctl->thr[q] = -__int_as_float(0x7f800000);
+        }
+        return;
+    }
+    int base = 0;
+#pragma unroll
+    for (int i = 0; i < CAP / 32; ++i) {
+        const bool keep = key[i] <= t;
+        const unsigned m = __ballot_sync(kFull, keep);
+        if (keep) __stcg(cq + base + __popc(m & ((1u << lane) - 1)), key[i]);
+        base += __popc(m);
+    }
+    if (lane == 0) {
+        ctl->cnt[q] = base;
+        ctl->thr[q] = ord2f((uint32_t)(t >> 32));
+    }
+}
+
+template <bool COS>
+__global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                   const __grid_constant__ CUtensorMap tmQ,
+                                                                   const BatchedParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *q_s = smem;
+    unsigned char *a_s = smem + (size_t)p.nslab * SLAB_B_BYTES;
+    BatchCtl *ctl = reinterpret_cast<BatchCtl *>(a_s + (size_t)p.stages * SLAB_A_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (smem_u32(smem) & 1023u) __trap();          // the 128-byte swizzle needs a 1024-byte aligned base
+    const uint32_t g = blockIdx.x % p.qgroups;     // query group of this CTA
+    const uint32_t member = blockIdx.x / p.qgroups;
+    const uint32_t my_tiles = member < p.ntiles ? (p.ntiles - member + p.cpg - 1) / p.cpg : 0;
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < p.stages; ++s) {
+            mbar_init(&ctl->full[s], 1);
+            mbar_init(&ctl->empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&ctl->tfull[a], 1);
+            mbar_init(&ctl->tempty[a], 4);
+        }
+        mbar_init(&ctl->qfull, 1);
+        ctl->flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < BN; i += kThreads) {
+        const bool live = g * BN + i < p.b;
+        ctl->thr[i] = live ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
+        ctl->cnt[i] = 0;
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = ctl->tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(&ctl->qfull, p.nslab * SLAB_B_BYTES);
+            for (uint32_t s = 0; s < p.nslab; ++s) tma_load_2d(q_s + (size_t)s * SLAB_B_BYTES, &tmQ, (int)(s * KS), (int)(g * BN), &ctl->qfull);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t i = 0; i < my_tiles; ++i) {
+                const uint32_t tile = member + i * p.cpg;
+                for (uint32_t s = 0; s < p.nslab; ++s) {
+                    mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    mbar_expect_tx(&ctl->full[stage], SLAB_A_BYTES);
+                    tma_load_2d(a_s + (size_t)stage * SLAB_A_BYTES, &tmX, (int)(s * KS), (int)(tile * BM), &ctl->full[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            mbar_wait(&ctl->qfull, 0);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t i = 0; i < my_tiles; ++i) {
+                const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
+                mbar_wait(&ctl->tempty[acc], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + acc * BN;
+                for (uint32_t s = 0; s < p.nslab; ++s) {
+                    mbar_wait(&ctl->full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(a_s + (size_t)stage * SLAB_A_BYTES);
+                    const uint32_t b_addr = smem_u32(q_s + (size_t)s * SLAB_B_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < KS / UMMA_K; ++kk) {
+                        tc_mma_tf32(d_tmem, umma_desc_sw128(a_addr + kk * UMMA_K * 4), umma_desc_sw128(b_addr + kk * UMMA_K * 4),
+                                    kIdescTf32, (s | (uint32_t)kk) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&ctl->empty[stage]);   // frees the slab when these MMAs have read it
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&ctl->tfull[acc]);         // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM -> registers -> threshold filter -> candidate lists =====
+        const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
+        const int ew = warp - 2;                     // 0..3
+        unsigned long long *cand = p.cand + (size_t)blockIdx.x * BN * CAP;
+        int fail = 0;
+        for (uint32_t i = 0; i < my_tiles; ++i) {
+            const uint32_t tile = member + i * p.cpg;
+            const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
+            const uint32_t row = tile * BM + quad * 32 + lane;
+            const bool rowok = row < p.n;
+            float hx = 0.f;
+            if (rowok) hx = COS ? __ldg(p.inv_norm + row) : 0.5f * __ldg(p.sq_norm + row);
+            mbar_wait(&ctl->tfull[acc], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 32; ++cb) {
+                uint32_t r[32];
+                tc_ld32(taddr + cb * 32, r);
+                tc_wait_ld();
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 th = *reinterpret_cast<const float4 *>(&ctl->thr[cb * 32 + j4 * 4]);
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float dot = __uint_as_float(r[j4 * 4 + e]);
+                        v[e] = COS ? -(dot * hx) : (hx - dot);
+                    }
+                    const bool c0 = v[0] < th.x, c1 = v[1] < th.y, c2 = v[2] < th.z, c3 = v[3] < th.w;
+                    if (rowok && (c0 | c1 | c2 | c3)) {
+                        const bool cs[4] = {c0, c1, c2, c3};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (cs[e]) {
+                                const int q = cb * 32 + j4 * 4 + e;
+                                const int pos = atomicAdd(&ctl->cnt[q], 1);
+                                if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v[e], row));
+                                else if (g * BN + q < p.b) atomicOr(p.qflags + g * BN + q, 1);   // cannot happen; checked
+                                if (pos >= PRUNE_AT) *(volatile int *)&ctl->flag = 1;
+                            }
+                        }
+                    }
+                }
+            }
+            // accumulator stage drained: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->tempty[acc]);
+            // list maintenance at the tile boundary (all four epilogue warps)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*(volatile int *)&ctl->flag) {
+                for (int q = ew; q < BN; q += 4) {
+                    if (ctl->cnt[q] > PRUNE_AT / 2) prune_list(cand + (size_t)q * CAP, q, ctl, p.kprime, lane, &fail);
+                    if (fail) {
+                        if (lane == 0 && g * BN + q < p.b) atomicOr(p.qflags + g * BN + q, 1);
+                        fail = 0;
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (ew == 0 && lane == 0) ctl->flag = 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int q = ew * 32 + lane; q < BN; q += 128) p.cnt_out[(size_t)blockIdx.x * BN + q] = ctl->cnt[q] < CAP ? ctl->cnt[q] : CAP;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// finish: one CTA per query -- merge the CTA lists, exact rerank, guard, hits
+// -------------------------------------------------------------------------------------------------
+struct FinishParams {
+    const float4 *rows4;
+    const float4 *q4;       // [b][ld4]
+    uint32_t n, ld4, b, k;
+    unsigned long long id_base;
+    int kprime, cap, water;
+    uint32_t qgroups, cpg;
+    const unsigned long long *cand;
+    const int *cnt_in;
+    const int *qflags;
+    const unsigned int *maxnorm_bits;   // max ||x||^2 of the shard, f32 bits
+    int *status;
+    Hit *out;
+    double eps_dot;         // relative error of the tf32 dot product w.r.t. ||x|| ||q||
+};
+
+constexpr int kFinCtl = 128;
+
+template <bool COS>
+__global__ void __launch_bounds__(kScanThreads, 2) batched_finish_kernel(const FinishParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    CandCtl *ctl = reinterpret_cast<CandCtl *>(smem);
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem + kFinCtl);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t qi = blockIdx.x;
+    const uint32_t g = qi / BN, ql = qi % BN;
+    const float4 *q4 = p.q4 + (size_t)qi * p.ld4;
+    if (tid == 0) {
+        cand_reset(ctl);
+        ctl->overflow = 0;
+    }
+    if (warp == 0) {
+        const double nq = canon_row_sum<2>(q4, q4, (int)p.ld4, lane);
+        if (lane == 0) ctl->nq = nq;
+    }
+    __syncthreads();
+    for (uint32_t m = 0; m < p.cpg; ++m) {
+        const uint32_t cta = g + m * p.qgroups;
+        const int c = p.cnt_in[(size_t)cta * BN + ql];
+        const unsigned long long *src = p.cand + ((size_t)cta * BN + ql) * CAP;
+        for (int i0 = 0; i0 < c; i0 += kScanThreads) {
+            const int i = i0 + tid;
+            if (i < c) {
+                const unsigned long long key = __ldcg(src + i);
+                if (key < *(volatile unsigned long long *)&ctl->thrkey) {
+                    const int pos = atomicAdd(&ctl->cnt, 1);
+                    if (pos < p.cap) buf[pos] = key;
+                    else ctl->overflow = 1;
+                }
+            }
+            __syncthreads();
+            if (ctl->cnt > p.water) block_prune(ctl, buf, p.kprime, p.cap, tid);
+        }
+    }
+    __syncthreads();
+    block_prune(ctl, buf, p.kprime, p.cap, tid);
+
+    const int ncand = ctl->cnt;
+    if (tid == 0) ctl->u_val = ncand > 0 ? ord2f((uint32_t)(buf[ncand - 1] >> 32)) : 0.f;
+    __syncthreads();
+    for (int c = warp; c < ncand; c += kScanWarps) {
+        const uint32_t row = (uint32_t)buf[c];
+        const float4 *x = p.rows4 + (size_t)row * p.ld4;
+        float dist;
+        if constexpr (COS) {
+            const double nx = canon_row_sum<2>(x, x, (int)p.ld4, lane);
+            const double dot = canon_row_sum<1>(x, q4, (int)p.ld4, lane);
+            dist = canon_cos_dist(dot, nx, ctl->nq);
+        } else {
+            dist = canon_l2_dist(canon_row_sum<0>(x, q4, (int)p.ld4, lane));
+        }
+        __syncwarp();
+        if (lane == 0) buf[c] = make_key(dist, row);
+    }
+    __syncthreads();
+    {
+        int P = 32;
+        while (P < ncand) P <<= 1;
+        for (int i = ncand + tid; i < P; i += kScanThreads) buf[i] = kKeyMax;
+        __syncthreads();
+        block_bitonic(buf, P, tid);
+    }
+    for (int i = tid; i < (int)p.k; i += kScanThreads) {
+        Hit h;
+        if (i < ncand) {
+            h.id = p.id_base + (uint32_t)buf[i];
+            h.dist = ord2f((uint32_t)(buf[i] >> 32));
+        } else {
+            h.id = kKeyMax;
+            h.dist = __int_as_float(0x7f800000);
+        }
+        h.pad = 0;
+        p.out[(size_t)qi * p.k + i] = h;
+    }
+    if (tid == 0) {
+        int bad = ctl->overflow | (p.qflags[qi] & 1);
+        if (p.n > (uint32_t)ncand) {
+            const int kk = (int)p.k < ncand ? (int)p.k : ncand;
+            const float T = ord2f((uint32_t)(buf[kk - 1] >> 32));
+            const double u = (double)ctl->u_val;
+            const double xn_max = (double)__uint_as_float(*p.maxnorm_bits) * (1.0 + 1.2e-7);
+            const double nq = ctl->nq, nqs = __dsqrt_rn(nq);
+            float lb;
+            if (!(u == u) || fabs(u) > 3.0e38) {
+                lb = -1.f;
+            } else if constexpr (COS) {
+                // v = -dot~ * inv~ ;  |v - (-dot/||x||)| <= (eps_dot + 3*2^-24) * ||q||
+                const double E = (p.eps_dot + 1.8e-7) * nqs;
+                lb = nqs > 0.0 ? __double2float_rd(1.0 + (u - E) / nqs - 1.0e-12) : -1.f;
+            } else {
+                // v = hx~ - dot~ ;  |v - (||x||^2/2 - dot)| <= eps_dot*||x||max*||q|| + 2^-23*(||x||max^2/2 + |u|)
+                const double E = p.eps_dot * __dsqrt_rn(xn_max) * nqs + 1.2e-7 * (0.5 * xn_max + fabs(u));
+                double s = 2.0 * (u - E) + nq;
+                s -= 1.0e-12 * (fabs(s) + nq);
+                lb = s > 0.0 ? __double2float_rd(__dsqrt_rd(s)) : 0.f;
+                if (!(s > 0.0)) lb = -1.f;
+            }
+            if (!(lb > T)) bad = 1;
+            if (kk < (int)p.k) bad = 1;
+        }
+        p.status[qi] = bad ? 1 : 0;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host
+// -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// 2D f32 tensor [rows][ld], box = {32 floats, box_rows}, 128-byte swizzle, zero fill out of bounds
+bool make_map(CUtensorMap *m, const float *base, uint64_t rows, uint32_t ld, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn || rows == 0) return false;
+    cuuint64_t dims[2] = {ld, rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {KS, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int next_pow2i(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+bool batched_supported(const ShardView &s, uint32_t b, uint32_t k) {
+    if (s.n == 0 || b == 0) return false;
+    if ((s.ld + KS - 1) / KS > MAX_SLABS) return false;   // query group must stay resident in shared memory
+    if (k > 120) return false;                            // k' = pow2 >= 2k+16 must stay <= 256 (CAP / 4)
+    return encode_fn() != nullptr;
+}
+
+cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t b, uint32_t k, int sm_count, void **scratch,
+                                  size_t *scratch_bytes, int *status, Hit *out, cudaStream_t st, BatchedStats *stats,
+                                  cudaEvent_t ev_start, cudaEvent_t ev_stop) {
+    const uint32_t nslab = (s.ld + KS - 1) / KS;
+    const uint32_t ntiles = (s.n + BM - 1) / BM;
+    uint32_t qgroups = (b + BN - 1) / BN;
+    // one CTA per SM; query groups beyond the SM count are handled in waves
+    cudaError_t e = cudaSuccess;
+    int kprime = next_pow2i((int)(2 * k + 16));
+    if (kprime < 64) kprime = 64;
+    const double eps_dot = ldexp(1.0, -9) * 1.01 + (double)s.ld * ldexp(1.0, -22);
+
+    for (uint32_t g0 = 0; g0 < qgroups; g0 += (uint32_t)sm_count) {
+        const uint32_t groups = qgroups - g0 < (uint32_t)sm_count ? qgroups - g0 : (uint32_t)sm_count;
+        uint32_t cpg = (uint32_t)sm_count / groups;
+        if (cpg > ntiles) cpg = ntiles;
+        const uint32_t grid = groups * cpg;
+        const uint32_t bq = b - g0 * BN < groups * BN ? b - g0 * BN : groups * BN;   // queries in this wave
+        const float *qw = d_q + (size_t)g0 * BN * s.ld;
+
+        // scratch: cand [grid][BN][CAP] u64, cnt [grid][BN] int, qflags [bq] int, maxnorm is part of the shard
+        const size_t cand_bytes = (size_t)grid * BN * CAP * sizeof(unsigned long long);
+        const size_t cnt_bytes = (size_t)grid * BN * sizeof(int);
+        const size_t flag_bytes = (((size_t)bq * sizeof(int)) + 255) & ~(size_t)255;
+        const size_t need = cand_bytes + cnt_bytes + flag_bytes + 256;
+        if (*scratch_bytes < need) {
+            if (*scratch) cudaFree(*scratch);
+            *scratch = nullptr;
+            *scratch_bytes = 0;
+            e = cudaMalloc(scratch, need);
+            if (e != cudaSuccess) return e;
+            *scratch_bytes = need;
+        }
+        unsigned char *base = reinterpret_cast<unsigned char *>(*scratch);
+        unsigned long long *cand = reinterpret_cast<unsigned long long *>(base);
+        int *cnt = reinterpret_cast<int *>(base + cand_bytes);
+        int *qflags = reinterpret_cast<int *>(base + cand_bytes + cnt_bytes);
+        e = cudaMemsetAsync(qflags, 0, flag_bytes, st);
+        if (e != cudaSuccess) return e;
+
+        CUtensorMap tmX, tmQ;
+        if (!make_map(&tmX, s.rows, s.n, s.ld, BM) || !make_map(&tmQ, qw, bq, s.ld, BN)) return cudaErrorInvalidValue;
+
+        BatchedParams p{};
+        p.sq_norm = s.sq_norm;
+        p.inv_norm = s.inv_norm;
+        p.n = s.n;
+        p.b = bq;
+        p.nslab = nslab;
+        p.qgroups = groups;
+        p.cpg = cpg;
+        p.ntiles = ntiles;
+        p.cand = cand;
+        p.cnt_out = cnt;
+        p.qflags = qflags;
+        p.kprime = kprime;
+        const size_t fixed = (size_t)nslab * SLAB_B_BYTES + sizeof(BatchCtl) + 1024;
+        size_t stages = (227 * 1024 - fixed) / SLAB_A_BYTES;
+        if (stages > 8) stages = 8;
+        if (stages < 2) return cudaErrorInvalidConfiguration;
+        p.stages = (uint32_t)stages;
+        const size_t smem = (size_t)nslab * SLAB_B_BYTES + stages * SLAB_A_BYTES + sizeof(BatchCtl);
+        auto tile_fn = s.metric ? batched_tile_kernel<true> : batched_tile_kernel<false>;
+        e = cudaFuncSetAttribute(tile_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (ev_start && g0 == 0) cudaEventRecord(ev_start, st);
+        tile_fn<<<grid, kThreads, smem, st>>>(tmX, tmQ, p);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (ev_stop && g0 + groups >= qgroups) cudaEventRecord(ev_stop, st);
+
+        FinishParams f{};
+        f.rows4 = reinterpret_cast<const float4 *>(s.rows);
+        f.q4 = reinterpret_cast<const float4 *>(qw);
+        f.n = s.n;
+        f.ld4 = s.ld / 4;
+        f.b = bq;
+        f.k = k;
+        f.id_base = s.id_base;
+        f.kprime = kprime;
+        f.cap = 2048;
+        f.water = f.cap - kScanThreads;
+        f.qgroups = groups;
+        f.cpg = cpg;
+        f.cand = cand;
+        f.cnt_in = cnt;
+        f.qflags = qflags;
+        f.maxnorm_bits = s.maxnorm_bits;
+        f.status = status + (size_t)g0 * BN;
+        f.out = out + (size_t)g0 * BN * k;
+        f.eps_dot = eps_dot;
+        const size_t fsmem = kFinCtl + (size_t)f.cap * sizeof(unsigned long long);
+        auto fin_fn = s.metric ? batched_finish_kernel<true> : batched_finish_kernel<false>;
+        fin_fn<<<bq, kScanThreads, fsmem, st>>>(f);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (stats) {
+            stats->launches += 2;
+            stats->tiles += (uint64_t)ntiles * groups;
+        }
+    }
+    return cudaSuccess;
 }
 
 }  // namespace vrod

@@ -426,8 +426,10 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const float4 *rows4, uin
         bad = __reduce_or_sync(kFull, bad);
         if (lane == 0) {
             inv_norm[row0 + r] = nx > 0.0 ? __double2float_rn(1.0 / sqrt(nx)) : 0.f;
-            sq_norm[row0 + r] = __double2float_rn(nx);
+            const float sqf = __double2float_rn(nx);
+            sq_norm[row0 + r] = sqf;
             if (bad) atomicOr(flags, bad);
+            if (!(bad & 1)) atomicMax(reinterpret_cast<unsigned int *>(flags) + 1, __float_as_uint(sqf));
         }
     }
 }

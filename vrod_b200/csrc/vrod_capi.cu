@@ -127,7 +127,7 @@ struct vrod_ctx {
     std::map<std::string, vrod_collection *> colls;
     // scratch shared by every collection of the context
     DevBuf blk_cand, small, q_pad, q_dev, hits_local, hits_all, out_ids, out_dist, batched;
-    PinBuf q_host, ids_host, dist_host;
+    PinBuf q_host, ids_host, dist_host, status_host;
     unsigned long long *dev_counters = nullptr;  // [0] exact rescans (counted on the device)
     vrod_stats stats{};
     // optional kernel timing (vrod_ctx_profile)
@@ -250,7 +250,7 @@ extern "C" void vrod_ctx_destroy(vrod_ctx *ctx) {
     DevBuf *dev[] = {&ctx->blk_cand, &ctx->small, &ctx->q_pad, &ctx->q_dev, &ctx->hits_local,
                      &ctx->hits_all, &ctx->out_ids, &ctx->out_dist, &ctx->batched};
     for (DevBuf *b : dev) b->release();
-    PinBuf *pin[] = {&ctx->q_host, &ctx->ids_host, &ctx->dist_host};
+    PinBuf *pin[] = {&ctx->q_host, &ctx->ids_host, &ctx->dist_host, &ctx->status_host};
     for (PinBuf *b : pin) b->release();
     cudaFree(ctx->dev_counters);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -502,6 +502,7 @@ static ShardView shard_view(const vrod_collection *c) {
     s.rows = c->rows;
     s.inv_norm = c->inv_norm;
     s.sq_norm = c->sq_norm;
+    s.maxnorm_bits = reinterpret_cast<const unsigned int *>(c->flags) + 1;
     s.n = (uint32_t)c->local;
     s.dim = c->dim;
     s.ld = c->ld;
@@ -528,19 +529,27 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
     const bool batched = !exact_only && batched_supported(s, b, k) && (c->path == 3 || (c->path == 0 && b >= 64));
     if (batched) {
         BatchedStats bs{};
-        vrod_status st = VROD_OK;
+        cudaEvent_t e0 = ctx->profiling ? ctx->prof_event() : nullptr, e1 = ctx->profiling ? ctx->prof_event() : nullptr;
         cudaError_t e = launch_batched_search(s, d_q, b, k, ctx->sms, &ctx->batched.p, &ctx->batched.bytes, ctx_status(ctx),
-                                              local, ctx->stream, &bs);
-        if (e != cudaSuccess) st = fail(VROD_ECUDA, std::string("batched search: ") + cudaGetErrorString(e));
-        if (st != VROD_OK) return st;
+                                              local, ctx->stream, &bs, e0, e1);
+        if (e != cudaSuccess) return fail(VROD_ECUDA, std::string("batched search: ") + cudaGetErrorString(e));
         ctx->stats.kernel_launches += bs.launches;
         ctx->stats.batched_tiles += bs.tiles;
-        // queries whose guard failed are rescanned exactly, decided on the device
+        // queries whose guard failed are answered by the single-query scan.  The count is only known on
+        // the device, so this path synchronises once (the shard-local rescans involve no collective).
+        VROD_CUDA(ctx->status_host.ensure(sizeof(int) * b));
+        int *hs = reinterpret_cast<int *>(ctx->status_host.p);
+        VROD_CUDA(cudaMemcpyAsync(hs, ctx_status(ctx), sizeof(int) * b, cudaMemcpyDeviceToHost, ctx->stream));
+        VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+        const ScanPlan fp = make_scan_plan(s, k, ctx->sms, false);
         const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
         for (uint32_t qi = 0; qi < b; ++qi) {
-            VROD_CUDA(launch_exact_scan(s, d_q + (size_t)qi * s.ld, k, xp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k,
-                                        oid(qi), odd(qi), ctx->stream));
-            ctx->stats.kernel_launches++;
+            if (!hs[qi]) continue;
+            const float *q = d_q + (size_t)qi * s.ld;
+            VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, nullptr, nullptr, ctx->stream));
+            VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, nullptr, nullptr, ctx->stream));
+            ctx->stats.kernel_launches += 2;
+            ctx->stats.fast_scans++;
         }
     } else if (exact_only) {
         const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
