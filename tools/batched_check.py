@@ -31,6 +31,8 @@ cases = [(1000, 128, 0, 10, 4), (50000, 128, 0, 10, 300), (50000, 128, 1, 100, 2
          (20000, 100, 1, 10, 64), (30000, 32, 0, 100, 100), (200000, 128, 0, 100, 1024), (300000, 96, 1, 10, 1000)]
 if len(sys.argv) > 1 and sys.argv[1] == "first":
     cases = cases[:1]
+if len(sys.argv) > 1 and sys.argv[1] == "prof":
+    cases = []
 for cs in cases:
     check(*cs)
 
@@ -51,7 +53,9 @@ def timeit(n, d, metric, k, b, iters=3):
     tf = 2.0 * b * n * d / (kms / kn / 1e3) / 1e12
     print(f"time n={n} d={d} metric={metric} k={k} b={b}: {dt*1e3:.2f} ms/batch {b/dt:.0f} qps; tile kernel {kms/kn:.3f} ms = {tf:.0f} TFLOP/s (tf32); rescanned={s1['fast_scans']-s0['fast_scans']}", flush=True)
     ctx.drop("t")
-if bad == 0 and not (len(sys.argv) > 1 and sys.argv[1] == "first"):
+if len(sys.argv) > 1 and sys.argv[1] == "prof":
+    timeit(1000000, 128, 0, 100, 1024, iters=2)
+elif bad == 0 and not (len(sys.argv) > 1 and sys.argv[1] == "first"):
     timeit(1000000, 128, 0, 10, 256)
     timeit(10000000, 128, 0, 100, 1024)
     timeit(10000000, 128, 1, 10, 1024)

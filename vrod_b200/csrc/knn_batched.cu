@@ -20,6 +20,9 @@
 
 #include <cuda.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "knn_device.cuh"
 
@@ -32,8 +35,10 @@ constexpr int BN = 256;          // queries per CTA           (UMMA N, TMEM colu
 constexpr int KS = 32;           // f32 elements per K slab = one 128-byte swizzle row
 constexpr int UMMA_K = 8;        // tf32
 constexpr int CAP = 1024;        // candidate keys per (CTA, query)
-constexpr int PRUNE_AT = CAP - 2 * BM;
-constexpr int kThreads = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int kCheckEvery = 4;     // tiles between two list-maintenance points of the epilogue warps
+constexpr int PRUNE_AT = CAP - (kCheckEvery + 2) * BM;   // lists longer than this ask for a prune at the next point
+constexpr int kEpiWarps = 8;     // two per TMEM lane quadrant (each takes half of the 256 columns)
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..9 epilogue
 constexpr int SLAB_A_BYTES = BM * KS * 4;   // 16 KB
 constexpr int SLAB_B_BYTES = BN * KS * 4;   // 32 KB
 constexpr int MAX_SLABS = 4;                // dim <= 128: the query group stays resident (128 KB)
@@ -41,11 +46,15 @@ constexpr int MAX_SLABS = 4;                // dim <= 128: the query group stays
 struct BatchedParams {
     const float *sq_norm, *inv_norm;
     uint32_t n, b, nslab, stages;
-    uint32_t qgroups, cpg, ntiles;
+    uint32_t qgroups, cpg;
+    uint32_t tile_begin, tile_end;   // this launch (phase) covers row tiles [tile_begin, tile_end)
+    const float *thr_init;      // [b] thresholds carried over from the previous phase (nullptr: +inf)
     unsigned long long *cand;   // [grid][BN][CAP]
     int *cnt_out;               // [grid][BN]
     int *qflags;                // [b] |= 1 when a list could not be pruned (query is rescanned)
     int kprime;
+    int debug_nocand;           // VROD_BATCHED_DEBUG=nocand: thresholds start at -inf (timing experiments only)
+    long long *dbg;             // VROD_BATCHED_DEBUG set: per-CTA cycle counters [grid][8]
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -104,6 +113,11 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    return r;
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -196,7 +210,8 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
     if (smem_u32(smem) & 1023u) __trap();          // the 128-byte swizzle needs a 1024-byte aligned base
     const uint32_t g = blockIdx.x % p.qgroups;     // query group of this CTA
     const uint32_t member = blockIdx.x / p.qgroups;
-    const uint32_t my_tiles = member < p.ntiles ? (p.ntiles - member + p.cpg - 1) / p.cpg : 0;
+    const uint32_t span = p.tile_end - p.tile_begin;
+    const uint32_t my_tiles = member < span ? (span - member + p.cpg - 1) / p.cpg : 0;
 
     if (tid == 0) {
         for (uint32_t s = 0; s < p.stages; ++s) {
@@ -205,15 +220,16 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&ctl->tfull[a], 1);
-            mbar_init(&ctl->tempty[a], 4);
+            mbar_init(&ctl->tempty[a], kEpiWarps);
         }
         mbar_init(&ctl->qfull, 1);
         ctl->flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < BN; i += kThreads) {
-        const bool live = g * BN + i < p.b;
-        ctl->thr[i] = live ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
+        const bool live = g * BN + i < p.b && !p.debug_nocand;
+        const float t0 = (live && p.thr_init) ? p.thr_init[g * BN + i] : __int_as_float(0x7f800000);
+        ctl->thr[i] = live ? t0 : -__int_as_float(0x7f800000);
         ctl->cnt[i] = 0;
     }
     if (warp == 1) {
@@ -233,28 +249,39 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             mbar_expect_tx(&ctl->qfull, p.nslab * SLAB_B_BYTES);
             for (uint32_t s = 0; s < p.nslab; ++s) tma_load_2d(q_s + (size_t)s * SLAB_B_BYTES, &tmQ, (int)(s * KS), (int)(g * BN), &ctl->qfull);
             uint32_t stage = 0, phase = 0;
+            long long w_empty = 0;
+            const long long tstart = clock64();
             for (uint32_t i = 0; i < my_tiles; ++i) {
-                const uint32_t tile = member + i * p.cpg;
+                const uint32_t tile = p.tile_begin + member + i * p.cpg;
                 for (uint32_t s = 0; s < p.nslab; ++s) {
+                    const long long t0 = clock64();
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    w_empty += clock64() - t0;
                     mbar_expect_tx(&ctl->full[stage], SLAB_A_BYTES);
                     tma_load_2d(a_s + (size_t)stage * SLAB_A_BYTES, &tmX, (int)(s * KS), (int)(tile * BM), &ctl->full[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
+
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             mbar_wait(&ctl->qfull, 0);
             uint32_t stage = 0, phase = 0;
+            long long w_tempty = 0, w_full = 0;
+            const long long tstart = clock64();
             for (uint32_t i = 0; i < my_tiles; ++i) {
                 const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
+                long long t0 = clock64();
                 mbar_wait(&ctl->tempty[acc], aphase ^ 1);
+                w_tempty += clock64() - t0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + acc * BN;
                 for (uint32_t s = 0; s < p.nslab; ++s) {
+                    t0 = clock64();
                     mbar_wait(&ctl->full[stage], phase);
+                    w_full += clock64() - t0;
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(a_s + (size_t)stage * SLAB_A_BYTES);
                     const uint32_t b_addr = smem_u32(q_s + (size_t)s * SLAB_B_BYTES);
@@ -268,74 +295,140 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 }
                 tc_commit(&ctl->tfull[acc]);         // accumulator complete
             }
+            if (p.dbg) {
+
+            }
         }
     } else {
         // ===== epilogue warps: TMEM -> registers -> threshold filter -> candidate lists =====
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
-        const int ew = warp - 2;                     // 0..3
+        const int ew = warp - 2;                     // 0..7
+        const int half = ew >> 2;                    // which 128 of the 256 query columns
         unsigned long long *cand = p.cand + (size_t)blockIdx.x * BN * CAP;
         int fail = 0;
+        long long w_tfull = 0, w_prune = 0, n_slow = 0, w_filter = 0;
+        const long long tstart = clock64();
+        // per-row factor of the NEXT tile is fetched one tile ahead (its global-load latency would otherwise
+        // sit on the critical path of every tile)
+        auto row_factor = [&](uint32_t r) -> float {
+            if (r >= p.n) return 0.f;
+            return COS ? __ldg(p.inv_norm + r) : 0.5f * __ldg(p.sq_norm + r);
+        };
+        float hx_next = my_tiles ? row_factor((p.tile_begin + member) * BM + quad * 32 + lane) : 0.f;
         for (uint32_t i = 0; i < my_tiles; ++i) {
-            const uint32_t tile = member + i * p.cpg;
+            const uint32_t tile = p.tile_begin + member + i * p.cpg;
             const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
             const uint32_t row = tile * BM + quad * 32 + lane;
             const bool rowok = row < p.n;
-            float hx = 0.f;
-            if (rowok) hx = COS ? __ldg(p.inv_norm + row) : 0.5f * __ldg(p.sq_norm + row);
+            const float hx = hx_next;
+            if (i + 1 < my_tiles) hx_next = row_factor((tile + p.cpg) * BM + quad * 32 + lane);
+            long long t0 = p.dbg ? clock64() : 0;
             mbar_wait(&ctl->tfull[acc], aphase);
+            if (p.dbg) w_tfull += clock64() - t0;
             tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * BN;
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * BN + half * (BN / 2);
+            // The loop over column blocks is deliberately NOT unrolled and the rare-candidate path is a
+            // run-time loop: the whole hot body must stay inside the instruction cache (a fully unrolled
+            // version was 130 KB of SASS and ran at ~0.04 IPC on instruction fetch).
+            uint32_t cur[32], nxt[32];
+            tc_ld32(taddr, cur);
+            tc_wait_ld();
 #pragma unroll 1
-            for (int cb = 0; cb < BN / 32; ++cb) {
-                uint32_t r[32];
-                tc_ld32(taddr + cb * 32, r);
-                tc_wait_ld();
+            for (int cb = 0; cb < BN / 64; ++cb) {
+                // software pipeline: the next 32 columns are in flight while this block is filtered
+                if (cb + 1 < BN / 64) tc_ld32(taddr + (cb + 1) * 32, nxt);
+                const int colbase = half * (BN / 2) + cb * 32;
+                uint32_t mask = 0;
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 th = *reinterpret_cast<const float4 *>(&ctl->thr[cb * 32 + j4 * 4]);
-                    float v[4];
+                    const float4 th = *reinterpret_cast<const float4 *>(&ctl->thr[colbase + j4 * 4]);
+                    const float t4[4] = {th.x, th.y, th.z, th.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float dot = __uint_as_float(r[j4 * 4 + e]);
-                        v[e] = COS ? -(dot * hx) : (hx - dot);
+                        const float dot = __uint_as_float(cur[j4 * 4 + e]);
+                        const float v = COS ? -(dot * hx) : (hx - dot);
+                        mask |= (v < t4[e]) ? (1u << (j4 * 4 + e)) : 0u;
                     }
-                    const bool c0 = v[0] < th.x, c1 = v[1] < th.y, c2 = v[2] < th.z, c3 = v[3] < th.w;
-                    if (rowok && (c0 | c1 | c2 | c3)) {
-                        const bool cs[4] = {c0, c1, c2, c3};
+                }
+                if (!rowok) mask = 0;
+                uint32_t colmask = __reduce_or_sync(kFull, mask);
+                if (colmask) {   // warp-uniform: some row of this warp beats some query's threshold
+                    n_slow++;
+                    // transpose the 32x32 candidate bit matrix: lane j learns which rows hit column j and claims
+                    // that many slots of query j's list -- ONE shared-memory atomic instruction for the warp
+                    unsigned mcol = 0;
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (cs[e]) {
-                                const int q = cb * 32 + j4 * 4 + e;
-                                const int pos = atomicAdd(&ctl->cnt[q], 1);
-                                if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v[e], row));
-                                else if (g * BN + q < p.b) atomicOr(p.qflags + g * BN + q, 1);   // cannot happen; checked
-                                if (pos >= PRUNE_AT) *(volatile int *)&ctl->flag = 1;
-                            }
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const unsigned m = __ballot_sync(kFull, (mask >> jj) & 1u);
+                        if (lane == jj) mcol = m;
+                    }
+                    const int c = __popc(mcol);
+                    int base = 0;
+                    if (c) {
+                        base = atomicAdd(&ctl->cnt[colbase + lane], c);
+                        if (base + c > PRUNE_AT) *(volatile int *)&ctl->flag = 1;
+                    }
+                    while (colmask) {   // warp-uniform loop over the columns that have candidates
+                        const int jj = __ffs(colmask) - 1;
+                        colmask &= colmask - 1;
+                        // each lane re-reads its own score of column jj from TMEM (a run-time register index
+                        // would force the block into local memory)
+                        const float dot = __uint_as_float(tc_ld1(taddr + cb * 32 + jj));
+                        tc_wait_ld();
+                        const int b0 = __shfl_sync(kFull, base, jj);
+                        const unsigned m = __shfl_sync(kFull, mcol, jj);
+                        if ((mask >> jj) & 1u) {
+                            const int q = colbase + jj;
+                            const int pos = b0 + __popc(m & ((1u << lane) - 1));
+                            const float v = COS ? -(dot * hx) : (hx - dot);
+                            if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
+                            else if (g * BN + q < p.b) atomicOr(p.qflags + g * BN + q, 1);   // cannot happen; checked
                         }
                     }
+                }
+                if (cb + 1 < BN / 64) {
+                    tc_wait_ld();
+#pragma unroll
+                    for (int jx = 0; jx < 32; ++jx) cur[jx] = nxt[jx];
                 }
             }
             // accumulator stage drained: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->tempty[acc]);
-            // list maintenance at the tile boundary (all four epilogue warps)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // list maintenance every kCheckEvery tiles (all epilogue warps; the lists have room for the
+            // appends of the tiles in between, see PRUNE_AT)
+            if ((i + 1) % kCheckEvery != 0) continue;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (*(volatile int *)&ctl->flag) {
-                for (int q = ew; q < BN; q += 4) {
+                t0 = clock64();
+                for (int q = ew; q < BN; q += kEpiWarps) {
                     if (ctl->cnt[q] > PRUNE_AT / 2) prune_list(cand + (size_t)q * CAP, q, ctl, p.kprime, lane, &fail);
                     if (fail) {
                         if (lane == 0 && g * BN + q < p.b) atomicOr(p.qflags + g * BN + q, 1);
                         fail = 0;
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (ew == 0 && lane == 0) ctl->flag = 0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                w_prune += clock64() - t0;
             }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int q = ew * 32 + lane; q < BN; q += 128) p.cnt_out[(size_t)blockIdx.x * BN + q] = ctl->cnt[q] < CAP ? ctl->cnt[q] : CAP;
+        if (p.dbg && ew == 0 && lane == 0) {
+            p.dbg[blockIdx.x * 8 + 7] = clock64() - tstart;
+            p.dbg[blockIdx.x * 8 + 0] = n_slow;
+            p.dbg[blockIdx.x * 8 + 1] = w_filter;
+            long long tot = 0;
+            for (int q = 0; q < BN; ++q) tot += ctl->cnt[q];
+            p.dbg[blockIdx.x * 8 + 2] = tot;
+            p.dbg[blockIdx.x * 8 + 3] = w_tfull;
+            p.dbg[blockIdx.x * 8 + 4] = w_prune;
+            p.dbg[blockIdx.x * 8 + 5] = 0;
+            p.dbg[blockIdx.x * 8 + 6] = 0;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int q = ew * 32 + lane; q < BN; q += 32 * kEpiWarps) p.cnt_out[(size_t)blockIdx.x * BN + q] = ctl->cnt[q] < CAP ? ctl->cnt[q] : CAP;
     }
     tc_fence_before();
     __syncthreads();
@@ -359,6 +452,11 @@ struct FinishParams {
     const int *cnt_in;
     const int *qflags;
     const unsigned int *maxnorm_bits;   // max ||x||^2 of the shard, f32 bits
+    unsigned long long *glist;          // [b][kprime] best keys over the phases so far (in/out)
+    int *gcnt;                          // [b]
+    float *gthr;                        // [b] out: threshold for the next phase
+    int final_phase;                    // 0: only merge + publish glist/gthr; 1: rerank, guard, hits
+    int first_phase;                    // 1: glist is empty
     int *status;
     Hit *out;
     double eps_dot;         // relative error of the tf32 dot product w.r.t. ||x|| ||q||
@@ -384,6 +482,14 @@ __global__ void __launch_bounds__(kScanThreads, 2) batched_finish_kernel(const F
         if (lane == 0) ctl->nq = nq;
     }
     __syncthreads();
+    if (!p.first_phase) {   // carry the best keys of the earlier phases
+        const int c = p.gcnt[qi];
+        for (int i = tid; i < c; i += kScanThreads) buf[i] = p.glist[(size_t)qi * p.kprime + i];
+        __syncthreads();
+        if (tid == 0) ctl->cnt = c;
+        __syncthreads();
+        block_prune(ctl, buf, p.kprime, p.cap, tid);
+    }
     for (uint32_t m = 0; m < p.cpg; ++m) {
         const uint32_t cta = g + m * p.qgroups;
         const int c = p.cnt_in[(size_t)cta * BN + ql];
@@ -406,6 +512,14 @@ __global__ void __launch_bounds__(kScanThreads, 2) batched_finish_kernel(const F
     block_prune(ctl, buf, p.kprime, p.cap, tid);
 
     const int ncand = ctl->cnt;
+    if (!p.final_phase) {
+        for (int i = tid; i < ncand; i += kScanThreads) p.glist[(size_t)qi * p.kprime + i] = buf[i];
+        if (tid == 0) {
+            p.gcnt[qi] = ncand;
+            p.gthr[qi] = ncand == p.kprime ? ord2f((uint32_t)(buf[ncand - 1] >> 32)) : __int_as_float(0x7f800000);
+        }
+        return;
+    }
     if (tid == 0) ctl->u_val = ncand > 0 ? ord2f((uint32_t)(buf[ncand - 1] >> 32)) : 0.f;
     __syncthreads();
     for (int c = warp; c < ncand; c += kScanWarps) {
@@ -504,6 +618,8 @@ bool make_map(CUtensorMap *m, const float *base, uint64_t rows, uint32_t ld, uin
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+long long *g_dbg_buf = nullptr;
+
 int next_pow2i(int v) {
     int p = 1;
     while (p < v) p <<= 1;
@@ -543,7 +659,8 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         const size_t cand_bytes = (size_t)grid * BN * CAP * sizeof(unsigned long long);
         const size_t cnt_bytes = (size_t)grid * BN * sizeof(int);
         const size_t flag_bytes = (((size_t)bq * sizeof(int)) + 255) & ~(size_t)255;
-        const size_t need = cand_bytes + cnt_bytes + flag_bytes + 256;
+        const size_t glist_bytes = (size_t)bq * kprime * sizeof(unsigned long long);
+        const size_t need = cand_bytes + cnt_bytes + 3 * flag_bytes + glist_bytes + 256;
         if (*scratch_bytes < need) {
             if (*scratch) cudaFree(*scratch);
             *scratch = nullptr;
@@ -556,6 +673,9 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         unsigned long long *cand = reinterpret_cast<unsigned long long *>(base);
         int *cnt = reinterpret_cast<int *>(base + cand_bytes);
         int *qflags = reinterpret_cast<int *>(base + cand_bytes + cnt_bytes);
+        int *gcnt = reinterpret_cast<int *>(base + cand_bytes + cnt_bytes + flag_bytes);
+        float *gthr = reinterpret_cast<float *>(base + cand_bytes + cnt_bytes + 2 * flag_bytes);
+        unsigned long long *glist = reinterpret_cast<unsigned long long *>(base + cand_bytes + cnt_bytes + 3 * flag_bytes);
         e = cudaMemsetAsync(qflags, 0, flag_bytes, st);
         if (e != cudaSuccess) return e;
 
@@ -570,11 +690,18 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         p.nslab = nslab;
         p.qgroups = groups;
         p.cpg = cpg;
-        p.ntiles = ntiles;
         p.cand = cand;
         p.cnt_out = cnt;
         p.qflags = qflags;
         p.kprime = kprime;
+        {
+            const char *dbg = getenv("VROD_BATCHED_DEBUG");
+            p.debug_nocand = dbg && strcmp(dbg, "nocand") == 0;
+            static long long *dbg_buf = nullptr;
+            if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 1024 * 8 * sizeof(long long));
+            p.dbg = dbg ? dbg_buf : nullptr;
+            if (dbg) g_dbg_buf = dbg_buf;
+        }
         const size_t fixed = (size_t)nslab * SLAB_B_BYTES + sizeof(BatchCtl) + 1024;
         size_t stages = (227 * 1024 - fixed) / SLAB_A_BYTES;
         if (stages > 8) stages = 8;
@@ -584,11 +711,6 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         auto tile_fn = s.metric ? batched_tile_kernel<true> : batched_tile_kernel<false>;
         e = cudaFuncSetAttribute(tile_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        if (ev_start && g0 == 0) cudaEventRecord(ev_start, st);
-        tile_fn<<<grid, kThreads, smem, st>>>(tmX, tmQ, p);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        if (ev_stop && g0 + groups >= qgroups) cudaEventRecord(ev_stop, st);
 
         FinishParams f{};
         f.rows4 = reinterpret_cast<const float4 *>(s.rows);
@@ -607,18 +729,54 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         f.cnt_in = cnt;
         f.qflags = qflags;
         f.maxnorm_bits = s.maxnorm_bits;
+        f.glist = glist;
+        f.gcnt = gcnt;
+        f.gthr = gthr;
         f.status = status + (size_t)g0 * BN;
         f.out = out + (size_t)g0 * BN * k;
         f.eps_dot = eps_dot;
         const size_t fsmem = kFinCtl + (size_t)f.cap * sizeof(unsigned long long);
         auto fin_fn = s.metric ? batched_finish_kernel<true> : batched_finish_kernel<false>;
-        fin_fn<<<bq, kScanThreads, fsmem, st>>>(f);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        if (stats) {
-            stats->launches += 2;
-            stats->tiles += (uint64_t)ntiles * groups;
+
+        // Phases over the row tiles: 1 tile per CTA first, then each phase 4x the rows seen so far.  Between
+        // phases the finish kernel merges all CTA lists of a query into its exact global k'-th threshold, so
+        // the candidate rate of a phase is ~k'/rows_seen instead of ~k'/rows_seen_by_one_CTA.
+        uint32_t t_begin = 0, t_end = cpg < ntiles ? cpg : ntiles;
+        bool first = true;
+        if (ev_start && g0 == 0) cudaEventRecord(ev_start, st);
+        while (true) {
+            const bool last = t_end >= ntiles;
+            p.tile_begin = t_begin;
+            p.tile_end = t_end;
+            p.thr_init = first ? nullptr : gthr;
+            tile_fn<<<grid, kThreads, smem, st>>>(tmX, tmQ, p);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            f.first_phase = first ? 1 : 0;
+            f.final_phase = last ? 1 : 0;
+            fin_fn<<<bq, kScanThreads, fsmem, st>>>(f);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            if (stats) stats->launches += 2;
+            if (g_dbg_buf && getenv("VROD_BATCHED_DEBUG")) {
+                static long long h[1024 * 8];
+                cudaStreamSynchronize(st);
+                cudaMemcpy(h, g_dbg_buf, sizeof(long long) * grid * 8, cudaMemcpyDeviceToHost);
+                double a[8] = {0};
+                for (uint32_t c = 0; c < grid; ++c)
+                    for (int jx = 0; jx < 8; ++jx) a[jx] += (double)h[c * 8 + jx] / grid;
+                fprintf(stderr, "[batched dbg] tiles [%u,%u) avg/CTA: warp2 slow entries %.0f, filter cycles %.0f, candidates %.0f | wait_tfull %.0f prune %.0f (%.0f %.0f) "
+                                "| total %.0f | tiles/CTA %u\n",
+                        t_begin, t_end, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], (t_end - t_begin + cpg - 1) / cpg);
+            }
+            if (last) break;
+            first = false;
+            t_begin = t_end;
+            const unsigned long long nxt = (unsigned long long)t_end * 4ull;
+            t_end = nxt >= ntiles ? ntiles : (uint32_t)nxt;
         }
+        if (ev_stop && g0 + groups >= qgroups) cudaEventRecord(ev_stop, st);
+        if (stats) stats->tiles += (uint64_t)ntiles * groups;
     }
     return cudaSuccess;
 }
