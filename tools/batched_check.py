@@ -31,7 +31,7 @@ cases = [(1000, 128, 0, 10, 4), (50000, 128, 0, 10, 300), (50000, 128, 1, 100, 2
          (20000, 100, 1, 10, 64), (30000, 32, 0, 100, 100), (200000, 128, 0, 100, 1024), (300000, 96, 1, 10, 1000)]
 if len(sys.argv) > 1 and sys.argv[1] == "first":
     cases = cases[:1]
-if len(sys.argv) > 1 and sys.argv[1] == "prof":
+if len(sys.argv) > 1 and sys.argv[1].startswith("prof"):
     cases = []
 for cs in cases:
     check(*cs)
@@ -55,6 +55,8 @@ def timeit(n, d, metric, k, b, iters=3):
     ctx.drop("t")
 if len(sys.argv) > 1 and sys.argv[1] == "prof":
     timeit(1000000, 128, 0, 100, 1024, iters=2)
+elif len(sys.argv) > 1 and sys.argv[1] == "prof10":
+    timeit(10000000, 128, 0, 100, 1024, iters=1)
 elif bad == 0 and not (len(sys.argv) > 1 and sys.argv[1] == "first"):
     timeit(1000000, 128, 0, 10, 256)
     timeit(10000000, 128, 0, 100, 1024)

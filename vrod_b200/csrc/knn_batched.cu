@@ -198,6 +198,102 @@ __device__ __forceinline__ void prune_list(unsigned long long *cq, int q, BatchC
     }
 }
 
+// The candidate test, in the one form both passes use (so they agree bit for bit):
+//   L2      dot + thr > hx           (hx = ||x||^2 / 2;  i.e. hx - dot < thr up to one rounding)
+//   cosine  fma(dot, hx, thr) > 0    (hx = 1 / ||x||;    i.e. -dot/||x|| < thr up to one rounding)
+// The one rounding is part of the guard's error budget (batched_finish_kernel).
+template <bool COS>
+__device__ __forceinline__ float cand_w(float dot, float thr, float hx) {
+    return COS ? fmaf(dot, hx, thr) : (dot + thr);
+}
+template <bool COS>
+__device__ __forceinline__ bool cand_hit(float w, float hx) {
+    return COS ? (w > 0.f) : (w > hx);
+}
+
+// Hot filter: 32 scores of one thread (its row x 32 query columns) -> max of the test values.  One add (or
+// fma) and one max per score, four independent chains; no per-score compare, select or branch.
+template <bool COS>
+__device__ __forceinline__ float block_max(const uint32_t (&r)[32], const float *thr, float hx, float m) {
+    float m0 = m, m1 = m, m2 = m, m3 = m;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 th = *reinterpret_cast<const float4 *>(thr + j4 * 4);
+        m0 = fmaxf(m0, cand_w<COS>(__uint_as_float(r[j4 * 4 + 0]), th.x, hx));
+        m1 = fmaxf(m1, cand_w<COS>(__uint_as_float(r[j4 * 4 + 1]), th.y, hx));
+        m2 = fmaxf(m2, cand_w<COS>(__uint_as_float(r[j4 * 4 + 2]), th.z, hx));
+        m3 = fmaxf(m3, cand_w<COS>(__uint_as_float(r[j4 * 4 + 3]), th.w, hx));
+    }
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// Rare pass: the same test per score -> bit mask of the columns this thread's row is a candidate for
+template <bool COS>
+__device__ __forceinline__ uint32_t filter_mask(const uint32_t (&r)[32], const float *thr, float hx) {
+    uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 th = *reinterpret_cast<const float4 *>(thr + j4 * 4);
+        const float t4[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool hit = cand_hit<COS>(cand_w<COS>(__uint_as_float(r[j4 * 4 + e]), t4[e], hx), hx);
+            if (e & 1) m1 |= hit ? (1u << (j4 * 4 + e)) : 0u;
+            else m0 |= hit ? (1u << (j4 * 4 + e)) : 0u;
+        }
+    }
+    return m0 | m1;
+}
+
+// Rare path, kept out of line so that the hot loop stays small: some row of this warp beat some threshold in
+// this accumulator half.  Re-reads the 4 column blocks from TMEM and appends the survivors to the lists.
+template <bool COS>
+__device__ __noinline__ void append_candidates(uint32_t taddr, int col0, uint32_t anycb, float hx, bool rowok, uint32_t row, BatchCtl *ctl,
+                                               unsigned long long *cand, int *qflags, uint32_t qbase, uint32_t b, int lane) {
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 64; ++cb) {
+        if (!(anycb & (1u << cb))) continue;   // warp-uniform
+        uint32_t r[32];
+        tc_ld32(taddr + cb * 32, r);
+        tc_wait_ld();
+        const int colbase = col0 + cb * 32;
+        uint32_t mask = filter_mask<COS>(r, ctl->thr + colbase, hx);
+        if (!rowok) mask = 0;
+        uint32_t colmask = __reduce_or_sync(kFull, mask);
+        if (!colmask) continue;
+        // transpose the 32x32 candidate bit matrix: lane j learns which rows hit column j and claims that many
+        // slots of query j's list -- ONE shared-memory atomic instruction for the whole warp
+        unsigned mcol = 0;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+            const unsigned m = __ballot_sync(kFull, (mask >> jj) & 1u);
+            if (lane == jj) mcol = m;
+        }
+        const int c = __popc(mcol);
+        int base = 0;
+        if (c) {
+            base = atomicAdd(&ctl->cnt[colbase + lane], c);
+            if (base + c > PRUNE_AT) *(volatile int *)&ctl->flag = 1;
+        }
+        while (colmask) {   // warp-uniform loop over the columns that have candidates
+            const int jj = __ffs(colmask) - 1;
+            colmask &= colmask - 1;
+            // each lane re-reads its own score of column jj (a run-time register index would go to local memory)
+            const float dot = __uint_as_float(tc_ld1(taddr + cb * 32 + jj));
+            tc_wait_ld();
+            const int b0 = __shfl_sync(kFull, base, jj);
+            const unsigned m = __shfl_sync(kFull, mcol, jj);
+            if ((mask >> jj) & 1u) {
+                const int q = colbase + jj;
+                const int pos = b0 + __popc(m & ((1u << lane) - 1));
+                const float v = COS ? -(dot * hx) : (hx - dot);
+                if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
+                else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
+            }
+        }
+    }
+}
+
 template <bool COS>
 __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                    const __grid_constant__ CUtensorMap tmQ,
@@ -327,70 +423,32 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             if (p.dbg) w_tfull += clock64() - t0;
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * BN + half * (BN / 2);
-            // The loop over column blocks is deliberately NOT unrolled and the rare-candidate path is a
-            // run-time loop: the whole hot body must stay inside the instruction cache (a fully unrolled
-            // version was 130 KB of SASS and ran at ~0.04 IPC on instruction fetch).
-            uint32_t cur[32], nxt[32];
-            tc_ld32(taddr, cur);
+            // Hot loop: branch-free filter of this warp's 32 rows x 128 columns, 32 columns at a time, the next
+            // TMEM load in flight while the current block is compared.  Not unrolled, rare path out of line:
+            // the body must stay inside the instruction cache (a fully unrolled version was 130 KB of SASS
+            // and ran at ~0.04 IPC on instruction fetch).
+            uint32_t ra[32], rb[32];
+            const float *thr_h = ctl->thr + half * (BN / 2);
+            const float ninf = -__int_as_float(0x7f800000);
+            uint32_t hitcb = 0;   // bit cb: this thread's row beats some threshold among columns [32 cb, 32 cb + 32)
+            tc_ld32(taddr, ra);
             tc_wait_ld();
-#pragma unroll 1
-            for (int cb = 0; cb < BN / 64; ++cb) {
-                // software pipeline: the next 32 columns are in flight while this block is filtered
-                if (cb + 1 < BN / 64) tc_ld32(taddr + (cb + 1) * 32, nxt);
-                const int colbase = half * (BN / 2) + cb * 32;
-                uint32_t mask = 0;
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 th = *reinterpret_cast<const float4 *>(&ctl->thr[colbase + j4 * 4]);
-                    const float t4[4] = {th.x, th.y, th.z, th.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float dot = __uint_as_float(cur[j4 * 4 + e]);
-                        const float v = COS ? -(dot * hx) : (hx - dot);
-                        mask |= (v < t4[e]) ? (1u << (j4 * 4 + e)) : 0u;
-                    }
-                }
-                if (!rowok) mask = 0;
-                uint32_t colmask = __reduce_or_sync(kFull, mask);
-                if (colmask) {   // warp-uniform: some row of this warp beats some query's threshold
-                    n_slow++;
-                    // transpose the 32x32 candidate bit matrix: lane j learns which rows hit column j and claims
-                    // that many slots of query j's list -- ONE shared-memory atomic instruction for the warp
-                    unsigned mcol = 0;
-#pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        const unsigned m = __ballot_sync(kFull, (mask >> jj) & 1u);
-                        if (lane == jj) mcol = m;
-                    }
-                    const int c = __popc(mcol);
-                    int base = 0;
-                    if (c) {
-                        base = atomicAdd(&ctl->cnt[colbase + lane], c);
-                        if (base + c > PRUNE_AT) *(volatile int *)&ctl->flag = 1;
-                    }
-                    while (colmask) {   // warp-uniform loop over the columns that have candidates
-                        const int jj = __ffs(colmask) - 1;
-                        colmask &= colmask - 1;
-                        // each lane re-reads its own score of column jj from TMEM (a run-time register index
-                        // would force the block into local memory)
-                        const float dot = __uint_as_float(tc_ld1(taddr + cb * 32 + jj));
-                        tc_wait_ld();
-                        const int b0 = __shfl_sync(kFull, base, jj);
-                        const unsigned m = __shfl_sync(kFull, mcol, jj);
-                        if ((mask >> jj) & 1u) {
-                            const int q = colbase + jj;
-                            const int pos = b0 + __popc(m & ((1u << lane) - 1));
-                            const float v = COS ? -(dot * hx) : (hx - dot);
-                            if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
-                            else if (g * BN + q < p.b) atomicOr(p.qflags + g * BN + q, 1);   // cannot happen; checked
-                        }
-                    }
-                }
-                if (cb + 1 < BN / 64) {
-                    tc_wait_ld();
-#pragma unroll
-                    for (int jx = 0; jx < 32; ++jx) cur[jx] = nxt[jx];
-                }
+            for (int cb = 0; cb < BN / 64; cb += 2) {
+                tc_ld32(taddr + (cb + 1) * 32, rb);
+                const float wa = block_max<COS>(ra, thr_h + cb * 32, hx, ninf);
+                tc_wait_ld();
+                if (cb + 2 < BN / 64) tc_ld32(taddr + (cb + 2) * 32, ra);
+                const float wb = block_max<COS>(rb, thr_h + (cb + 1) * 32, hx, ninf);
+                if (cb + 2 < BN / 64) tc_wait_ld();
+                hitcb |= (cand_hit<COS>(wa, hx) ? 1u : 0u) << cb;
+                hitcb |= (cand_hit<COS>(wb, hx) ? 1u : 0u) << (cb + 1);
+            }
+            if (!rowok) hitcb = 0;
+            const uint32_t anycb = __reduce_or_sync(kFull, hitcb);
+            if (anycb) {
+                n_slow++;
+                append_candidates<COS>(taddr, half * (BN / 2), anycb, hx, rowok, row, ctl, cand, p.qflags, g * BN, p.b, lane);
             }
             // accumulator stage drained: hand it back to the MMA warp
             tc_fence_before();
@@ -482,30 +540,55 @@ __global__ void __launch_bounds__(kScanThreads, 2) batched_finish_kernel(const F
         if (lane == 0) ctl->nq = nq;
     }
     __syncthreads();
-    if (!p.first_phase) {   // carry the best keys of the earlier phases
-        const int c = p.gcnt[qi];
-        for (int i = tid; i < c; i += kScanThreads) buf[i] = p.glist[(size_t)qi * p.kprime + i];
-        __syncthreads();
-        if (tid == 0) ctl->cnt = c;
-        __syncthreads();
-        block_prune(ctl, buf, p.kprime, p.cap, tid);
+    // offsets of this query's lists (previous global list first, then one list per CTA of the group)
+    int *offs = reinterpret_cast<int *>(buf + p.cap);   // [cpg + 2]
+    if (tid == 0) {
+        int acc = p.first_phase ? 0 : p.gcnt[qi];
+        offs[0] = 0;
+        offs[1] = acc;
+        for (uint32_t m = 0; m < p.cpg; ++m) {
+            acc += p.cnt_in[(size_t)(g + m * p.qgroups) * BN + ql];
+            offs[m + 2] = acc;
+        }
     }
-    for (uint32_t m = 0; m < p.cpg; ++m) {
-        const uint32_t cta = g + m * p.qgroups;
-        const int c = p.cnt_in[(size_t)cta * BN + ql];
-        const unsigned long long *src = p.cand + ((size_t)cta * BN + ql) * CAP;
-        for (int i0 = 0; i0 < c; i0 += kScanThreads) {
-            const int i = i0 + tid;
-            if (i < c) {
-                const unsigned long long key = __ldcg(src + i);
-                if (key < *(volatile unsigned long long *)&ctl->thrkey) {
-                    const int pos = atomicAdd(&ctl->cnt, 1);
-                    if (pos < p.cap) buf[pos] = key;
-                    else ctl->overflow = 1;
-                }
-            }
+    __syncthreads();
+    const int total = offs[p.cpg + 1];
+    if (total <= p.cap) {
+        // common case: everything fits the sort buffer -- gather all lists in parallel, select once
+        for (int i = tid; i < offs[1]; i += kScanThreads) buf[i] = p.glist[(size_t)qi * p.kprime + i];
+        for (uint32_t m = warp; m < p.cpg; m += kScanWarps) {
+            const int o = offs[m + 1], c = offs[m + 2] - o;
+            const unsigned long long *src = p.cand + ((size_t)(g + m * p.qgroups) * BN + ql) * CAP;
+            for (int i = lane; i < c; i += 32) buf[o + i] = __ldcg(src + i);
+        }
+        __syncthreads();
+        if (tid == 0) ctl->cnt = total;
+    } else {
+        if (!p.first_phase) {   // carry the best keys of the earlier phases
+            const int c = p.gcnt[qi];
+            for (int i = tid; i < c; i += kScanThreads) buf[i] = p.glist[(size_t)qi * p.kprime + i];
             __syncthreads();
-            if (ctl->cnt > p.water) block_prune(ctl, buf, p.kprime, p.cap, tid);
+            if (tid == 0) ctl->cnt = c;
+            __syncthreads();
+            block_prune(ctl, buf, p.kprime, p.cap, tid);
+        }
+        for (uint32_t m = 0; m < p.cpg; ++m) {
+            const uint32_t cta = g + m * p.qgroups;
+            const int c = p.cnt_in[(size_t)cta * BN + ql];
+            const unsigned long long *src = p.cand + ((size_t)cta * BN + ql) * CAP;
+            for (int i0 = 0; i0 < c; i0 += kScanThreads) {
+                const int i = i0 + tid;
+                if (i < c) {
+                    const unsigned long long key = __ldcg(src + i);
+                    if (key < *(volatile unsigned long long *)&ctl->thrkey) {
+                        const int pos = atomicAdd(&ctl->cnt, 1);
+                        if (pos < p.cap) buf[pos] = key;
+                        else ctl->overflow = 1;
+                    }
+                }
+                __syncthreads();
+                if (ctl->cnt > p.water) block_prune(ctl, buf, p.kprime, p.cap, tid);
+            }
         }
     }
     __syncthreads();
@@ -569,11 +652,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) batched_finish_kernel(const F
                 lb = -1.f;
             } else if constexpr (COS) {
                 // v = -dot~ * inv~ ;  |v - (-dot/||x||)| <= (eps_dot + 3*2^-24) * ||q||
-                const double E = (p.eps_dot + 1.8e-7) * nqs;
+                const double E = (p.eps_dot + 3.0e-7) * nqs + 1.2e-7 * fabs(u);
                 lb = nqs > 0.0 ? __double2float_rd(1.0 + (u - E) / nqs - 1.0e-12) : -1.f;
             } else {
                 // v = hx~ - dot~ ;  |v - (||x||^2/2 - dot)| <= eps_dot*||x||max*||q|| + 2^-23*(||x||max^2/2 + |u|)
-                const double E = p.eps_dot * __dsqrt_rn(xn_max) * nqs + 1.2e-7 * (0.5 * xn_max + fabs(u));
+                const double E = (p.eps_dot + 2.4e-7) * __dsqrt_rn(xn_max) * nqs + 2.4e-7 * (0.5 * xn_max + fabs(u));
                 double s = 2.0 * (u - E) + nq;
                 s -= 1.0e-12 * (fabs(s) + nq);
                 lb = s > 0.0 ? __double2float_rd(__dsqrt_rd(s)) : 0.f;
@@ -735,7 +818,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         f.status = status + (size_t)g0 * BN;
         f.out = out + (size_t)g0 * BN * k;
         f.eps_dot = eps_dot;
-        const size_t fsmem = kFinCtl + (size_t)f.cap * sizeof(unsigned long long);
+        const size_t fsmem = kFinCtl + (size_t)f.cap * sizeof(unsigned long long) + (cpg + 2) * sizeof(int);
         auto fin_fn = s.metric ? batched_finish_kernel<true> : batched_finish_kernel<false>;
 
         // Phases over the row tiles: 1 tile per CTA first, then each phase 4x the rows seen so far.  Between
