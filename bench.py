@@ -105,41 +105,64 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_leg(rows, dim, metric, k, steps, warmup, budget_s=20.0):
+def cpu_oracle_leg(rows, dim, metric, k, steps, warmup, budget_s=20.0, batch=1):
     """Time the CPU oracle on a bounded sample of the workload: the first `sample` rows of the same
-    seeded collection, one query per step, all host threads.  qps is scaled to the full row count."""
+    seeded collection, min(batch, 4) queries per step, all host threads.  qps is scaled to the full row count."""
     from oracle import oracle as O
     O.build()
     sample = min(rows, max(10_000, (1 << 30) // (dim * 4)))     # <= 1 GiB of rows on the host
+    qb = min(batch, 4)
     X = O.fill(sample, dim, DATA_SEED)
-    Q = O.fill(max(steps + warmup, 1), dim, QUERY_SEED)
+    Q = O.fill(max(steps + warmup, 1) * qb, dim, QUERY_SEED)
     for i in range(warmup):
-        O.search(X, Q[i], k, metric)
+        O.search(X, Q[i * qb:(i + 1) * qb], k, metric)
     t_used, times = 0.0, []
     for i in range(steps):
         t0 = time.perf_counter()
-        O.search(X, Q[warmup + i], k, metric)
+        O.search(X, Q[(warmup + i) * qb:(warmup + i + 1) * qb], k, metric)
         dt = time.perf_counter() - t0
         times.append(dt)
         t_used += dt
         if t_used > budget_s and len(times) >= 3:
             break
-    per_query_full = statistics.mean(times) * (rows / sample)
+    per_query_full = statistics.mean(times) / qb * (rows / sample)
     return {"value": 1.0 / per_query_full, "unit": "queries/s", "cores": O.max_threads(), "kind": "port",
-            "sample": f"first {sample} of {rows} rows x {dim} (same Philox stream), {len(times)} single-query top-{k} "
-                      f"scans by oracle/knn_oracle.c (canonical f64), time scaled by {rows / sample:g} to the full collection",
+            "sample": f"first {sample} of {rows} rows x {dim} (same Philox stream), {len(times)} steps of {qb} top-{k} "
+                      f"queries by oracle/knn_oracle.c (canonical f64), time scaled by {rows / sample:g} to the full collection",
             "ms_per_step_sample": statistics.mean(times) * 1e3, "steps": len(times)}
+
+
+def measure_tf32_peak():
+    """Dense TF32 tensor peak of this GPU, measured the way MEASURED_PEAKS.json measures bf16: torch.matmul on
+    8192^3 with TF32 allowed, best of 10 (burst).  Library GEMM used ONLY as the roofline denominator."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.randn(8192, 8192, device="cuda")
+    b = torch.randn(8192, 8192, device="cuda")
+    for _ in range(3):
+        a @ b
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2 * 8192 ** 3 / (best / 1e3) / 1e12
 
 
 def run_reference(args, rank):
     rows, dim, metric, k, batch, label = WORKLOADS[args.workload]
     if rank != 0:
         return
-    leg = cpu_oracle_leg(rows, dim, metric, k, args.steps, args.warmup, budget_s=60.0)
+    leg = cpu_oracle_leg(rows, dim, metric, k, args.steps, args.warmup, budget_s=60.0, batch=batch)
     line = {"impl": "reference", "metric": METRIC_NAME, "value": leg["value"], "unit": "queries/s", "n_gpus": args.gpus,
             "steps": leg["steps"], "warmup": args.warmup, "ms_per_step": 1e3 / leg["value"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": label, "rows": rows, "dim": dim, "k": k, "batch": 1,
+            "config": {"workload": label, "rows": rows, "dim": dim, "k": k, "batch": batch,
                        "note": "sekulas/vRod's SEARCH body is empty (src/command/types.rs:114-119) and rustc is absent: "
                                "the reference arm is the CPU oracle port of the written semantics, all host threads"},
             "cpu_baseline": {k2: leg[k2] for k2 in ("value", "unit", "cores", "kind", "sample")},
@@ -151,7 +174,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="vrod_b200", choices=["vrod_b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
@@ -213,15 +236,18 @@ def main():
         ctx.synchronize()
 
     def step_resident(i):
-        coll.search_device(q_dev[i * batch].data_ptr(), batch, k, ids_dev.data_ptr(), dist_dev.data_ptr())
+        coll.search_device(q_dev[i * batch:(i + 1) * batch].data_ptr(), batch, k, ids_dev.data_ptr(), dist_dev.data_ptr())
 
     # ---- resident leg: `value` ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # nvidia-smi needs ~0.2 s to print its first line: start it before the warm-up
     for i in range(args.warmup):
         step_resident(i)
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        time.sleep(0.3)
+        sampler.lines.clear()    # keep only what is sampled from here on (the timed region)
     s0 = ctx.stats()
     ctx.profile(True)
     ctx.profile_read()
@@ -267,6 +293,7 @@ def main():
         algo_bytes = 4.0 * local_rows * dim                 # 4*N_local*d per pass, once per batch
         achieved = algo_bytes / (kern_avg_ms / 1e3) / 1e9 if kern_avg_ms > 0 else None
         traffic = ncu_traffic(args.workload if world == 1 else f"{args.workload}@{world}")
+        used_batched = (s1["batched_tiles"] - s0["batched_tiles"]) > 0
         line = {
             "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -287,6 +314,18 @@ def main():
                          "kernel_ms": kern_avg_ms, "launches_timed": int(kern_n)},
             "clocks": clocks,
         }
+        if used_batched:
+            # batched path: a dense contraction, 2*B*N_local*d flops per step; the bracketed time is
+            # the whole phased tile-kernel sequence (tiles + inter-phase merges) of one batch
+            tf32_peak = measure_tf32_peak()
+            flops = 2.0 * batch * local_rows * dim
+            ach = flops / (kern_avg_ms / 1e3) / 1e12
+            line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                                "frac": ach / tf32_peak, "traffic": traffic,
+                                "peak_source": "measured here: torch.matmul 8192^3 TF32, best of 10 (burst); the kernel's MMA kind is tf32",
+                                "kernel": "batched_tile_kernel (tcgen05.mma kind::tf32) + inter-phase batched_finish_kernel",
+                                "algorithmic_flops_per_step": flops, "kernel_ms": kern_avg_ms, "launches_timed": int(kern_n),
+                                "hbm_floor": {"algorithmic_bytes": algo_bytes, "peak_gbs": peak}}
         # e2e h2d: the timed host leg ran after s1 was read; report the per-step bytes the call copies
         line["e2e"]["h2d_bytes_per_step"] = batch * ((dim + 3) // 4 * 4) * 4
         # cheap live check of the last answer: sorted, and the claimed rows sit at the claimed distances
@@ -294,11 +333,11 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             O.build()
-            qlast = from_host[(args.warmup + args.steps - 1) * batch]
+            qlast = from_host[(args.warmup + args.steps - 1) * batch]   # query 0 of the last batch
             for j in (0, k - 1):
                 row = O.fill(1, dim, DATA_SEED, row0=int(last_ids[0, j]))[0]
                 assert np.float32(O.distance(row, qlast, metric)) == last_dist[0, j], "distance check against the oracle failed"
-            line["cpu_baseline"] = {k2: v for k2, v in cpu_oracle_leg(rows, dim, metric, k, 12, 1).items()
+            line["cpu_baseline"] = {k2: v for k2, v in cpu_oracle_leg(rows, dim, metric, k, 12, 1, batch=batch).items()
                                     if k2 in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     barrier()

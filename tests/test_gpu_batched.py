@@ -1,0 +1,95 @@
+"""GPU parity tests of the batched-query path (tcgen05 tf32 tiles + exact f64 rerank + guard), forced with
+set_path(3), against the CPU oracle: bit-exact ids and distances, like the scan path."""
+import numpy as np
+import pytest
+
+from tests.util import assert_same
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # n, d, metric, k, b
+    (1000, 128, 0, 10, 4), (50000, 128, 0, 10, 300), (50000, 128, 1, 100, 256), (100, 128, 0, 10, 7),
+    (20000, 64, 0, 10, 513), (20000, 100, 1, 10, 64), (30000, 32, 0, 100, 100), (200000, 128, 0, 100, 1024),
+    (300000, 96, 1, 10, 1000), (129, 8, 0, 1, 3), (4000, 128, 1, 120, 33),
+]
+
+
+@pytest.mark.parametrize("n,d,metric,k,b", CASES)
+def test_batched_matches_oracle(ctx, oracle, n, d, metric, k, b):
+    c = ctx.create(f"b{n}_{d}_{metric}_{k}", d, metric, n)
+    c.fill_synthetic(n, 300 + d)
+    c.set_path(3)
+    X = oracle.fill(n, d, 300 + d)
+    Q = oracle.fill(b, d, 400 + d)
+    s0 = ctx.stats()
+    ids, dist = c.search(Q, k)
+    s1 = ctx.stats()
+    assert s1["batched_tiles"] > s0["batched_tiles"], "the tensor-core path did not run"
+    assert_same(ids, dist, *oracle.search(X, Q, k, metric), f"n={n} d={d} metric={metric} k={k} b={b}")
+    ctx.drop(c.name)
+
+
+def test_batched_is_chosen_automatically_for_large_batches(ctx, oracle):
+    n, d = 60000, 128
+    c = ctx.create("auto_b", d, 0, n)
+    c.fill_synthetic(n, 5)
+    Q = oracle.fill(128, d, 6)
+    s0 = ctx.stats()
+    ids, dist = c.search(Q, 10)
+    s1 = ctx.stats()
+    assert s1["batched_tiles"] > s0["batched_tiles"] and s1["fast_scans"] == s0["fast_scans"]
+    assert_same(ids, dist, *oracle.search(oracle.fill(n, d, 5), Q, 10, 0))
+    # dims whose query group does not fit shared memory fall back to per-query scans
+    c2 = ctx.create("auto_b2", 768, 1, 3000)
+    c2.fill_synthetic(3000, 7)
+    Q2 = oracle.fill(70, 768, 8)
+    s0 = ctx.stats()
+    ids, dist = c2.search(Q2, 5)
+    s1 = ctx.stats()
+    assert s1["batched_tiles"] == s0["batched_tiles"] and s1["fast_scans"] - s0["fast_scans"] == 70
+    assert_same(ids, dist, *oracle.search(oracle.fill(3000, 768, 7), Q2, 5, 1))
+    ctx.drop("auto_b")
+    ctx.drop("auto_b2")
+
+
+def test_batched_guard_failures_are_rescanned(ctx, oracle):
+    """Blocks of duplicate rows make the tf32 pass unable to prove its candidates for some queries; those
+    queries are re-answered by the scan path and the result is still exact."""
+    n, d, k = 40000, 128, 10
+    X = oracle.fill(n, d, 21)
+    X[1000:1400] = X[7]            # 401 copies of one vector
+    Q = oracle.fill(80, d, 22)
+    Q[3] = X[7]                    # a query sitting exactly on the duplicate block
+    Q[5] = X[7] + np.float32(1e-3)
+    c = ctx.create("dups_b", d, 0, n)
+    c.insert(X)
+    c.set_path(3)
+    s0 = ctx.stats()
+    ids, dist = c.search(Q, k)
+    s1 = ctx.stats()
+    assert_same(ids, dist, *oracle.search(X, Q, k, 0))
+    assert list(ids[3][:2]) == [7, 1000] and dist[3][0] == 0.0
+    assert s1["fast_scans"] > s0["fast_scans"], "the duplicate-block query should have failed the tf32 guard"
+    ctx.drop("dups_b")
+
+
+def test_batched_config2_shape_spot_check(ctx, oracle):
+    """BASELINE configs[2] (10M x 128 L2, 1024 queries, top-100) at full size; the oracle answers a sample of
+    the 1024 queries (~0.5 s each on the host), the rest are checked by size-independent properties."""
+    n, d, k, b = 10_000_000, 128, 100, 1024
+    c = ctx.create("cfg2b", d, 0, n)
+    c.fill_synthetic(n, 0x5EED0001)
+    Q = oracle.fill(b, d, 0x5EED0002)
+    c.set_path(3)
+    ids, dist = c.search(Q, k)
+    assert np.all(np.diff(dist, axis=1) >= 0) and np.all(ids < n)
+    assert all(len(set(r)) == k for r in ids.tolist())
+    X = oracle.fill(n, d, 0x5EED0001)
+    sample = [0, 1, 255, 256, 511, 777, 1023]
+    assert_same(ids[sample], dist[sample], *oracle.search(X, Q[sample], k, 0))
+    # the scan path gives the same rows for other queries (two independent GPU implementations)
+    c.set_path(1)
+    other = [100, 600, 900]
+    sid, sdist = c.search(Q[other], k)
+    assert_same(ids[other], dist[other], sid, sdist)
+    ctx.drop("cfg2b")
