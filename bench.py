@@ -64,45 +64,69 @@ def ncu_traffic(workload):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md clocks line), sampled every
+    50 ms from a background thread through NVML in-process.  (An `nvidia-smi -lms` child process was measured
+    to slow the sampled GPU by ~50 % on an 8-GPU box, which then held back every other rank.)"""
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.samples, self._stop, self._thr = index, [], threading.Event(), None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: match by UUID of the torch device when possible
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            handle = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                u = pynvml.nvmlDeviceGetUUID(h)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u or u.replace("GPU-", "") == uuid:
+                    handle = h
+                    break
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._nv, self._h = pynvml, handle
+        except Exception:
+            self._nv = None
+            return
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        def loop():
+            nv, h = self._nv, self._h
+            while not self._stop.is_set():
+                try:
+                    self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                         nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                                         (getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons)(h)))
+                except Exception:
+                    pass
+                self._stop.wait(0.05)
+
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
+
+    def clear(self):
+        self.samples = []
 
     def stop(self):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=1.0)
+        nv = getattr(self, "_nv", None)
+        sm = [s[0] for s in self.samples]
+        mx = [s[1] for s in self.samples]
+        reasons = set()
+        if nv:
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            for s in self.samples:
+                for name, bit in bits.items():
+                    if s[2] & bit:
+                        reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml in-process, 50 ms period"}
 
 
 def cpu_oracle_leg(rows, dim, metric, k, steps, warmup, budget_s=20.0, batch=1):
@@ -241,13 +265,12 @@ def main():
     # ---- resident leg: `value` ----
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()          # nvidia-smi needs ~0.2 s to print its first line: start it before the warm-up
+        sampler.start()
     for i in range(args.warmup):
         step_resident(i)
     barrier()
     if rank == 0:
-        time.sleep(0.3)
-        sampler.lines.clear()    # keep only what is sampled from here on (the timed region)
+        sampler.clear()          # keep only what is sampled from here on (the timed region)
     s0 = ctx.stats()
     ctx.profile(True)
     ctx.profile_read()
