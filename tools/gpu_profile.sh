@@ -1,14 +1,15 @@
 #!/bin/bash
-# One GPU call: smoke, the bench lines, the ncu launch list and one full capture of the scan kernel.
-set -x
+# One GPU call: ncu launch lists + full captures for the bench workloads (each after a plain run exited 0).
 mkdir -p gpurun_out
-python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1 || { tail -20 gpurun_out/smoke.log; exit 1; }
-python bench.py --steps 50 --warmup 5 > gpurun_out/bench_cfg3.json 2> gpurun_out/bench_cfg3.err || { tail -20 gpurun_out/bench_cfg3.err; exit 1; }
-python bench.py --workload cfg1 --steps 200 --warmup 5 > gpurun_out/bench_cfg1.json 2> gpurun_out/bench_cfg1.err || { tail -20 gpurun_out/bench_cfg1.err; exit 1; }
-CMD="python bench.py --workload ${PROF_WORKLOAD:-cfg1} --steps 5 --warmup 3 --no-cpu-baseline"
-$CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+for W in cfg3 cfg2; do
+  CMD="python bench.py --workload $W --steps 4 --warmup 3 --no-cpu-baseline"
+  $CMD > gpurun_out/plain_$W.log 2>&1 &&
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$W.csv $CMD > gpurun_out/ncu_launches_$W.log 2>&1
+done
+CMD="python bench.py --workload cfg3 --steps 4 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:fast_scan -s 4 -c 2 -f -o gpurun_out/prof_scan $CMD > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/ncu_full.log
-cat gpurun_out/bench_cfg3.json gpurun_out/bench_cfg1.json
+ncu --set full --clock-control none --import-source on -k regex:fast_scan -s 4 -c 1 -f -o gpurun_out/prof_scan_cfg3 $CMD > gpurun_out/ncu_full_cfg3.log 2>&1
+CMD="python bench.py --workload cfg2 --steps 4 --warmup 3 --no-cpu-baseline"
+$CMD > gpurun_out/plain3.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:batched_tile -s 27 -c 1 -f -o gpurun_out/prof_tile_cfg2 $CMD > gpurun_out/ncu_full_cfg2.log 2>&1
+tail -2 gpurun_out/ncu_full_cfg3.log gpurun_out/ncu_full_cfg2.log

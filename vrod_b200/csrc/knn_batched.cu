@@ -406,9 +406,10 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
         const long long tstart = clock64();
         // per-row factor of the NEXT tile is fetched one tile ahead (its global-load latency would otherwise
         // sit on the critical path of every tile)
+        // (the raw value is kept and scaled only when used, so nothing waits on the load here)
         auto row_factor = [&](uint32_t r) -> float {
             if (r >= p.n) return 0.f;
-            return COS ? __ldg(p.inv_norm + r) : 0.5f * __ldg(p.sq_norm + r);
+            return COS ? __ldg(p.inv_norm + r) : __ldg(p.sq_norm + r);
         };
         float hx_next = my_tiles ? row_factor((p.tile_begin + member) * BM + quad * 32 + lane) : 0.f;
         for (uint32_t i = 0; i < my_tiles; ++i) {
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
             const uint32_t row = tile * BM + quad * 32 + lane;
             const bool rowok = row < p.n;
-            const float hx = hx_next;
+            const float hx = COS ? hx_next : 0.5f * hx_next;
             if (i + 1 < my_tiles) hx_next = row_factor((tile + p.cpg) * BM + quad * 32 + lane);
             long long t0 = p.dbg ? clock64() : 0;
             mbar_wait(&ctl->tfull[acc], aphase);
@@ -523,7 +524,7 @@ struct FinishParams {
 constexpr int kFinCtl = 128;
 
 template <bool COS>
-__global__ void __launch_bounds__(kScanThreads, 2) batched_finish_kernel(const FinishParams p) {
+__global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const FinishParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     CandCtl *ctl = reinterpret_cast<CandCtl *>(smem);
     unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem + kFinCtl);
@@ -542,12 +543,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) batched_finish_kernel(const F
     __syncthreads();
     // offsets of this query's lists (previous global list first, then one list per CTA of the group)
     int *offs = reinterpret_cast<int *>(buf + p.cap);   // [cpg + 2]
+    for (uint32_t m = tid; m < p.cpg; m += kScanThreads) offs[m + 2] = p.cnt_in[(size_t)(g + m * p.qgroups) * BN + ql];
     if (tid == 0) {
-        int acc = p.first_phase ? 0 : p.gcnt[qi];
         offs[0] = 0;
-        offs[1] = acc;
+        offs[1] = p.first_phase ? 0 : p.gcnt[qi];
+    }
+    __syncthreads();
+    if (tid == 0) {   // in-place inclusive scan over <= 148 shared-memory words
+        int acc = offs[1];
         for (uint32_t m = 0; m < p.cpg; ++m) {
-            acc += p.cnt_in[(size_t)(g + m * p.qgroups) * BN + ql];
+            acc += offs[m + 2];
             offs[m + 2] = acc;
         }
     }
@@ -605,20 +610,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) batched_finish_kernel(const F
     }
     if (tid == 0) ctl->u_val = ncand > 0 ? ord2f((uint32_t)(buf[ncand - 1] >> 32)) : 0.f;
     __syncthreads();
-    for (int c = warp; c < ncand; c += kScanWarps) {
-        const uint32_t row = (uint32_t)buf[c];
-        const float4 *x = p.rows4 + (size_t)row * p.ld4;
-        float dist;
-        if constexpr (COS) {
-            const double nx = canon_row_sum<2>(x, x, (int)p.ld4, lane);
-            const double dot = canon_row_sum<1>(x, q4, (int)p.ld4, lane);
-            dist = canon_cos_dist(dot, nx, ctl->nq);
-        } else {
-            dist = canon_l2_dist(canon_row_sum<0>(x, q4, (int)p.ld4, lane));
-        }
-        __syncwarp();
-        if (lane == 0) buf[c] = make_key(dist, row);
-    }
+    rerank_candidates<COS>(buf, ncand, p.rows4, q4, (int)p.ld4, ctl->nq, warp, lane);
     __syncthreads();
     {
         int P = 32;

@@ -212,11 +212,74 @@ __device__ __forceinline__ double canon_row_sum(const float4 *x, const float4 *q
     return canon_warp_tree(canon_lane_fold(p));
 }
 
+// NR rows at once (independent loads and fma chains in flight together); MODE as above.
+template <int MODE, int NR>
+__device__ __forceinline__ void canon_rows_sum(const float4 *const (&x)[NR], const float4 *q, int ld4, int lane, double (&out)[NR]) {
+    double p[NR][4];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) p[r][e] = 0.0;
+    for (int c = lane; c < ld4; c += 32) {
+        float4 xv[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) xv[r] = __ldg(x[r] + c);
+        float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (MODE != 2) qv = __ldg(q + c);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            if constexpr (MODE == 0) canon_accum<false>(xv[r], qv, p[r]);
+            else if constexpr (MODE == 1) canon_accum<true>(xv[r], qv, p[r]);
+            else canon_accum<true>(xv[r], xv[r], p[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) out[r] = canon_warp_tree(canon_lane_fold(p[r]));
+}
+
 __device__ __forceinline__ float canon_l2_dist(double sq) { return __double2float_rn(__dsqrt_rn(sq)) + 0.0f; }
 __device__ __forceinline__ float canon_cos_dist(double dot, double nx, double nq) {
     if (nx == 0.0 || nq == 0.0) return 1.0f;
     const double den = __dmul_rn(__dsqrt_rn(nx), __dsqrt_rn(nq));
     return __double2float_rn(__dsub_rn(1.0, __ddiv_rn(dot, den))) + 0.0f;
+}
+
+// Exact re-evaluation of the candidates buf[0..ncand) (approximate keys whose low word is the local row) in the
+// canonical f64 order; each entry is replaced by its exact (f32 dist, row) key.  One warp takes NR candidates
+// at a time so that their row loads are in flight together.
+template <bool COS>
+__device__ __forceinline__ void rerank_candidates(unsigned long long *buf, int ncand, const float4 *rows4, const float4 *q4,
+                                                  int ld4, double nq, int warp, int lane) {
+    constexpr int NR = COS ? 2 : 4;
+    for (int c0 = warp * NR; c0 < ncand; c0 += kScanWarps * NR) {
+        const float4 *x[NR];
+        uint32_t row[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int c = c0 + r < ncand ? c0 + r : c0;
+            row[r] = (uint32_t)buf[c];
+            x[r] = rows4 + (size_t)row[r] * ld4;
+        }
+        float dist[NR];
+        if constexpr (COS) {
+            double nx[NR], dot[NR];
+            canon_rows_sum<2, NR>(x, q4, ld4, lane, nx);
+            canon_rows_sum<1, NR>(x, q4, ld4, lane, dot);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) dist[r] = canon_cos_dist(dot[r], nx[r], nq);
+        } else {
+            double sq[NR];
+            canon_rows_sum<0, NR>(x, q4, ld4, lane, sq);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) dist[r] = canon_l2_dist(sq[r]);
+        }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+                if (c0 + r < ncand) buf[c0 + r] = make_key(dist[r], row[r]);
+        }
+    }
 }
 
 }  // namespace vrod

@@ -19,6 +19,12 @@
 
 namespace vrod {
 
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // -------------------------------------------------------------------------------------------------
 struct ScanParams {
     const float4 *rows4;
@@ -34,6 +40,8 @@ struct ScanParams {
     int *status;
     unsigned long long *counters;
     const int *only_if;
+    unsigned long long *dbg;   // VROD_SCAN_DEBUG: globaltimer stamps [0] first CTA start, [1] last scan-loop end,
+                               // [2] last-CTA merge start, [3] merge end, [4] rerank end, [5] kernel end
     Hit *out;
     unsigned long long *out_ids;  // optional: final [k] ids / distances of this query (single-GPU contexts
     float *out_dist;              // skip the merge kernel)
@@ -66,6 +74,7 @@ __device__ __forceinline__ bool finish_and_merge(CandCtl *ctl, unsigned long lon
     __syncthreads();
     if (!ctl->is_last) return false;
     __threadfence();
+    if (p.dbg && tid == 0) p.dbg[2] = gtimer();
 
     // ---- last CTA: merge gridDim.x sorted lists, walking them by depth ----
     if (tid == 0) {
@@ -168,6 +177,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) fast_scan_kernel(const ScanPa
 #pragma unroll
         for (int c = 0; c < CH; ++c) qv[c] = __ldg(p.q4 + ls + LPR * c);
     }
+    if (p.dbg && tid == 0) atomicMin(p.dbg + 0, gtimer());
     __syncthreads();
 
     const int water = p.water;
@@ -246,7 +256,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) fast_scan_kernel(const ScanPa
         }
     }
 
+    if (p.dbg && tid == 0) atomicMax(p.dbg + 1, gtimer());
     if (!finish_and_merge(ctl, buf, p, tid)) return;
+    if (p.dbg && tid == 0) p.dbg[3] = gtimer();
 
     // ---- last CTA: exact rerank of the survivors in canonical f64, guard, output ----
     const int ncand = ctl->cnt;
@@ -259,21 +271,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) fast_scan_kernel(const ScanPa
         if (lane == 0) ctl->nq = nq;
     }
     __syncthreads();
-    for (int c = warp; c < ncand; c += kScanWarps) {
-        const uint32_t row = (uint32_t)buf[c];
-        const float4 *x = p.rows4 + (size_t)row * p.ld4;
-        float dist;
-        if constexpr (COS) {
-            const double nx = canon_row_sum<2>(x, x, (int)p.ld4, lane);
-            const double dot = canon_row_sum<1>(x, p.q4, (int)p.ld4, lane);
-            dist = canon_cos_dist(dot, nx, ctl->nq);
-        } else {
-            dist = canon_l2_dist(canon_row_sum<0>(x, p.q4, (int)p.ld4, lane));
-        }
-        __syncwarp();
-        if (lane == 0) buf[c] = make_key(dist, row);
-    }
+    rerank_candidates<COS>(buf, ncand, p.rows4, p.q4, (int)p.ld4, ctl->nq, warp, lane);
     __syncthreads();
+    if (p.dbg && tid == 0) p.dbg[4] = gtimer();
     {
         int P = 32;
         while (P < ncand) P <<= 1;
@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) fast_scan_kernel(const ScanPa
     }
     write_hits(buf, ncand, p, tid);
     if (tid == 0) {
+        if (p.dbg) p.dbg[5] = gtimer();
         int bad = ctl->overflow;
         if (p.n > (uint32_t)ncand) {
             // rows were dropped: every dropped row has surrogate >= u_val.  Bound its exact distance
@@ -600,6 +601,15 @@ ScanPlan make_scan_plan(const ShardView &s, uint32_t k, int sm_count, bool exact
 
 size_t scan_cand_bytes(int sm_count) { return (size_t)sm_count * 8 * 2048 * sizeof(unsigned long long); }
 
+unsigned long long *g_scan_dbg = nullptr;   // set by scan_debug_enable() (development aid)
+
+unsigned long long *scan_debug_enable() {
+    if (!g_scan_dbg) {
+        cudaMalloc(&g_scan_dbg, 64);
+    }
+    return g_scan_dbg;
+}
+
 static ScanParams make_params(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan, const ScanScratch &scr,
                               int rows_per_iter) {
     ScanParams p{};
@@ -623,6 +633,7 @@ static ScanParams make_params(const ShardView &s, const float *q, uint32_t k, co
     p.ticket = scr.ticket;
     p.counters = scr.counters;
     p.eps = plan.eps;
+    p.dbg = g_scan_dbg;
     return p;
 }
 

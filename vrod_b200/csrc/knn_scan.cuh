@@ -40,6 +40,7 @@ struct Hit {
 };
 
 int scan_sm_count(int device);
+unsigned long long *scan_debug_enable();   // development aid: device buffer of 8 globaltimer stamps (VROD_SCAN_DEBUG)
 ScanPlan make_scan_plan(const ShardView &s, uint32_t k, int sm_count, bool exact);
 size_t scan_cand_bytes(int sm_count);
 

@@ -10,6 +10,8 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <nccl.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -564,9 +566,24 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
         for (uint32_t qi = 0; qi < b; ++qi) {
             const float *q = d_q + (size_t)qi * s.ld;
+            static const bool scan_dbg = getenv("VROD_SCAN_DEBUG") != nullptr;
+            unsigned long long *dbgbuf = nullptr;
+            if (scan_dbg) {
+                dbgbuf = scan_debug_enable();
+                const unsigned long long init[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};
+                cudaMemcpyAsync(dbgbuf, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream);
+            }
             if (ctx->profiling) VROD_CUDA(cudaEventRecord(ctx->prof_event(), ctx->stream));
             VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, oid(qi), odd(qi),
                                        ctx->stream));
+            if (scan_dbg) {
+                unsigned long long h[8];
+                cudaStreamSynchronize(ctx->stream);
+                cudaMemcpy(h, dbgbuf, sizeof(h), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[scan dbg] scan loops %.1f us | wait+ticket %.1f | merge %.1f | rerank %.1f | sort+write %.1f | total %.1f us\n",
+                        (h[1] - h[0]) / 1e3, (h[2] - h[1]) / 1e3, (h[3] - h[2]) / 1e3, (h[4] - h[3]) / 1e3, (h[5] - h[4]) / 1e3,
+                        (h[5] - h[0]) / 1e3);
+            }
             if (ctx->profiling) VROD_CUDA(cudaEventRecord(ctx->prof_event(), ctx->stream));
             VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, oid(qi), odd(qi),
                                         ctx->stream));
