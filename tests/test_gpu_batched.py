@@ -11,6 +11,8 @@ CASES = [  # n, d, metric, k, b
     (1000, 128, 0, 10, 4), (50000, 128, 0, 10, 300), (50000, 128, 1, 100, 256), (100, 128, 0, 10, 7),
     (20000, 64, 0, 10, 513), (20000, 100, 1, 10, 64), (30000, 32, 0, 100, 100), (200000, 128, 0, 100, 1024),
     (300000, 96, 1, 10, 1000), (129, 8, 0, 1, 3), (4000, 128, 1, 120, 33),
+    # dims above 128: the query slabs are streamed with the row slabs
+    (30000, 384, 1, 10, 256), (20000, 768, 1, 10, 70), (9000, 1536, 0, 100, 300), (15000, 200, 0, 10, 40), (5000, 260, 1, 5, 9),
 ]
 
 
@@ -39,14 +41,14 @@ def test_batched_is_chosen_automatically_for_large_batches(ctx, oracle):
     s1 = ctx.stats()
     assert s1["batched_tiles"] > s0["batched_tiles"] and s1["fast_scans"] == s0["fast_scans"]
     assert_same(ids, dist, *oracle.search(oracle.fill(n, d, 5), Q, 10, 0))
-    # dims whose query group does not fit shared memory fall back to per-query scans
+    # small batches stay on the per-query scan
     c2 = ctx.create("auto_b2", 768, 1, 3000)
     c2.fill_synthetic(3000, 7)
-    Q2 = oracle.fill(70, 768, 8)
+    Q2 = oracle.fill(20, 768, 8)
     s0 = ctx.stats()
     ids, dist = c2.search(Q2, 5)
     s1 = ctx.stats()
-    assert s1["batched_tiles"] == s0["batched_tiles"] and s1["fast_scans"] - s0["fast_scans"] == 70
+    assert s1["batched_tiles"] == s0["batched_tiles"] and s1["fast_scans"] - s0["fast_scans"] == 20
     assert_same(ids, dist, *oracle.search(oracle.fill(3000, 768, 7), Q2, 5, 1))
     ctx.drop("auto_b")
     ctx.drop("auto_b2")

@@ -59,6 +59,10 @@ elif len(sys.argv) > 1 and sys.argv[1] == "prof10":
     timeit(10000000, 128, 0, 100, 1024, iters=1)
 elif bad == 0 and not (len(sys.argv) > 1 and sys.argv[1] == "first"):
     timeit(1000000, 128, 0, 10, 256)
+    timeit(1000000, 64, 0, 10, 256)
+    timeit(1000000, 384, 1, 10, 256)
+    timeit(1000000, 768, 1, 10, 256)
+    timeit(1000000, 1536, 0, 100, 256)
     timeit(10000000, 128, 0, 100, 1024)
     timeit(10000000, 128, 1, 10, 1024)
 print("bad =", bad)

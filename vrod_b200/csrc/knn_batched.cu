@@ -53,6 +53,7 @@ struct BatchedParams {
     int *cnt_out;               // [grid][BN]
     int *qflags;                // [b] |= 1 when a list could not be pruned (query is rescanned)
     int kprime;
+    int stream_q;               // 1: the query slabs are streamed with the row slabs (dim > 128: the group does not fit)
     int debug_nocand;           // VROD_BATCHED_DEBUG=nocand: thresholds start at -inf (timing experiments only)
     long long *dbg;             // VROD_BATCHED_DEBUG set: per-CTA cycle counters [grid][8]
 };
@@ -299,9 +300,11 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                                                                    const __grid_constant__ CUtensorMap tmQ,
                                                                    const BatchedParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    // resident mode: [nslab query slabs][stages row slabs]; streamed mode: [stages x (row slab + query slab)]
+    const uint32_t stage_bytes = p.stream_q ? (SLAB_A_BYTES + SLAB_B_BYTES) : SLAB_A_BYTES;
     unsigned char *q_s = smem;
-    unsigned char *a_s = smem + (size_t)p.nslab * SLAB_B_BYTES;
-    BatchCtl *ctl = reinterpret_cast<BatchCtl *>(a_s + (size_t)p.stages * SLAB_A_BYTES);
+    unsigned char *a_s = p.stream_q ? smem : smem + (size_t)p.nslab * SLAB_B_BYTES;
+    BatchCtl *ctl = reinterpret_cast<BatchCtl *>(a_s + (size_t)p.stages * stage_bytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (smem_u32(smem) & 1023u) __trap();          // the 128-byte swizzle needs a 1024-byte aligned base
     const uint32_t g = blockIdx.x % p.qgroups;     // query group of this CTA
@@ -342,8 +345,10 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            mbar_expect_tx(&ctl->qfull, p.nslab * SLAB_B_BYTES);
-            for (uint32_t s = 0; s < p.nslab; ++s) tma_load_2d(q_s + (size_t)s * SLAB_B_BYTES, &tmQ, (int)(s * KS), (int)(g * BN), &ctl->qfull);
+            if (!p.stream_q) {
+                mbar_expect_tx(&ctl->qfull, p.nslab * SLAB_B_BYTES);
+                for (uint32_t s = 0; s < p.nslab; ++s) tma_load_2d(q_s + (size_t)s * SLAB_B_BYTES, &tmQ, (int)(s * KS), (int)(g * BN), &ctl->qfull);
+            }
             uint32_t stage = 0, phase = 0;
             long long w_empty = 0;
             const long long tstart = clock64();
@@ -353,8 +358,10 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                     const long long t0 = clock64();
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
                     w_empty += clock64() - t0;
-                    mbar_expect_tx(&ctl->full[stage], SLAB_A_BYTES);
-                    tma_load_2d(a_s + (size_t)stage * SLAB_A_BYTES, &tmX, (int)(s * KS), (int)(tile * BM), &ctl->full[stage]);
+                    mbar_expect_tx(&ctl->full[stage], stage_bytes);
+                    tma_load_2d(a_s + (size_t)stage * stage_bytes, &tmX, (int)(s * KS), (int)(tile * BM), &ctl->full[stage]);
+                    if (p.stream_q)
+                        tma_load_2d(a_s + (size_t)stage * stage_bytes + SLAB_A_BYTES, &tmQ, (int)(s * KS), (int)(g * BN), &ctl->full[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -363,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            mbar_wait(&ctl->qfull, 0);
+            if (!p.stream_q) mbar_wait(&ctl->qfull, 0);
             uint32_t stage = 0, phase = 0;
             long long w_tempty = 0, w_full = 0;
             const long long tstart = clock64();
@@ -379,8 +386,8 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                     mbar_wait(&ctl->full[stage], phase);
                     w_full += clock64() - t0;
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(a_s + (size_t)stage * SLAB_A_BYTES);
-                    const uint32_t b_addr = smem_u32(q_s + (size_t)s * SLAB_B_BYTES);
+                    const uint32_t a_addr = smem_u32(a_s + (size_t)stage * stage_bytes);
+                    const uint32_t b_addr = p.stream_q ? a_addr + SLAB_A_BYTES : smem_u32(q_s + (size_t)s * SLAB_B_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < KS / UMMA_K; ++kk) {
                         tc_mma_tf32(d_tmem, umma_desc_sw128(a_addr + kk * UMMA_K * 4), umma_desc_sw128(b_addr + kk * UMMA_K * 4),
@@ -705,7 +712,7 @@ int next_pow2i(int v) {
 
 bool batched_supported(const ShardView &s, uint32_t b, uint32_t k) {
     if (s.n == 0 || b == 0) return false;
-    if ((s.ld + KS - 1) / KS > MAX_SLABS) return false;   // query group must stay resident in shared memory
+    if (s.ld > 4096) return false;
     if (k > 120) return false;                            // k' = pow2 >= 2k+16 must stay <= 256 (CAP / 4)
     return encode_fn() != nullptr;
 }
@@ -777,12 +784,16 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             p.dbg = dbg ? dbg_buf : nullptr;
             if (dbg) g_dbg_buf = dbg_buf;
         }
-        const size_t fixed = (size_t)nslab * SLAB_B_BYTES + sizeof(BatchCtl) + 1024;
-        size_t stages = (227 * 1024 - fixed) / SLAB_A_BYTES;
+        // dim <= 128: the query group is resident (nslab x 32 KB) and only row slabs stream; larger dims stream the
+        // query slab next to every row slab (48 KB stages, L2-bandwidth bound: DESIGN.md)
+        p.stream_q = nslab > MAX_SLABS ? 1 : 0;
+        const size_t resident = p.stream_q ? 0 : (size_t)nslab * SLAB_B_BYTES;
+        const size_t stage_bytes = p.stream_q ? (SLAB_A_BYTES + SLAB_B_BYTES) : SLAB_A_BYTES;
+        size_t stages = (227 * 1024 - resident - sizeof(BatchCtl) - 1024) / stage_bytes;
         if (stages > 8) stages = 8;
         if (stages < 2) return cudaErrorInvalidConfiguration;
         p.stages = (uint32_t)stages;
-        const size_t smem = (size_t)nslab * SLAB_B_BYTES + stages * SLAB_A_BYTES + sizeof(BatchCtl);
+        const size_t smem = resident + stages * stage_bytes + sizeof(BatchCtl);
         auto tile_fn = s.metric ? batched_tile_kernel<true> : batched_tile_kernel<false>;
         e = cudaFuncSetAttribute(tile_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
