@@ -122,8 +122,18 @@ VROD_API vrod_status vrod_collection_info(vrod_collection *c, uint32_t *dim, vro
 
 /* INSERT / BULKINSERT: append n rows (row-major n x dim f32).  Ids are insertion indices; the id of
  * the first appended row is written to *first_id (may be NULL).  In a sharded context every rank
- * passes the same rows and keeps the part that falls into its range. */
+ * passes the same rows and keeps the part that falls into its range.  A single-GPU collection that is full
+ * grows (capacity doubles, rows are moved device-to-device); a sharded one returns VROD_ENOMEM. */
 VROD_API vrod_status vrod_collection_insert(vrod_collection *c, const float *rows, uint64_t n, uint64_t *first_id);
+
+/* Persistence (the step after INSERT; the reference's Database::load is a todo!(), src/database/mod.rs:19-21).
+ * vrod_collection_save writes this collection to `path`: a 64-byte header ("VRODCOL1", dim, metric, count)
+ * followed by count x dim f32 rows, row-major, unpadded, little-endian.  Single-GPU contexts only.
+ * vrod_collection_load creates collection `name` from such a file; capacity_rows = 0 means "as many as the
+ * file holds".  In a sharded context every rank reads only the rows of its own id range. */
+VROD_API vrod_status vrod_collection_save(vrod_collection *c, const char *path);
+VROD_API vrod_status vrod_collection_load(vrod_ctx *ctx, const char *name, const char *path, uint64_t capacity_rows,
+                                          vrod_collection **out);
 
 /* Append n synthetic rows generated ON THE DEVICE: element (i, j) of a collection is
  * u2f(philox4x32_10(counter = (i*dim + j) >> 2, key = seed)[(i*dim + j) & 3]), uniform [-1, 1);

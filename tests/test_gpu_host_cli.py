@@ -63,3 +63,38 @@ def test_cli_end_to_end(tmp_path, oracle, metric):
     assert "k must be an integer in [1, 1024]" in r.stderr
     assert "query has 3 components, collection has 24" in r.stderr
     assert "no collection 'nope'" in r.stderr
+
+
+def test_database_directory_persists_across_processes(tmp_path, oracle):
+    """--init-database, then one command per process with the reference's flags (-d -c -e -a): the collection
+    created and filled by earlier processes is loaded from DIR and searched by a later one."""
+    n, d, k = 300, 16, 5
+    X = oracle.fill(n, d, 7)
+    recs = tmp_path / "recs.txt"
+    with open(recs, "w") as f:
+        for i in range(n):
+            f.write("%s;word%d\n" % (",".join("%.9g" % x for x in X[i]), i))
+    db = tmp_path / "mydb"
+
+    def cli(*args):
+        return subprocess.run([CLI, *args], capture_output=True, text=True, timeout=300)
+
+    assert cli("-i", str(tmp_path), "-n", "mydb").returncode == 0
+    r = cli("-d", str(db), "-e", "CREATE", "-a", "words;;cosine")
+    assert r.returncode == 0 and "created words" in r.stdout, r.stderr
+    r = cli("-d", str(db), "-c", "words", "-e", "BULKINSERT", "-a", str(recs))
+    assert r.returncode == 0 and f"inserted {n} records" in r.stdout, r.stderr
+    assert sorted(os.listdir(db)) == ["vr_config", "vr_wal", "words.payloads", "words.vrc"]
+    q = oracle.fill(1, d, 8)[0]
+    r = cli("--database", str(db), "--collection", "words", "--execute", "search", "--command-arg",
+            "%d;%s" % (k, ",".join("%.9g" % x for x in q)))
+    assert r.returncode == 0, r.stderr
+    ids, dist, words = parse_hits(r.stdout.splitlines())
+    rid, rdist = oracle.search(X, q, k, 1)
+    assert_same(ids, dist, rid[0], rdist[0], "SEARCH after reload")
+    assert words == [f"word{int(i)}" for i in rid[0]]
+    r = cli("-d", str(db), "-e", "LISTCOLLECTIONS")
+    assert r.stdout.split() == ["words"]
+    assert cli("-d", str(db), "-e", "DROP", "-a", "words").returncode == 0
+    assert sorted(os.listdir(db)) == ["vr_config", "vr_wal"]
+    assert cli("-d", str(db), "-e", "LISTCOLLECTIONS").stdout.strip() == ""

@@ -247,3 +247,30 @@ def test_k_up_to_the_maximum(ctx, oracle):
         for k in (500, 1024):
             assert_same(*c.search(Q, k), *oracle.search(X, Q, k, metric), f"k={k}")
         ctx.drop(c.name)
+
+
+def test_collection_grows_and_round_trips_through_a_file(ctx, oracle, tmp_path):
+    """N1/N4: a full single-GPU collection grows on insert; save + load reproduce it bit for bit."""
+    X = oracle.fill(9000, 48, 51)
+    Q = oracle.fill(3, 48, 52)
+    c = ctx.create("grow", 48, 1, 1000)            # capacity 1000, 9000 rows arrive in four inserts
+    for lo, hi in [(0, 900), (900, 1000), (1000, 4097), (4097, 9000)]:
+        assert c.insert(X[lo:hi]) == lo
+    info = c.info()
+    assert info["count"] == 9000 and info["capacity"] >= 9000
+    want = oracle.search(X, Q, 10, 1)
+    assert_same(*c.search(Q, 10), *want)
+    path = tmp_path / "grow.vrc"
+    c.save(path)
+    assert os.path.getsize(path) == 64 + 9000 * 48 * 4
+    c2 = ctx.load("grow2", path)
+    assert c2.info() == {"dim": 48, "metric": 1, "count": 9000, "capacity": 9000}
+    assert np.array_equal(c2.read_rows(0, 9000), X)
+    assert_same(*c2.search(Q, 10), *want)
+    with open(tmp_path / "junk.vrc", "wb") as f:
+        f.write(b"not a collection")
+    from vrod_b200 import ffi
+    with pytest.raises(ffi.VrodError):
+        ctx.load("junk", tmp_path / "junk.vrc")
+    ctx.drop("grow")
+    ctx.drop("grow2")

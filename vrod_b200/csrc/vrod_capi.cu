@@ -436,6 +436,34 @@ static vrod_status finish_append(vrod_collection *c, uint64_t loc0, uint64_t cnt
     return VROD_OK;
 }
 
+// single-GPU collections: make room for at least `need` rows (capacity at least doubles)
+static vrod_status collection_grow(vrod_collection *c, uint64_t need) {
+    vrod_ctx *ctx = c->ctx;
+    uint64_t cap = c->capacity * 2 > need ? c->capacity * 2 : need;
+    if (cap >= 0xFFFFFFFFull) cap = 0xFFFFFFFEull;
+    if (cap < need) return fail(VROD_ENOMEM, "more than 2^32-2 rows on one GPU");
+    float *rows = nullptr, *inv = nullptr, *sq = nullptr;
+    cudaError_t e = cudaMalloc(&rows, (size_t)cap * c->ld * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&inv, (size_t)cap * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&sq, (size_t)cap * sizeof(float));
+    if (e == cudaSuccess && c->local) {
+        e = cudaMemcpyAsync(rows, c->rows, (size_t)c->local * c->ld * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(inv, c->inv_norm, (size_t)c->local * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sq, c->sq_norm, (size_t)c->local * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(rows); cudaFree(inv); cudaFree(sq);
+        return fail(e == cudaErrorMemoryAllocation ? VROD_ENOMEM : VROD_ECUDA, std::string("growing the collection: ") + cudaGetErrorString(e));
+    }
+    cudaFree(c->rows); cudaFree(c->inv_norm); cudaFree(c->sq_norm);
+    c->rows = rows; c->inv_norm = inv; c->sq_norm = sq;
+    c->capacity = cap;
+    c->shard_rows = cap;
+    return VROD_OK;
+}
+
 extern "C" vrod_status vrod_collection_insert(vrod_collection *c, const float *rows, uint64_t n, uint64_t *first_id) {
     if (!c) return fail(VROD_EINVAL, "collection is NULL");
     if (n == 0) {
@@ -443,9 +471,13 @@ extern "C" vrod_status vrod_collection_insert(vrod_collection *c, const float *r
         return VROD_OK;
     }
     if (!rows) return fail(VROD_EINVAL, "rows is NULL");
-    if (c->count + n > c->capacity) return fail(VROD_ENOMEM, "collection capacity exceeded");
     vrod_ctx *ctx = c->ctx;
     VROD_CUDA(cudaSetDevice(ctx->device));
+    if (c->count + n > c->capacity) {
+        if (ctx->world > 1) return fail(VROD_ENOMEM, "collection capacity exceeded (sharded collections do not grow)");
+        vrod_status gs = collection_grow(c, c->count + n);
+        if (gs != VROD_OK) return gs;
+    }
     uint64_t loc0, cnt, off;
     shard_overlap(c, c->count, n, &loc0, &cnt, &off);
     if (cnt) {
@@ -493,6 +525,86 @@ extern "C" vrod_status vrod_collection_read_rows(vrod_collection *c, uint64_t ro
                                 (size_t)c->ld * sizeof(float), (size_t)c->dim * sizeof(float), (size_t)n,
                                 cudaMemcpyDeviceToHost, ctx->stream));
     VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VROD_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// persistence
+// -------------------------------------------------------------------------------------------------
+struct ColFileHeader {
+    char magic[8];        // "VRODCOL1"
+    uint32_t dim, metric;
+    uint64_t count;
+    uint8_t reserved[40];
+};
+static_assert(sizeof(ColFileHeader) == 64, "header is 64 bytes");
+constexpr uint64_t kIoChunkRows = 1u << 16;
+
+extern "C" vrod_status vrod_collection_save(vrod_collection *c, const char *path) {
+    if (!c || !path) return fail(VROD_EINVAL, "NULL argument");
+    vrod_ctx *ctx = c->ctx;
+    if (ctx->world > 1) return fail(VROD_EINVAL, "vrod_collection_save: single-GPU contexts only");
+    VROD_CUDA(cudaSetDevice(ctx->device));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(VROD_EINVAL, std::string("cannot open '") + path + "' for writing");
+    ColFileHeader h{};
+    memcpy(h.magic, "VRODCOL1", 8);
+    h.dim = c->dim;
+    h.metric = (uint32_t)c->metric;
+    h.count = c->count;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+    std::vector<float> buf((size_t)kIoChunkRows * c->dim);
+    for (uint64_t r0 = 0; ok && r0 < c->local; r0 += kIoChunkRows) {
+        const uint64_t n = c->local - r0 < kIoChunkRows ? c->local - r0 : kIoChunkRows;
+        vrod_status st = vrod_collection_read_rows(c, r0, n, buf.data());
+        if (st != VROD_OK) {
+            fclose(f);
+            return st;
+        }
+        ok = fwrite(buf.data(), sizeof(float) * c->dim, n, f) == n;
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? VROD_OK : fail(VROD_EINVAL, std::string("short write to '") + path + "'");
+}
+
+extern "C" vrod_status vrod_collection_load(vrod_ctx *ctx, const char *name, const char *path, uint64_t capacity_rows,
+                                            vrod_collection **out) {
+    if (out) *out = nullptr;
+    if (!ctx || !name || !path) return fail(VROD_EINVAL, "NULL argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(VROD_ENOTFOUND, std::string("cannot open '") + path + "'");
+    ColFileHeader h{};
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "VRODCOL1", 8) != 0 || h.dim == 0 || h.metric > 1) {
+        fclose(f);
+        return fail(VROD_EINVAL, std::string("'") + path + "' is not a vrod collection file");
+    }
+    const uint64_t cap = capacity_rows > h.count ? capacity_rows : (h.count ? h.count : 1);
+    vrod_collection *c = nullptr;
+    vrod_status st = vrod_collection_create(ctx, name, h.dim, (vrod_metric)h.metric, cap, &c);
+    if (st != VROD_OK) {
+        fclose(f);
+        return st;
+    }
+    // every rank appends the whole file in chunks; vrod_collection_insert keeps the rows of its own range
+    // (a sharded rank still reads the whole file: simple, and the file is read once)
+    std::vector<float> buf((size_t)kIoChunkRows * h.dim);
+    for (uint64_t r0 = 0; r0 < h.count; r0 += kIoChunkRows) {
+        const uint64_t n = h.count - r0 < kIoChunkRows ? h.count - r0 : kIoChunkRows;
+        if (fread(buf.data(), sizeof(float) * h.dim, n, f) != n) {
+            fclose(f);
+            vrod_collection_drop(ctx, name);
+            return fail(VROD_EINVAL, std::string("'") + path + "' is truncated");
+        }
+        st = vrod_collection_insert(c, buf.data(), n, nullptr);
+        if (st != VROD_OK) {
+            fclose(f);
+            const std::string msg = g_last_error;
+            vrod_collection_drop(ctx, name);
+            return fail(st, msg);
+        }
+    }
+    fclose(f);
+    if (out) *out = c;
     return VROD_OK;
 }
 

@@ -26,7 +26,8 @@ SYMBOLS = [
     "vrod_ctx_rank", "vrod_ctx_world",
     "vrod_collection_create", "vrod_collection_get", "vrod_collection_drop", "vrod_collection_list",
     "vrod_collection_info", "vrod_collection_insert", "vrod_collection_fill_synthetic",
-    "vrod_collection_read_rows", "vrod_collection_shard", "vrod_collection_search",
+    "vrod_collection_read_rows", "vrod_collection_shard", "vrod_collection_save", "vrod_collection_load",
+    "vrod_collection_search",
     "vrod_collection_search_device", "vrod_collection_set_path", "vrod_last_error", "vrod_version",
 ]
 
@@ -78,6 +79,8 @@ def lib():
         L.vrod_collection_fill_synthetic.argtypes = [vp, u64, u64]
         L.vrod_collection_read_rows.argtypes = [vp, u64, u64, vp]
         L.vrod_collection_shard.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+        L.vrod_collection_save.argtypes = [vp, C.c_char_p]
+        L.vrod_collection_load.argtypes = [vp, C.c_char_p, C.c_char_p, u64, C.POINTER(vp)]
         L.vrod_collection_search.argtypes = [vp, vp, u32, u32, vp, vp]
         L.vrod_collection_search_device.argtypes = [vp, vp, u32, u32, vp, vp]
         L.vrod_collection_set_path.argtypes = [vp, i32]
@@ -135,6 +138,9 @@ class Collection:
 
     def set_path(self, path):
         _check(lib().vrod_collection_set_path(self.h, path))
+
+    def save(self, path):
+        _check(lib().vrod_collection_save(self.h, str(path).encode()))
 
     def search(self, queries, k):
         """Host buffers in, host buffers out: (ids [b,k] uint64, dist [b,k] float32)."""
@@ -209,6 +215,11 @@ class Context:
     def get(self, name):
         h = C.c_void_p()
         _check(lib().vrod_collection_get(self.h, name.encode(), C.byref(h)))
+        return Collection(self, h, name)
+
+    def load(self, name, path, capacity=0):
+        h = C.c_void_p()
+        _check(lib().vrod_collection_load(self.h, name.encode(), str(path).encode(), capacity, C.byref(h)))
         return Collection(self, h, name)
 
     def drop(self, name):

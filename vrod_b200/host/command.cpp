@@ -107,6 +107,7 @@ void CreateCollectionCommand::execute() const {
         db->pending[name] = spec;   // the first INSERT fixes the dimension
     }
     db->payloads[name];
+    db->dirty = true;
     std::printf("created %s\n", name.c_str());
 }
 
@@ -115,6 +116,14 @@ void DropCollectionCommand::execute() const {
     db->last = CommandResult{};
     if (db->pending.erase(*collection_name) == 0 && !api(db, vrod_collection_drop(db->ctx(), collection_name->c_str()))) return;
     db->payloads.erase(*collection_name);
+    db->dirty = true;
+    {   // forget its files too, if this database lives in a directory
+        std::error_code ec;
+        if (!db->path.empty()) {
+            std::filesystem::remove(db->path / (*collection_name + ".vrc"), ec);
+            std::filesystem::remove(db->path / (*collection_name + ".payloads"), ec);
+        }
+    }
     std::printf("dropped %s\n", collection_name->c_str());
 }
 
@@ -152,6 +161,7 @@ void InsertCommand::execute() const {
     db->last = CommandResult{};
     db->last.first_id = first;
     db->last.inserted = 1;
+    db->dirty = true;
     std::printf("inserted id %llu\n", (unsigned long long)first);
 }
 
@@ -177,6 +187,7 @@ void BulkInsertCommand::execute() const {
     db->last = CommandResult{};
     db->last.first_id = first;
     db->last.inserted = pl.size() - first;
+    db->dirty = true;
     std::printf("inserted %llu records, first id %llu\n", (unsigned long long)db->last.inserted, (unsigned long long)first);
 }
 

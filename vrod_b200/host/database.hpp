@@ -39,8 +39,16 @@ class Database {
     // Database::new(path, name) (mod.rs:13-17): creates path/name with empty vr_config and vr_wal,
     // io error AlreadyExists if the directory exists (src/database/setup.rs:3-26).
     static Database create(const std::filesystem::path &path, const std::string &name);
-    // An in-memory database on one GPU (collections are not persisted: SURVEY.md 8(f) N4).
+    // An in-memory database on one GPU.
     explicit Database(int device = 0) : device_(device) {}
+    // Database::load(path) (mod.rs:19-21, todo!() upstream): opens a directory made by create() and loads
+    // every collection listed in its vr_config into GPU memory.  Throws std::runtime_error on a directory
+    // without vr_config or a damaged collection file.
+    static Database load(const std::filesystem::path &dir, int device = 0);
+    // Writes vr_config, one <name>.vrc rows file (vrod_collection_save) and one <name>.payloads text file per
+    // collection into `path`.  vr_wal is left untouched: there is no write-ahead log in this build.
+    void save();
+    bool dirty = false;   // set by the commands that change collections
     ~Database();
     Database(Database &&o) noexcept;
     Database(const Database &) = delete;

@@ -4,7 +4,8 @@
 //   -i/--init-database PATH  -n/--init-database-name NAME   create PATH/NAME with vr_config + vr_wal
 //   -d/--database DIR  -c/--collection NAME  -e/--execute COMMAND  -a/--command-arg ARG
 //   -g/--generate-embeddings AMOUNT   dev-only in the reference (fastembed); not provided here
-// Additions (collections live in GPU memory and are not persisted, so one process runs many commands):
+// With -d DIR the collections are loaded from DIR at start and written back after the commands (rows as
+// <name>.vrc, payloads as <name>.payloads, the list in vr_config).  Additions:
 //   --script FILE|-   one command per line: COMMAND <collection|-> [ARG...rest of line]
 //   --describe        build the command and print its type and fields instead of executing it
 //   --device N        CUDA ordinal (default 0)
@@ -59,8 +60,9 @@ int main(int argc, char **argv) {
             Database::create(*init_db, *init_name);
             return 0;
         }
-        Db db = std::make_shared<Database>(device);
-        if (database) db->path = *database;
+        // -d DIR: main.rs:64-74 (commented out upstream) loads the database from DIR; without -d the database
+        // lives in GPU memory for this process only
+        Db db = database ? std::make_shared<Database>(Database::load(*database, device)) : std::make_shared<Database>(device);
         CommandBuilder builder(db);
         int rc = 0;
         auto run = [&](OptStr coll, const std::string &cmd, OptStr arg) {
@@ -97,6 +99,7 @@ int main(int argc, char **argv) {
                 run(coll.empty() || coll == "-" ? OptStr() : OptStr(coll), cmd, rest.empty() ? OptStr() : OptStr(rest));
             }
         }
+        if (database && db->dirty && !describe) db->save();
         return rc;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "Error: %s\n", e.what());
