@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python __graft_entry__.py smoke 2>&1 | tail -2
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+CMD="python tools/batched_check.py prof10"
+$CMD > gpurun_out/plain_p10.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_p10.csv $CMD > /dev/null 2>&1
+grep time gpurun_out/plain_p10.log

@@ -376,15 +376,15 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             const long long tstart = clock64();
             for (uint32_t i = 0; i < my_tiles; ++i) {
                 const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
-                long long t0 = clock64();
+                long long t0 = p.dbg ? clock64() : 0;
                 mbar_wait(&ctl->tempty[acc], aphase ^ 1);
-                w_tempty += clock64() - t0;
+                if (p.dbg) w_tempty += clock64() - t0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + acc * BN;
                 for (uint32_t s = 0; s < p.nslab; ++s) {
-                    t0 = clock64();
+                    t0 = p.dbg ? clock64() : 0;
                     mbar_wait(&ctl->full[stage], phase);
-                    w_full += clock64() - t0;
+                    if (p.dbg) w_full += clock64() - t0;
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(a_s + (size_t)stage * stage_bytes);
                     const uint32_t b_addr = p.stream_q ? a_addr + SLAB_A_BYTES : smem_u32(q_s + (size_t)s * SLAB_B_BYTES);
@@ -399,7 +399,9 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 tc_commit(&ctl->tfull[acc]);         // accumulator complete
             }
             if (p.dbg) {
-
+                p.dbg[blockIdx.x * 8 + 5] = w_tempty;
+                p.dbg[blockIdx.x * 8 + 6] = w_full;
+                p.dbg[blockIdx.x * 8 + 1] = clock64() - tstart;
             }
         }
     } else {
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
         const int half = ew >> 2;                    // which 128 of the 256 query columns
         unsigned long long *cand = p.cand + (size_t)blockIdx.x * BN * CAP;
         int fail = 0;
-        long long w_tfull = 0, w_prune = 0, n_slow = 0, w_filter = 0;
+        long long w_tfull = 0, w_prune = 0, n_slow = 0;
         const long long tstart = clock64();
         // per-row factor of the NEXT tile is fetched one tile ahead (its global-load latency would otherwise
         // sit on the critical path of every tile)
@@ -484,14 +486,13 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
         if (p.dbg && ew == 0 && lane == 0) {
             p.dbg[blockIdx.x * 8 + 7] = clock64() - tstart;
             p.dbg[blockIdx.x * 8 + 0] = n_slow;
-            p.dbg[blockIdx.x * 8 + 1] = w_filter;
+
             long long tot = 0;
             for (int q = 0; q < BN; ++q) tot += ctl->cnt[q];
             p.dbg[blockIdx.x * 8 + 2] = tot;
             p.dbg[blockIdx.x * 8 + 3] = w_tfull;
             p.dbg[blockIdx.x * 8 + 4] = w_prune;
-            p.dbg[blockIdx.x * 8 + 5] = 0;
-            p.dbg[blockIdx.x * 8 + 6] = 0;
+
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int q = ew * 32 + lane; q < BN; q += 32 * kEpiWarps) p.cnt_out[(size_t)blockIdx.x * BN + q] = ctl->cnt[q] < CAP ? ctl->cnt[q] : CAP;
@@ -851,8 +852,8 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
                 double a[8] = {0};
                 for (uint32_t c = 0; c < grid; ++c)
                     for (int jx = 0; jx < 8; ++jx) a[jx] += (double)h[c * 8 + jx] / grid;
-                fprintf(stderr, "[batched dbg] tiles [%u,%u) avg/CTA: warp2 slow entries %.0f, filter cycles %.0f, candidates %.0f | wait_tfull %.0f prune %.0f (%.0f %.0f) "
-                                "| total %.0f | tiles/CTA %u\n",
+                fprintf(stderr, "[batched dbg] tiles [%u,%u) avg/CTA: warp2 slow entries %.0f, mma total %.0f, candidates %.0f | epi wait_tfull %.0f prune %.0f | mma wait_tempty %.0f wait_full %.0f "
+                                "| epi total %.0f | tiles/CTA %u\n",
                         t_begin, t_end, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], (t_end - t_begin + cpg - 1) / cpg);
             }
             if (last) break;

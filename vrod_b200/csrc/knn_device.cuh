@@ -54,13 +54,13 @@ __device__ __forceinline__ float word_to_unit(uint32_t w) {
 
 // ---- multi-row butterfly reduction --------------------------------------------------------------
 // Each lane holds N partial sums (one per row slot).  After the call every lane holds the full sum
-// of ONE row slot (returned; its index is added to rsel), replicated over the lanes that differ in
-// the bits not used for slot selection.  N row slots cost N-1 + log2(LPR/N) shuffles instead of
+// of ONE row slot (returned), replicated over the lanes that differ in the bits not used for slot
+// selection; which slot a lane ends up with depends only on its lane id (callers compute it once).  N row slots cost N-1 + log2(LPR/N) shuffles instead of
 // N*log2(LPR).  ASC = true walks lane offsets 1,2,4,.. (the canonical adjacent-pair order of the
 // exact f64 sums); ASC = false walks LPR/2,..,1.
 template <typename T, int N, int OFF, int LPR, bool ASC>
 struct RowsReduce {
-    static __device__ __forceinline__ T run(T *p, int lane, int &rsel, int weight) {
+    static __device__ __forceinline__ T run(T *p, int lane) {
         constexpr bool live = ASC ? (OFF < LPR) : (OFF >= 1);
         if constexpr (!live) {
             static_assert(N == 1, "more row slots than lanes per row");
@@ -76,11 +76,10 @@ struct RowsReduce {
                     const T keep = up ? p[j + H] : p[j];
                     p[j] = keep + __shfl_xor_sync(kFull, send, OFF);
                 }
-                if (up) rsel += H;
-                return RowsReduce<T, H, NEXT, LPR, ASC>::run(p, lane, rsel, weight);
+                return RowsReduce<T, H, NEXT, LPR, ASC>::run(p, lane);
             } else {
                 p[0] = p[0] + __shfl_xor_sync(kFull, p[0], OFF);
-                return RowsReduce<T, 1, NEXT, LPR, ASC>::run(p, lane, rsel, weight);
+                return RowsReduce<T, 1, NEXT, LPR, ASC>::run(p, lane);
             }
         }
     }

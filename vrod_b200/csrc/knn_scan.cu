@@ -213,8 +213,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) fast_scan_kernel(const ScanPa
                 for (int c = 0; c < CH; ++c) acc = chunk_acc<COS>(v[r][c], qv[c], acc);
                 part[r] = acc;
             }
-            int slot = 0;
-            float tot = RowsReduce<float, RB, LPR / 2, LPR, false>::run(part, lane, slot, 0);
+            float tot = RowsReduce<float, RB, LPR / 2, LPR, false>::run(part, lane);
             if constexpr (COS) tot = -tot * inv;
             const float thr = *(volatile float *)&ctl->thr_f;
             if (myok && owner && !(tot > thr)) cand_append(ctl, buf, make_key(tot, (uint32_t)myrow), p.cap, water);
@@ -248,8 +247,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) fast_scan_kernel(const ScanPa
 #pragma unroll
                     for (int u = 0; u < 4; ++u) part[r] = chunk_acc<COS>(v[r][u], q[u], part[r]);
             }
-            int slot = 0;
-            float tot = RowsReduce<float, RB, LPR / 2, LPR, false>::run(part, lane, slot, 0);
+            float tot = RowsReduce<float, RB, LPR / 2, LPR, false>::run(part, lane);
             if constexpr (COS) tot = -tot * inv;
             const float thr = *(volatile float *)&ctl->thr_f;
             if (myok && owner && !(tot > thr)) cand_append(ctl, buf, make_key(tot, (uint32_t)myrow), p.cap, water);
@@ -384,12 +382,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) exact_scan_kernel(const ScanP
             part[r] = canon_lane_fold(acc[r]);
             if constexpr (COS) partx[r] = canon_lane_fold(accx[r]);
         }
-        int slot = 0;
-        const double tot = RowsReduce<double, RB, 1, 32, true>::run(part, lane, slot, 0);
+        const double tot = RowsReduce<double, RB, 1, 32, true>::run(part, lane);
         float dist;
         if constexpr (COS) {
-            int slot2 = 0;
-            const double nx = RowsReduce<double, RB, 1, 32, true>::run(partx, lane, slot2, 0);
+            const double nx = RowsReduce<double, RB, 1, 32, true>::run(partx, lane);
             dist = canon_cos_dist(tot, nx, nq);
         } else {
             dist = canon_l2_dist(tot);

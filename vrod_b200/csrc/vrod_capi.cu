@@ -34,6 +34,22 @@ static vrod_status fail(vrod_status st, const std::string &msg) {
     g_last_error = msg;
     return st;
 }
+
+// No C++ exception crosses the C ABI: every entry point that can allocate runs inside this guard.
+template <typename F>
+static vrod_status guarded(F &&body) noexcept {
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        try { g_last_error = "host allocation failed"; } catch (...) {}
+        return VROD_ENOMEM;
+    } catch (const std::exception &e) {
+        try { g_last_error = std::string("internal error: ") + e.what(); } catch (...) {}
+        return VROD_EINVAL;
+    } catch (...) {
+        return VROD_EINVAL;
+    }
+}
 #define VROD_CUDA(expr)                                                                                   \
     do {                                                                                                  \
         cudaError_t e__ = (expr);                                                                         \
@@ -190,7 +206,11 @@ static vrod_status ctx_init(vrod_ctx *c, int device) {
 // -------------------------------------------------------------------------------------------------
 // context API
 // -------------------------------------------------------------------------------------------------
+static vrod_status vrod_ctx_create_impl(int device, vrod_ctx **out);
 extern "C" vrod_status vrod_ctx_create(int device, vrod_ctx **out) {
+    return guarded([&]() -> vrod_status { return vrod_ctx_create_impl(device, out); });
+}
+static vrod_status vrod_ctx_create_impl(int device, vrod_ctx **out) {
     if (!out) return fail(VROD_EINVAL, "out is NULL");
     *out = nullptr;
     std::unique_ptr<vrod_ctx> c(new (std::nothrow) vrod_ctx());
@@ -201,7 +221,11 @@ extern "C" vrod_status vrod_ctx_create(int device, vrod_ctx **out) {
     return VROD_OK;
 }
 
+static vrod_status vrod_comm_unique_id_impl(void *out);
 extern "C" vrod_status vrod_comm_unique_id(void *out) {
+    return guarded([&]() -> vrod_status { return vrod_comm_unique_id_impl(out); });
+}
+static vrod_status vrod_comm_unique_id_impl(void *out) {
     if (!out) return fail(VROD_EINVAL, "out is NULL");
     vrod_status st = nccl_load();
     if (st != VROD_OK) return st;
@@ -212,7 +236,11 @@ extern "C" vrod_status vrod_comm_unique_id(void *out) {
     return VROD_OK;
 }
 
+static vrod_status vrod_ctx_create_sharded_impl(int device, int rank, int world, const void *comm_id, vrod_ctx **out);
 extern "C" vrod_status vrod_ctx_create_sharded(int device, int rank, int world, const void *comm_id, vrod_ctx **out) {
+    return guarded([&]() -> vrod_status { return vrod_ctx_create_sharded_impl(device, rank, world, comm_id, out); });
+}
+static vrod_status vrod_ctx_create_sharded_impl(int device, int rank, int world, const void *comm_id, vrod_ctx **out) {
     if (!out) return fail(VROD_EINVAL, "out is NULL");
     *out = nullptr;
     if (world < 1 || world > 256 || rank < 0 || rank >= world) return fail(VROD_EINVAL, "bad rank/world");
@@ -260,7 +288,11 @@ extern "C" void vrod_ctx_destroy(vrod_ctx *ctx) {
     delete ctx;
 }
 
+static vrod_status vrod_ctx_synchronize_impl(vrod_ctx *ctx);
 extern "C" vrod_status vrod_ctx_synchronize(vrod_ctx *ctx) {
+    return guarded([&]() -> vrod_status { return vrod_ctx_synchronize_impl(ctx); });
+}
+static vrod_status vrod_ctx_synchronize_impl(vrod_ctx *ctx) {
     if (!ctx) return fail(VROD_EINVAL, "ctx is NULL");
     VROD_CUDA(cudaStreamSynchronize(ctx->stream));
     return VROD_OK;
@@ -269,13 +301,21 @@ extern "C" void *vrod_ctx_stream(vrod_ctx *ctx) { return ctx ? (void *)ctx->stre
 extern "C" int vrod_ctx_rank(vrod_ctx *ctx) { return ctx ? ctx->rank : -1; }
 extern "C" int vrod_ctx_world(vrod_ctx *ctx) { return ctx ? ctx->world : -1; }
 
+static vrod_status vrod_ctx_profile_impl(vrod_ctx *ctx, int enable);
 extern "C" vrod_status vrod_ctx_profile(vrod_ctx *ctx, int enable) {
+    return guarded([&]() -> vrod_status { return vrod_ctx_profile_impl(ctx, enable); });
+}
+static vrod_status vrod_ctx_profile_impl(vrod_ctx *ctx, int enable) {
     if (!ctx) return fail(VROD_EINVAL, "ctx is NULL");
     ctx->profiling = enable != 0;
     return VROD_OK;
 }
 
+static vrod_status vrod_ctx_profile_read_impl(vrod_ctx *ctx, double *kernel_ms, uint64_t *launches);
 extern "C" vrod_status vrod_ctx_profile_read(vrod_ctx *ctx, double *kernel_ms, uint64_t *launches) {
+    return guarded([&]() -> vrod_status { return vrod_ctx_profile_read_impl(ctx, kernel_ms, launches); });
+}
+static vrod_status vrod_ctx_profile_read_impl(vrod_ctx *ctx, double *kernel_ms, uint64_t *launches) {
     if (!ctx) return fail(VROD_EINVAL, "ctx is NULL");
     VROD_CUDA(cudaSetDevice(ctx->device));
     VROD_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -291,7 +331,11 @@ extern "C" vrod_status vrod_ctx_profile_read(vrod_ctx *ctx, double *kernel_ms, u
     return VROD_OK;
 }
 
+static vrod_status vrod_ctx_stats_impl(vrod_ctx *ctx, vrod_stats *out);
 extern "C" vrod_status vrod_ctx_stats(vrod_ctx *ctx, vrod_stats *out) {
+    return guarded([&]() -> vrod_status { return vrod_ctx_stats_impl(ctx, out); });
+}
+static vrod_status vrod_ctx_stats_impl(vrod_ctx *ctx, vrod_stats *out) {
     if (!ctx || !out) return fail(VROD_EINVAL, "NULL argument");
     VROD_CUDA(cudaSetDevice(ctx->device));
     unsigned long long dc[2] = {0, 0};
@@ -305,7 +349,13 @@ extern "C" vrod_status vrod_ctx_stats(vrod_ctx *ctx, vrod_stats *out) {
 // -------------------------------------------------------------------------------------------------
 // collections
 // -------------------------------------------------------------------------------------------------
+static vrod_status vrod_collection_create_impl(vrod_ctx *ctx, const char *name, uint32_t dim, vrod_metric metric,
+                                              uint64_t capacity_rows, vrod_collection **out);
 extern "C" vrod_status vrod_collection_create(vrod_ctx *ctx, const char *name, uint32_t dim, vrod_metric metric,
+                                              uint64_t capacity_rows, vrod_collection **out) {
+    return guarded([&]() -> vrod_status { return vrod_collection_create_impl(ctx, name, dim, metric, capacity_rows, out); });
+}
+static vrod_status vrod_collection_create_impl(vrod_ctx *ctx, const char *name, uint32_t dim, vrod_metric metric,
                                               uint64_t capacity_rows, vrod_collection **out) {
     if (out) *out = nullptr;
     if (!ctx || !name || !*name) return fail(VROD_EINVAL, "ctx/name is NULL or empty");
@@ -343,7 +393,11 @@ extern "C" vrod_status vrod_collection_create(vrod_ctx *ctx, const char *name, u
     return VROD_OK;
 }
 
+static vrod_status vrod_collection_get_impl(vrod_ctx *ctx, const char *name, vrod_collection **out);
 extern "C" vrod_status vrod_collection_get(vrod_ctx *ctx, const char *name, vrod_collection **out) {
+    return guarded([&]() -> vrod_status { return vrod_collection_get_impl(ctx, name, out); });
+}
+static vrod_status vrod_collection_get_impl(vrod_ctx *ctx, const char *name, vrod_collection **out) {
     if (!ctx || !name || !out) return fail(VROD_EINVAL, "NULL argument");
     auto it = ctx->colls.find(name);
     if (it == ctx->colls.end()) {
@@ -354,7 +408,11 @@ extern "C" vrod_status vrod_collection_get(vrod_ctx *ctx, const char *name, vrod
     return VROD_OK;
 }
 
+static vrod_status vrod_collection_drop_impl(vrod_ctx *ctx, const char *name);
 extern "C" vrod_status vrod_collection_drop(vrod_ctx *ctx, const char *name) {
+    return guarded([&]() -> vrod_status { return vrod_collection_drop_impl(ctx, name); });
+}
+static vrod_status vrod_collection_drop_impl(vrod_ctx *ctx, const char *name) {
     if (!ctx || !name) return fail(VROD_EINVAL, "NULL argument");
     auto it = ctx->colls.find(name);
     if (it == ctx->colls.end()) return fail(VROD_ENOTFOUND, std::string("no collection '") + name + "'");
@@ -365,7 +423,11 @@ extern "C" vrod_status vrod_collection_drop(vrod_ctx *ctx, const char *name) {
     return VROD_OK;
 }
 
+static vrod_status vrod_collection_list_impl(vrod_ctx *ctx, char *buf, size_t cap, size_t *needed);
 extern "C" vrod_status vrod_collection_list(vrod_ctx *ctx, char *buf, size_t cap, size_t *needed) {
+    return guarded([&]() -> vrod_status { return vrod_collection_list_impl(ctx, buf, cap, needed); });
+}
+static vrod_status vrod_collection_list_impl(vrod_ctx *ctx, char *buf, size_t cap, size_t *needed) {
     if (!ctx) return fail(VROD_EINVAL, "ctx is NULL");
     std::string s;
     for (auto &kv : ctx->colls) {
@@ -381,7 +443,13 @@ extern "C" vrod_status vrod_collection_list(vrod_ctx *ctx, char *buf, size_t cap
     return VROD_OK;
 }
 
+static vrod_status vrod_collection_info_impl(vrod_collection *c, uint32_t *dim, vrod_metric *metric, uint64_t *count,
+                                            uint64_t *capacity);
 extern "C" vrod_status vrod_collection_info(vrod_collection *c, uint32_t *dim, vrod_metric *metric, uint64_t *count,
+                                            uint64_t *capacity) {
+    return guarded([&]() -> vrod_status { return vrod_collection_info_impl(c, dim, metric, count, capacity); });
+}
+static vrod_status vrod_collection_info_impl(vrod_collection *c, uint32_t *dim, vrod_metric *metric, uint64_t *count,
                                             uint64_t *capacity) {
     if (!c) return fail(VROD_EINVAL, "collection is NULL");
     if (dim) *dim = c->dim;
@@ -391,14 +459,22 @@ extern "C" vrod_status vrod_collection_info(vrod_collection *c, uint32_t *dim, v
     return VROD_OK;
 }
 
+static vrod_status vrod_collection_shard_impl(vrod_collection *c, uint64_t *id_base, uint64_t *local_rows);
 extern "C" vrod_status vrod_collection_shard(vrod_collection *c, uint64_t *id_base, uint64_t *local_rows) {
+    return guarded([&]() -> vrod_status { return vrod_collection_shard_impl(c, id_base, local_rows); });
+}
+static vrod_status vrod_collection_shard_impl(vrod_collection *c, uint64_t *id_base, uint64_t *local_rows) {
     if (!c) return fail(VROD_EINVAL, "collection is NULL");
     if (id_base) *id_base = c->id_base;
     if (local_rows) *local_rows = c->local;
     return VROD_OK;
 }
 
+static vrod_status vrod_collection_set_path_impl(vrod_collection *c, int path);
 extern "C" vrod_status vrod_collection_set_path(vrod_collection *c, int path) {
+    return guarded([&]() -> vrod_status { return vrod_collection_set_path_impl(c, path); });
+}
+static vrod_status vrod_collection_set_path_impl(vrod_collection *c, int path) {
     if (!c || path < 0 || path > 3) return fail(VROD_EINVAL, "bad path");
     c->path = path;
     return VROD_OK;
@@ -464,7 +540,11 @@ static vrod_status collection_grow(vrod_collection *c, uint64_t need) {
     return VROD_OK;
 }
 
+static vrod_status vrod_collection_insert_impl(vrod_collection *c, const float *rows, uint64_t n, uint64_t *first_id);
 extern "C" vrod_status vrod_collection_insert(vrod_collection *c, const float *rows, uint64_t n, uint64_t *first_id) {
+    return guarded([&]() -> vrod_status { return vrod_collection_insert_impl(c, rows, n, first_id); });
+}
+static vrod_status vrod_collection_insert_impl(vrod_collection *c, const float *rows, uint64_t n, uint64_t *first_id) {
     if (!c) return fail(VROD_EINVAL, "collection is NULL");
     if (n == 0) {
         if (first_id) *first_id = c->count;
@@ -495,7 +575,11 @@ extern "C" vrod_status vrod_collection_insert(vrod_collection *c, const float *r
     return VROD_OK;
 }
 
+static vrod_status vrod_collection_fill_synthetic_impl(vrod_collection *c, uint64_t n, uint64_t seed);
 extern "C" vrod_status vrod_collection_fill_synthetic(vrod_collection *c, uint64_t n, uint64_t seed) {
+    return guarded([&]() -> vrod_status { return vrod_collection_fill_synthetic_impl(c, n, seed); });
+}
+static vrod_status vrod_collection_fill_synthetic_impl(vrod_collection *c, uint64_t n, uint64_t seed) {
     if (!c) return fail(VROD_EINVAL, "collection is NULL");
     if (c->count + n > c->capacity) return fail(VROD_ENOMEM, "collection capacity exceeded");
     vrod_ctx *ctx = c->ctx;
@@ -515,7 +599,11 @@ extern "C" vrod_status vrod_collection_fill_synthetic(vrod_collection *c, uint64
     return VROD_OK;
 }
 
+static vrod_status vrod_collection_read_rows_impl(vrod_collection *c, uint64_t row0, uint64_t n, float *out);
 extern "C" vrod_status vrod_collection_read_rows(vrod_collection *c, uint64_t row0, uint64_t n, float *out) {
+    return guarded([&]() -> vrod_status { return vrod_collection_read_rows_impl(c, row0, n, out); });
+}
+static vrod_status vrod_collection_read_rows_impl(vrod_collection *c, uint64_t row0, uint64_t n, float *out) {
     if (!c || (!out && n)) return fail(VROD_EINVAL, "NULL argument");
     if (row0 + n > c->local) return fail(VROD_EINVAL, "row range outside this rank's shard");
     if (n == 0) return VROD_OK;
@@ -540,7 +628,11 @@ struct ColFileHeader {
 static_assert(sizeof(ColFileHeader) == 64, "header is 64 bytes");
 constexpr uint64_t kIoChunkRows = 1u << 16;
 
+static vrod_status vrod_collection_save_impl(vrod_collection *c, const char *path);
 extern "C" vrod_status vrod_collection_save(vrod_collection *c, const char *path) {
+    return guarded([&]() -> vrod_status { return vrod_collection_save_impl(c, path); });
+}
+static vrod_status vrod_collection_save_impl(vrod_collection *c, const char *path) {
     if (!c || !path) return fail(VROD_EINVAL, "NULL argument");
     vrod_ctx *ctx = c->ctx;
     if (ctx->world > 1) return fail(VROD_EINVAL, "vrod_collection_save: single-GPU contexts only");
@@ -567,7 +659,13 @@ extern "C" vrod_status vrod_collection_save(vrod_collection *c, const char *path
     return ok ? VROD_OK : fail(VROD_EINVAL, std::string("short write to '") + path + "'");
 }
 
+static vrod_status vrod_collection_load_impl(vrod_ctx *ctx, const char *name, const char *path, uint64_t capacity_rows,
+                                            vrod_collection **out);
 extern "C" vrod_status vrod_collection_load(vrod_ctx *ctx, const char *name, const char *path, uint64_t capacity_rows,
+                                            vrod_collection **out) {
+    return guarded([&]() -> vrod_status { return vrod_collection_load_impl(ctx, name, path, capacity_rows, out); });
+}
+static vrod_status vrod_collection_load_impl(vrod_ctx *ctx, const char *name, const char *path, uint64_t capacity_rows,
                                             vrod_collection **out) {
     if (out) *out = nullptr;
     if (!ctx || !name || !path) return fail(VROD_EINVAL, "NULL argument");
@@ -729,7 +827,13 @@ static vrod_status check_search_args(vrod_collection *c, const void *q, uint32_t
     return VROD_OK;
 }
 
+static vrod_status vrod_collection_search_device_impl(vrod_collection *c, const float *d_queries, uint32_t b, uint32_t k,
+                                                     uint64_t *d_out_ids, float *d_out_dist);
 extern "C" vrod_status vrod_collection_search_device(vrod_collection *c, const float *d_queries, uint32_t b, uint32_t k,
+                                                     uint64_t *d_out_ids, float *d_out_dist) {
+    return guarded([&]() -> vrod_status { return vrod_collection_search_device_impl(c, d_queries, b, k, d_out_ids, d_out_dist); });
+}
+static vrod_status vrod_collection_search_device_impl(vrod_collection *c, const float *d_queries, uint32_t b, uint32_t k,
                                                      uint64_t *d_out_ids, float *d_out_dist) {
     vrod_status st = check_search_args(c, d_queries, b, k, d_out_ids, d_out_dist);
     if (st != VROD_OK || b == 0) return st;
@@ -745,7 +849,13 @@ extern "C" vrod_status vrod_collection_search_device(vrod_collection *c, const f
     return search_enqueue(c, q, b, k, d_out_ids, d_out_dist, false);
 }
 
+static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *queries, uint32_t b, uint32_t k,
+                                              uint64_t *out_ids, float *out_dist);
 extern "C" vrod_status vrod_collection_search(vrod_collection *c, const float *queries, uint32_t b, uint32_t k,
+                                              uint64_t *out_ids, float *out_dist) {
+    return guarded([&]() -> vrod_status { return vrod_collection_search_impl(c, queries, b, k, out_ids, out_dist); });
+}
+static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *queries, uint32_t b, uint32_t k,
                                               uint64_t *out_ids, float *out_dist) {
     vrod_status st = check_search_args(c, queries, b, k, out_ids, out_dist);
     if (st != VROD_OK || b == 0) return st;
