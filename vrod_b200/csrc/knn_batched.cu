@@ -39,14 +39,15 @@ constexpr int kCheckEvery = 4;     // tiles between two list-maintenance points 
 constexpr int PRUNE_AT = CAP - (kCheckEvery + 2) * BM;   // lists longer than this ask for a prune at the next point
 constexpr int kEpiWarps = 8;     // two per TMEM lane quadrant (each takes half of the 256 columns)
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..9 epilogue
-constexpr int SLAB_A_BYTES = BM * KS * 4;   // 16 KB
-constexpr int SLAB_B_BYTES = BN * KS * 4;   // 32 KB
+constexpr int SLAB_A_BYTES = BM * KS * 4;   // 16 KB: 128 rows x 128 B
+// query slab of one CTA: all BN queries (32 KB) alone, its half (16 KB) in a CTA pair
+__host__ __device__ constexpr int slab_b_bytes(int psz) { return BN / psz * KS * 4; }
 constexpr int MAX_SLABS = 4;                // dim <= 128: the query group stays resident (128 KB)
 
 struct BatchedParams {
     const float *sq_norm, *inv_norm;
     uint32_t n, b, nslab, stages;
-    uint32_t qgroups, cpg;
+    uint32_t qgroups, units;         // units = CTAs (PSZ = 1) or CTA pairs (PSZ = 2); unit u serves query group u % qgroups
     uint32_t tile_begin, tile_end;   // this launch (phase) covers row tiles [tile_begin, tile_end)
     const float *thr_init;      // [b] thresholds carried over from the previous phase (nullptr: +inf)
     unsigned long long *cand;   // [grid][BN][CAP]
@@ -90,6 +91,38 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// CTA-pair (cta_group::2) forms.  The leader (rank 0 of the pair) owns the tmem-empty barriers and the
+// peer-full barriers; the peer's warps arrive there through the cluster-mapped address.
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {   // arrive on CTA rank 0's copy of `bar`
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {        // arrives on the barrier in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -132,14 +165,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;             // SWIZZLE_128B
     return d;
 }
-// kind::tf32, f32 accumulate, A and B K-major, M = 128, N = 256
-constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::tf32, f32 accumulate, A and B K-major, N = 256, M = 128 (one CTA) or 256 (CTA pair: 128 rows per CTA)
+__host__ __device__ constexpr uint32_t idesc_tf32(int psz) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * psz) >> 4) << 24);
+}
 
 struct BatchCtl {
     uint64_t full[8], empty[8], tfull[2], tempty[2], qfull;
+    uint64_t pfull[8], pqfull;   // leader's view of the PEER's slabs / query slabs (CTA pairs only)
     uint32_t tmem_base;
     int flag;
-    float thr[BN];
+    alignas(16) float thr[BN];
     int cnt[BN];
 };
 
@@ -295,33 +331,47 @@ __device__ __noinline__ void append_candidates(uint32_t taddr, int col0, uint32_
     }
 }
 
-template <bool COS>
+// PSZ = 1 (default): one CTA per unit (tcgen05 cta_group::1, M = 128).  PSZ = 2 (experiment, VROD_BATCHED_PAIR=1):
+// a CTA pair per unit (cluster of 2, cta_group::2, M = 256): each CTA streams its own 128-row tile and keeps
+// only HALF of the query group in shared memory; only the leader CTA issues MMAs, both run TMA and epilogue, the
+// peer's idle MMA warp forwards "slab landed" to the leader.  The 1-CTA kernel spends ~2600 instead of 2048
+// cycles per tile in the MMA (12 KB of shared-memory operands per K=8 step); the pair was meant to cut that to
+// 8 KB per CTA but measured slower in round 1.
+template <bool COS, int PSZ>
 __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                    const __grid_constant__ CUtensorMap tmQ,
                                                                    const BatchedParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int SLAB_B = slab_b_bytes(PSZ);
     // resident mode: [nslab query slabs][stages row slabs]; streamed mode: [stages x (row slab + query slab)]
-    const uint32_t stage_bytes = p.stream_q ? (SLAB_A_BYTES + SLAB_B_BYTES) : SLAB_A_BYTES;
+    const uint32_t stage_bytes = p.stream_q ? (SLAB_A_BYTES + SLAB_B) : SLAB_A_BYTES;
     unsigned char *q_s = smem;
-    unsigned char *a_s = p.stream_q ? smem : smem + (size_t)p.nslab * SLAB_B_BYTES;
+    unsigned char *a_s = p.stream_q ? smem : smem + (size_t)p.nslab * SLAB_B;
     BatchCtl *ctl = reinterpret_cast<BatchCtl *>(a_s + (size_t)p.stages * stage_bytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (smem_u32(smem) & 1023u) __trap();          // the 128-byte swizzle needs a 1024-byte aligned base
-    const uint32_t g = blockIdx.x % p.qgroups;     // query group of this CTA
-    const uint32_t member = blockIdx.x / p.qgroups;
-    const uint32_t span = p.tile_end - p.tile_begin;
-    const uint32_t my_tiles = member < span ? (span - member + p.cpg - 1) / p.cpg : 0;
+    const uint32_t rank = PSZ == 2 ? cluster_ctarank() : 0;   // position in the pair
+    const bool leader = rank == 0;
+    const uint32_t unit = blockIdx.x / PSZ;
+    const uint32_t g = unit % p.qgroups;           // query group of this unit
+    const uint32_t member = unit / p.qgroups;
+    const uint32_t cpg = (p.units - g + p.qgroups - 1) / p.qgroups;        // units serving this group
+    const uint32_t span = (p.tile_end - p.tile_begin + PSZ - 1) / PSZ;     // super-tiles (PSZ row tiles) of the phase
+    const uint32_t my_tiles = member < span ? (span - member + cpg - 1) / cpg : 0;
+    auto tile_of = [&](uint32_t i) { return p.tile_begin + (member + i * cpg) * PSZ + rank; };
 
     if (tid == 0) {
         for (uint32_t s = 0; s < p.stages; ++s) {
-            mbar_init(&ctl->full[s], 1);
+            mbar_init(&ctl->full[s], 1);             // this CTA's own TMA (local transaction bytes)
+            mbar_init(&ctl->pfull[s], 1);            // pair leader only: the peer's forwarder arrives here
             mbar_init(&ctl->empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&ctl->tfull[a], 1);
-            mbar_init(&ctl->tempty[a], kEpiWarps);
+            mbar_init(&ctl->tempty[a], kEpiWarps * PSZ);
         }
         mbar_init(&ctl->qfull, 1);
+        mbar_init(&ctl->pqfull, 1);
         ctl->flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -332,45 +382,67 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
         ctl->cnt[i] = 0;
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
-                     "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PSZ == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PSZ == 2) cluster_sync_all();    // both CTAs' barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem = ctl->tmem_base;
+    const int q_row0 = (int)(g * BN + rank * (BN / PSZ));   // first query row of this CTA's (half of the) group
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (both CTAs of a pair: each loads its own row tile and its share of the queries) =====
         if (lane == 0) {
+            // every CTA completes its TMA bytes on its OWN barrier (completing the peer's bytes on the leader's
+            // barrier through the cluster made the loads ~2x slower); the peer's forwarder warp tells the leader
+            auto load = [&](void *dst, const CUtensorMap *m, int c0, int c1, uint64_t *bar) { tma_load_2d(dst, m, c0, c1, bar); };
+            auto arm = [&](uint64_t *bar, uint32_t bytes) { mbar_expect_tx(bar, bytes); };
             if (!p.stream_q) {
-                mbar_expect_tx(&ctl->qfull, p.nslab * SLAB_B_BYTES);
-                for (uint32_t s = 0; s < p.nslab; ++s) tma_load_2d(q_s + (size_t)s * SLAB_B_BYTES, &tmQ, (int)(s * KS), (int)(g * BN), &ctl->qfull);
+                arm(&ctl->qfull, p.nslab * SLAB_B);
+                for (uint32_t s = 0; s < p.nslab; ++s) load(q_s + (size_t)s * SLAB_B, &tmQ, (int)(s * KS), q_row0, &ctl->qfull);
             }
             uint32_t stage = 0, phase = 0;
-            long long w_empty = 0;
-            const long long tstart = clock64();
             for (uint32_t i = 0; i < my_tiles; ++i) {
-                const uint32_t tile = p.tile_begin + member + i * p.cpg;
+                const uint32_t tile = tile_of(i);
                 for (uint32_t s = 0; s < p.nslab; ++s) {
-                    const long long t0 = clock64();
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
-                    w_empty += clock64() - t0;
-                    mbar_expect_tx(&ctl->full[stage], stage_bytes);
-                    tma_load_2d(a_s + (size_t)stage * stage_bytes, &tmX, (int)(s * KS), (int)(tile * BM), &ctl->full[stage]);
-                    if (p.stream_q)
-                        tma_load_2d(a_s + (size_t)stage * stage_bytes + SLAB_A_BYTES, &tmQ, (int)(s * KS), (int)(g * BN), &ctl->full[stage]);
+                    arm(&ctl->full[stage], stage_bytes);
+                    load(a_s + (size_t)stage * stage_bytes, &tmX, (int)(s * KS), (int)(tile * BM), &ctl->full[stage]);
+                    if (p.stream_q) load(a_s + (size_t)stage * stage_bytes + SLAB_A_BYTES, &tmQ, (int)(s * KS), q_row0, &ctl->full[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
-
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            if (!p.stream_q) mbar_wait(&ctl->qfull, 0);
+        // ===== peer CTA of a pair: forward "my slab has landed" to the leader, one remote arrive per slab =====
+        if (lane == 0 && !leader) {
+            if (!p.stream_q) {
+                mbar_wait(&ctl->qfull, 0);
+                mbar_arrive_leader(&ctl->pqfull);
+            }
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t i = 0; i < my_tiles; ++i)
+                for (uint32_t s = 0; s < p.nslab; ++s) {
+                    mbar_wait(&ctl->full[stage], phase);
+                    mbar_arrive_leader(&ctl->pfull[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+        }
+        // ===== MMA issuer (one thread of the leader CTA) =====
+        if (lane == 0 && leader) {
+            if (!p.stream_q) {
+                mbar_wait(&ctl->qfull, 0);
+                if constexpr (PSZ == 2) mbar_wait(&ctl->pqfull, 0);
+            }
             uint32_t stage = 0, phase = 0;
             long long w_tempty = 0, w_full = 0;
             const long long tstart = clock64();
@@ -384,19 +456,26 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 for (uint32_t s = 0; s < p.nslab; ++s) {
                     t0 = p.dbg ? clock64() : 0;
                     mbar_wait(&ctl->full[stage], phase);
+                    if constexpr (PSZ == 2) mbar_wait(&ctl->pfull[stage], phase);
                     if (p.dbg) w_full += clock64() - t0;
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(a_s + (size_t)stage * stage_bytes);
-                    const uint32_t b_addr = p.stream_q ? a_addr + SLAB_A_BYTES : smem_u32(q_s + (size_t)s * SLAB_B_BYTES);
+                    const uint32_t b_addr = p.stream_q ? a_addr + SLAB_A_BYTES : smem_u32(q_s + (size_t)s * SLAB_B);
 #pragma unroll
                     for (int kk = 0; kk < KS / UMMA_K; ++kk) {
-                        tc_mma_tf32(d_tmem, umma_desc_sw128(a_addr + kk * UMMA_K * 4), umma_desc_sw128(b_addr + kk * UMMA_K * 4),
-                                    kIdescTf32, (s | (uint32_t)kk) != 0 ? 1u : 0u);
+                        const uint64_t ad = umma_desc_sw128(a_addr + kk * UMMA_K * 4), bd = umma_desc_sw128(b_addr + kk * UMMA_K * 4);
+                        const uint32_t accum = (s | (uint32_t)kk) != 0 ? 1u : 0u;
+                        if constexpr (PSZ == 2) tc_mma_tf32_pair(d_tmem, ad, bd, idesc_tf32(2), accum);
+                        else tc_mma_tf32(d_tmem, ad, bd, idesc_tf32(1), accum);
                     }
-                    tc_commit(&ctl->empty[stage]);   // frees the slab when these MMAs have read it
+                    // frees the slab (in both CTAs) when these MMAs have read it
+                    if constexpr (PSZ == 2) tc_commit_pair(&ctl->empty[stage]);
+                    else tc_commit(&ctl->empty[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&ctl->tfull[acc]);         // accumulator complete
+                // accumulator complete (each CTA's epilogue waits on its own copy of the barrier)
+                if constexpr (PSZ == 2) tc_commit_pair(&ctl->tfull[acc]);
+                else tc_commit(&ctl->tfull[acc]);
             }
             if (p.dbg) {
                 p.dbg[blockIdx.x * 8 + 5] = w_tempty;
@@ -420,14 +499,14 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             if (r >= p.n) return 0.f;
             return COS ? __ldg(p.inv_norm + r) : __ldg(p.sq_norm + r);
         };
-        float hx_next = my_tiles ? row_factor((p.tile_begin + member) * BM + quad * 32 + lane) : 0.f;
+        float hx_next = my_tiles ? row_factor(tile_of(0) * BM + quad * 32 + lane) : 0.f;
         for (uint32_t i = 0; i < my_tiles; ++i) {
-            const uint32_t tile = p.tile_begin + member + i * p.cpg;
+            const uint32_t tile = tile_of(i);
             const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
             const uint32_t row = tile * BM + quad * 32 + lane;
             const bool rowok = row < p.n;
             const float hx = COS ? hx_next : 0.5f * hx_next;
-            if (i + 1 < my_tiles) hx_next = row_factor((tile + p.cpg) * BM + quad * 32 + lane);
+            if (i + 1 < my_tiles) hx_next = row_factor(tile_of(i + 1) * BM + quad * 32 + lane);
             long long t0 = p.dbg ? clock64() : 0;
             mbar_wait(&ctl->tfull[acc], aphase);
             if (p.dbg) w_tfull += clock64() - t0;
@@ -460,10 +539,13 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 n_slow++;
                 append_candidates<COS>(taddr, half * (BN / 2), anycb, hx, rowok, row, ctl, cand, p.qflags, g * BN, p.b, lane);
             }
-            // accumulator stage drained: hand it back to the MMA warp
+            // accumulator stage drained: hand it back to the MMA warp (of the leader CTA)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->tempty[acc]);
+            if (lane == 0) {
+                if (leader) mbar_arrive(&ctl->tempty[acc]);
+                else mbar_arrive_leader(&ctl->tempty[acc]);
+            }
             // list maintenance every kCheckEvery tiles (all epilogue warps; the lists have room for the
             // appends of the tiles in between, see PRUNE_AT)
             if ((i + 1) % kCheckEvery != 0) continue;
@@ -499,9 +581,11 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PSZ == 2) cluster_sync_all();    // the peer's TMEM and barriers stay alive until the leader is done
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        if constexpr (PSZ == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
 
@@ -514,7 +598,7 @@ struct FinishParams {
     uint32_t n, ld4, b, k;
     unsigned long long id_base;
     int kprime, cap, water;
-    uint32_t qgroups, cpg;
+    uint32_t qgroups, units, psz;   // list layout of the tile kernel: unit u = g + m*qgroups, CTA = u*psz + r
     const unsigned long long *cand;
     const int *cnt_in;
     const int *qflags;
@@ -540,6 +624,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
     const uint32_t qi = blockIdx.x;
     const uint32_t g = qi / BN, ql = qi % BN;
     const float4 *q4 = p.q4 + (size_t)qi * p.ld4;
+    const uint32_t nlists = (p.units - g + p.qgroups - 1) / p.qgroups * p.psz;   // CTAs that scanned rows for this query
+    auto cta_of = [&](uint32_t l) { return (g + (l / p.psz) * p.qgroups) * p.psz + (l % p.psz); };
     if (tid == 0) {
         cand_reset(ctl);
         ctl->overflow = 0;
@@ -551,7 +637,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
     __syncthreads();
     // offsets of this query's lists (previous global list first, then one list per CTA of the group)
     int *offs = reinterpret_cast<int *>(buf + p.cap);   // [cpg + 2]
-    for (uint32_t m = tid; m < p.cpg; m += kScanThreads) offs[m + 2] = p.cnt_in[(size_t)(g + m * p.qgroups) * BN + ql];
+    for (uint32_t m = tid; m < nlists; m += kScanThreads) offs[m + 2] = p.cnt_in[(size_t)cta_of(m) * BN + ql];
     if (tid == 0) {
         offs[0] = 0;
         offs[1] = p.first_phase ? 0 : p.gcnt[qi];
@@ -559,19 +645,19 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
     __syncthreads();
     if (tid == 0) {   // in-place inclusive scan over <= 148 shared-memory words
         int acc = offs[1];
-        for (uint32_t m = 0; m < p.cpg; ++m) {
+        for (uint32_t m = 0; m < nlists; ++m) {
             acc += offs[m + 2];
             offs[m + 2] = acc;
         }
     }
     __syncthreads();
-    const int total = offs[p.cpg + 1];
+    const int total = offs[nlists + 1];
     if (total <= p.cap) {
         // common case: everything fits the sort buffer -- gather all lists in parallel, select once
         for (int i = tid; i < offs[1]; i += kScanThreads) buf[i] = p.glist[(size_t)qi * p.kprime + i];
-        for (uint32_t m = warp; m < p.cpg; m += kScanWarps) {
+        for (uint32_t m = warp; m < nlists; m += kScanWarps) {
             const int o = offs[m + 1], c = offs[m + 2] - o;
-            const unsigned long long *src = p.cand + ((size_t)(g + m * p.qgroups) * BN + ql) * CAP;
+            const unsigned long long *src = p.cand + ((size_t)cta_of(m) * BN + ql) * CAP;
             for (int i = lane; i < c; i += 32) buf[o + i] = __ldcg(src + i);
         }
         __syncthreads();
@@ -585,8 +671,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
             __syncthreads();
             block_prune(ctl, buf, p.kprime, p.cap, tid);
         }
-        for (uint32_t m = 0; m < p.cpg; ++m) {
-            const uint32_t cta = g + m * p.qgroups;
+        for (uint32_t m = 0; m < nlists; ++m) {
+            const uint32_t cta = cta_of(m);
             const int c = p.cnt_in[(size_t)cta * BN + ql];
             const unsigned long long *src = p.cand + ((size_t)cta * BN + ql) * CAP;
             for (int i0 = 0; i0 < c; i0 += kScanThreads) {
@@ -730,11 +816,23 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
     if (kprime < 64) kprime = 64;
     const double eps_dot = ldexp(1.0, -9) * 1.01 + (double)s.ld * ldexp(1.0, -22);
 
-    for (uint32_t g0 = 0; g0 < qgroups; g0 += (uint32_t)sm_count) {
-        const uint32_t groups = qgroups - g0 < (uint32_t)sm_count ? qgroups - g0 : (uint32_t)sm_count;
-        uint32_t cpg = (uint32_t)sm_count / groups;
-        if (cpg > ntiles) cpg = ntiles;
-        const uint32_t grid = groups * cpg;
+    // One CTA per unit (cta_group::1) by default.  VROD_BATCHED_PAIR=1 selects the CTA-pair kernel (cta_group::2,
+    // M = 256): it passes the same parity tests but measured SLOWER on B200 in round 1 (8.1 vs 5.6 ms per batch at
+    // configs[2]: the MMA issue time per tile did not drop and the leader waits for operand slabs ~50 % of the
+    // time), so it stays an experiment until that is understood.
+    static const bool want_pair = getenv("VROD_BATCHED_PAIR") != nullptr;
+    const uint32_t psz = (want_pair && !(sm_count & 1)) ? 2u : 1u;
+    const uint32_t max_units = (uint32_t)sm_count / psz;
+    const uint32_t super_tiles = (ntiles + psz - 1) / psz;
+
+    for (uint32_t g0 = 0; g0 < qgroups; g0 += max_units) {
+        const uint32_t groups = qgroups - g0 < max_units ? qgroups - g0 : max_units;
+        // the same number of units for every query group: the units of different groups that need the same row
+        // tile then run in lockstep and all but one of them hit L2
+        uint32_t units = groups * (max_units / groups);
+        if ((unsigned long long)groups * super_tiles < units) units = groups * super_tiles;   // no more units than work
+        const uint32_t cpg_max = (units + groups - 1) / groups;
+        const uint32_t grid = units * psz;
         const uint32_t bq = b - g0 * BN < groups * BN ? b - g0 * BN : groups * BN;   // queries in this wave
         const float *qw = d_q + (size_t)g0 * BN * s.ld;
 
@@ -763,7 +861,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         if (e != cudaSuccess) return e;
 
         CUtensorMap tmX, tmQ;
-        if (!make_map(&tmX, s.rows, s.n, s.ld, BM) || !make_map(&tmQ, qw, bq, s.ld, BN)) return cudaErrorInvalidValue;
+        if (!make_map(&tmX, s.rows, s.n, s.ld, BM) || !make_map(&tmQ, qw, bq, s.ld, BN / psz)) return cudaErrorInvalidValue;
 
         BatchedParams p{};
         p.sq_norm = s.sq_norm;
@@ -772,7 +870,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         p.b = bq;
         p.nslab = nslab;
         p.qgroups = groups;
-        p.cpg = cpg;
+        p.units = units;
         p.cand = cand;
         p.cnt_out = cnt;
         p.qflags = qflags;
@@ -788,16 +886,31 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         // dim <= 128: the query group is resident (nslab x 32 KB) and only row slabs stream; larger dims stream the
         // query slab next to every row slab (48 KB stages, L2-bandwidth bound: DESIGN.md)
         p.stream_q = nslab > MAX_SLABS ? 1 : 0;
-        const size_t resident = p.stream_q ? 0 : (size_t)nslab * SLAB_B_BYTES;
-        const size_t stage_bytes = p.stream_q ? (SLAB_A_BYTES + SLAB_B_BYTES) : SLAB_A_BYTES;
+        const size_t slab_b = (size_t)slab_b_bytes((int)psz);
+        const size_t resident = p.stream_q ? 0 : (size_t)nslab * slab_b;
+        const size_t stage_bytes = p.stream_q ? (SLAB_A_BYTES + slab_b) : SLAB_A_BYTES;
         size_t stages = (227 * 1024 - resident - sizeof(BatchCtl) - 1024) / stage_bytes;
         if (stages > 8) stages = 8;
         if (stages < 2) return cudaErrorInvalidConfiguration;
         p.stages = (uint32_t)stages;
         const size_t smem = resident + stages * stage_bytes + sizeof(BatchCtl);
-        auto tile_fn = s.metric ? batched_tile_kernel<true> : batched_tile_kernel<false>;
+        void (*tile_fn)(const CUtensorMap, const CUtensorMap, const BatchedParams) =
+            psz == 2 ? (s.metric ? batched_tile_kernel<true, 2> : batched_tile_kernel<false, 2>)
+                     : (s.metric ? batched_tile_kernel<true, 1> : batched_tile_kernel<false, 1>);
         e = cudaFuncSetAttribute(tile_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute cattr[1];
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cattr[0].id = cudaLaunchAttributeClusterDimension;
+        cattr[0].val.clusterDim.x = psz;
+        cattr[0].val.clusterDim.y = 1;
+        cattr[0].val.clusterDim.z = 1;
+        cfg.attrs = cattr;
+        cfg.numAttrs = 1;
 
         FinishParams f{};
         f.rows4 = reinterpret_cast<const float4 *>(s.rows);
@@ -811,7 +924,8 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         f.cap = 2048;
         f.water = f.cap - kScanThreads;
         f.qgroups = groups;
-        f.cpg = cpg;
+        f.units = units;
+        f.psz = psz;
         f.cand = cand;
         f.cnt_in = cnt;
         f.qflags = qflags;
@@ -822,13 +936,14 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         f.status = status + (size_t)g0 * BN;
         f.out = out + (size_t)g0 * BN * k;
         f.eps_dot = eps_dot;
-        const size_t fsmem = kFinCtl + (size_t)f.cap * sizeof(unsigned long long) + (cpg + 2) * sizeof(int);
+        const size_t fsmem = kFinCtl + (size_t)f.cap * sizeof(unsigned long long) + ((size_t)cpg_max * psz + 2) * sizeof(int);
         auto fin_fn = s.metric ? batched_finish_kernel<true> : batched_finish_kernel<false>;
 
-        // Phases over the row tiles: 1 tile per CTA first, then each phase 4x the rows seen so far.  Between
+        // Phases over the row tiles: 1 tile per CTA first, then each phase 4x the rows seen so far (phase
+        // boundaries are multiples of the pair size).  Between
         // phases the finish kernel merges all CTA lists of a query into its exact global k'-th threshold, so
         // the candidate rate of a phase is ~k'/rows_seen instead of ~k'/rows_seen_by_one_CTA.
-        uint32_t t_begin = 0, t_end = cpg < ntiles ? cpg : ntiles;
+        uint32_t t_begin = 0, t_end = cpg_max * psz < ntiles ? cpg_max * psz : ntiles;
         bool first = true;
         if (ev_start && g0 == 0) cudaEventRecord(ev_start, st);
         while (true) {
@@ -836,8 +951,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             p.tile_begin = t_begin;
             p.tile_end = t_end;
             p.thr_init = first ? nullptr : gthr;
-            tile_fn<<<grid, kThreads, smem, st>>>(tmX, tmQ, p);
-            e = cudaGetLastError();
+            e = cudaLaunchKernelEx(&cfg, tile_fn, tmX, tmQ, p);
             if (e != cudaSuccess) return e;
             f.first_phase = first ? 1 : 0;
             f.final_phase = last ? 1 : 0;
@@ -854,12 +968,13 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
                     for (int jx = 0; jx < 8; ++jx) a[jx] += (double)h[c * 8 + jx] / grid;
                 fprintf(stderr, "[batched dbg] tiles [%u,%u) avg/CTA: warp2 slow entries %.0f, mma total %.0f, candidates %.0f | epi wait_tfull %.0f prune %.0f | mma wait_tempty %.0f wait_full %.0f "
                                 "| epi total %.0f | tiles/CTA %u\n",
-                        t_begin, t_end, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], (t_end - t_begin + cpg - 1) / cpg);
+                        t_begin, t_end, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], (t_end - t_begin + cpg_max * psz - 1) / (cpg_max * psz));
             }
             if (last) break;
             first = false;
             t_begin = t_end;
-            const unsigned long long nxt = (unsigned long long)t_end * 4ull;
+            unsigned long long nxt = (unsigned long long)t_end * 4ull;
+            nxt -= nxt % psz;
             t_end = nxt >= ntiles ? ntiles : (uint32_t)nxt;
         }
         if (ev_stop && g0 + groups >= qgroups) cudaEventRecord(ev_stop, st);
