@@ -312,10 +312,31 @@ __device__ __noinline__ void append_candidates(uint32_t taddr, int col0, uint32_
             base = atomicAdd(&ctl->cnt[colbase + lane], c);
             if (base + c > PRUNE_AT) *(volatile int *)&ctl->flag = 1;
         }
-        while (colmask) {   // warp-uniform loop over the columns that have candidates
+        if (__popc(colmask) >= 6) {
+            // dense block (early phases: most columns have candidates): walk all 32 columns with the scores
+            // already in registers -- static register indices, no TMEM re-read
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+                if (colmask & (1u << jj)) {
+                    const int b0 = __shfl_sync(kFull, base, jj);
+                    const unsigned m = __shfl_sync(kFull, mcol, jj);
+                    if ((mask >> jj) & 1u) {
+                        const int q = colbase + jj;
+                        const int pos = b0 + __popc(m & ((1u << lane) - 1));
+                        const float dot = __uint_as_float(r[jj]);
+                        const float v = COS ? -(dot * hx) : (hx - dot);
+                        if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
+                        else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
+                    }
+                }
+            }
+            continue;
+        }
+        while (colmask) {   // sparse block: warp-uniform loop over the few columns that have candidates
             const int jj = __ffs(colmask) - 1;
             colmask &= colmask - 1;
-            // each lane re-reads its own score of column jj (a run-time register index would go to local memory)
+            // each lane re-reads its own score of column jj from TMEM (a run-time register index would push the
+            // whole block into local memory; measured slower)
             const float dot = __uint_as_float(tc_ld1(taddr + cb * 32 + jj));
             tc_wait_ld();
             const int b0 = __shfl_sync(kFull, base, jj);
@@ -939,7 +960,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         const size_t fsmem = kFinCtl + (size_t)f.cap * sizeof(unsigned long long) + ((size_t)cpg_max * psz + 2) * sizeof(int);
         auto fin_fn = s.metric ? batched_finish_kernel<true> : batched_finish_kernel<false>;
 
-        // Phases over the row tiles: 1 tile per CTA first, then each phase 4x the rows seen so far (phase
+        // Phases over the row tiles: 1 tile per CTA first, then each phase 3.5x the rows seen so far (phase
         // boundaries are multiples of the pair size).  Between
         // phases the finish kernel merges all CTA lists of a query into its exact global k'-th threshold, so
         // the candidate rate of a phase is ~k'/rows_seen instead of ~k'/rows_seen_by_one_CTA.
@@ -973,7 +994,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             if (last) break;
             first = false;
             t_begin = t_end;
-            unsigned long long nxt = (unsigned long long)t_end * 4ull;
+            unsigned long long nxt = (unsigned long long)t_end * 7ull / 2ull;   // 3.5x: new + carried keys mostly fit a 1024-key sort
             nxt -= nxt % psz;
             t_end = nxt >= ntiles ? ntiles : (uint32_t)nxt;
         }
