@@ -41,15 +41,25 @@ def test_batched_is_chosen_automatically_for_large_batches(ctx, oracle):
     s1 = ctx.stats()
     assert s1["batched_tiles"] > s0["batched_tiles"] and s1["fast_scans"] == s0["fast_scans"]
     assert_same(ids, dist, *oracle.search(oracle.fill(n, d, 5), Q, 10, 0))
-    # small batches stay on the per-query scan
+    # on a small collection a handful of queries is cheaper as single-query scans (cost model in vrod_capi.cu)
     c2 = ctx.create("auto_b2", 768, 1, 3000)
     c2.fill_synthetic(3000, 7)
-    Q2 = oracle.fill(20, 768, 8)
+    Q2 = oracle.fill(6, 768, 8)
     s0 = ctx.stats()
     ids, dist = c2.search(Q2, 5)
     s1 = ctx.stats()
-    assert s1["batched_tiles"] == s0["batched_tiles"] and s1["fast_scans"] - s0["fast_scans"] == 20
+    assert s1["batched_tiles"] == s0["batched_tiles"] and s1["fast_scans"] - s0["fast_scans"] == 6
     assert_same(ids, dist, *oracle.search(oracle.fill(3000, 768, 7), Q2, 5, 1))
+    # ... while on a large one even 8 queries go through the tensor cores
+    c3 = ctx.create("auto_b3", 128, 0, 2_000_000)
+    c3.fill_synthetic(2_000_000, 9)
+    Q3 = oracle.fill(8, 128, 10)
+    s0 = ctx.stats()
+    ids, dist = c3.search(Q3, 10)
+    s1 = ctx.stats()
+    assert s1["batched_tiles"] > s0["batched_tiles"]
+    assert_same(ids, dist, *oracle.search(oracle.fill(2_000_000, 128, 9), Q3, 10, 0))
+    ctx.drop("auto_b3")
     ctx.drop("auto_b")
     ctx.drop("auto_b2")
 

@@ -76,12 +76,16 @@ def test_config1_1m_x768_cosine_top10_full_size(ctx, oracle):
     c.fill_synthetic(n, 0x5EED0001)
     X = oracle.fill(n, d, 0x5EED0001)
     Q = oracle.fill(4, d, 0x5EED0002)
+    c.set_path(1)                      # the single-query scan (a 4-query call would otherwise go batched)
     before = ctx.stats()
     ids, dist = c.search(Q, 10)
-    assert_same(ids, dist, *oracle.search(X, Q, 10, 1))
+    want = oracle.search(X, Q, 10, 1)
+    assert_same(ids, dist, *want)
     after = ctx.stats()
     assert after["fast_scans"] - before["fast_scans"] == 4
     assert after["exact_rescans"] == before["exact_rescans"], "random data must not need the f64 rescan"
+    c.set_path(0)                      # automatic: the same answer through whatever path the cost model picks
+    assert_same(*c.search(Q, 10), *want)
     # k = 100 and the exact path agree too
     assert_same(*c.search(Q[:2], 100), *oracle.search(X, Q[:2], 100, 1))
     c.set_path(2)

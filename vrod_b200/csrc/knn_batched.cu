@@ -97,7 +97,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {   // arrive 
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
         : "memory");
 }
 __device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {        // arrives on the barrier in BOTH CTAs
@@ -432,16 +432,20 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 for (uint32_t s = 0; s < p.nslab; ++s) load(q_s + (size_t)s * SLAB_B, &tmQ, (int)(s * KS), q_row0, &ctl->qfull);
             }
             uint32_t stage = 0, phase = 0;
+            long long w_empty = 0;
             for (uint32_t i = 0; i < my_tiles; ++i) {
                 const uint32_t tile = tile_of(i);
                 for (uint32_t s = 0; s < p.nslab; ++s) {
+                    const long long te = p.dbg ? clock64() : 0;
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    if (p.dbg) w_empty += clock64() - te;
                     arm(&ctl->full[stage], stage_bytes);
                     load(a_s + (size_t)stage * stage_bytes, &tmX, (int)(s * KS), (int)(tile * BM), &ctl->full[stage]);
                     if (p.stream_q) load(a_s + (size_t)stage * stage_bytes + SLAB_A_BYTES, &tmQ, (int)(s * KS), q_row0, &ctl->full[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
+            if (p.dbg) p.dbg[blockIdx.x * 16 + 9] = w_empty;
         }
     } else if (warp == 1) {
         // ===== peer CTA of a pair: forward "my slab has landed" to the leader, one remote arrive per slab =====
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 if constexpr (PSZ == 2) mbar_wait(&ctl->pqfull, 0);
             }
             uint32_t stage = 0, phase = 0;
-            long long w_tempty = 0, w_full = 0;
+            long long w_tempty = 0, w_full = 0, w_pfull = 0;
             const long long tstart = clock64();
             for (uint32_t i = 0; i < my_tiles; ++i) {
                 const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
@@ -477,8 +481,12 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 for (uint32_t s = 0; s < p.nslab; ++s) {
                     t0 = p.dbg ? clock64() : 0;
                     mbar_wait(&ctl->full[stage], phase);
-                    if constexpr (PSZ == 2) mbar_wait(&ctl->pfull[stage], phase);
                     if (p.dbg) w_full += clock64() - t0;
+                    if constexpr (PSZ == 2) {
+                        t0 = p.dbg ? clock64() : 0;
+                        mbar_wait(&ctl->pfull[stage], phase);
+                        if (p.dbg) w_pfull += clock64() - t0;
+                    }
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(a_s + (size_t)stage * stage_bytes);
                     const uint32_t b_addr = p.stream_q ? a_addr + SLAB_A_BYTES : smem_u32(q_s + (size_t)s * SLAB_B);
@@ -499,9 +507,10 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 else tc_commit(&ctl->tfull[acc]);
             }
             if (p.dbg) {
-                p.dbg[blockIdx.x * 8 + 5] = w_tempty;
-                p.dbg[blockIdx.x * 8 + 6] = w_full;
-                p.dbg[blockIdx.x * 8 + 1] = clock64() - tstart;
+                p.dbg[blockIdx.x * 16 + 5] = w_tempty;
+                p.dbg[blockIdx.x * 16 + 6] = w_full;
+                p.dbg[blockIdx.x * 16 + 8] = w_pfull;
+                p.dbg[blockIdx.x * 16 + 1] = clock64() - tstart;
             }
         }
     } else {
@@ -587,14 +596,14 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             }
         }
         if (p.dbg && ew == 0 && lane == 0) {
-            p.dbg[blockIdx.x * 8 + 7] = clock64() - tstart;
-            p.dbg[blockIdx.x * 8 + 0] = n_slow;
+            p.dbg[blockIdx.x * 16 + 7] = clock64() - tstart;
+            p.dbg[blockIdx.x * 16 + 0] = n_slow;
 
             long long tot = 0;
             for (int q = 0; q < BN; ++q) tot += ctl->cnt[q];
-            p.dbg[blockIdx.x * 8 + 2] = tot;
-            p.dbg[blockIdx.x * 8 + 3] = w_tfull;
-            p.dbg[blockIdx.x * 8 + 4] = w_prune;
+            p.dbg[blockIdx.x * 16 + 2] = tot;
+            p.dbg[blockIdx.x * 16 + 3] = w_tfull;
+            p.dbg[blockIdx.x * 16 + 4] = w_prune;
 
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -651,64 +660,80 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
         cand_reset(ctl);
         ctl->overflow = 0;
     }
-    if (warp == 0) {
+    if (warp == 1 && p.final_phase) {   // only the last phase reranks
         const double nq = canon_row_sum<2>(q4, q4, (int)p.ld4, lane);
         if (lane == 0) ctl->nq = nq;
     }
-    __syncthreads();
-    // offsets of this query's lists (previous global list first, then one list per CTA of the group)
-    int *offs = reinterpret_cast<int *>(buf + p.cap);   // [cpg + 2]
-    for (uint32_t m = tid; m < nlists; m += kScanThreads) offs[m + 2] = p.cnt_in[(size_t)cta_of(m) * BN + ql];
-    if (tid == 0) {
-        offs[0] = 0;
-        offs[1] = p.first_phase ? 0 : p.gcnt[qi];
-    }
-    __syncthreads();
-    if (tid == 0) {   // in-place inclusive scan over <= 148 shared-memory words
-        int acc = offs[1];
-        for (uint32_t m = 0; m < nlists; ++m) {
-            acc += offs[m + 2];
-            offs[m + 2] = acc;
+    // offsets of this query's lists (previous global list first, then one list per CTA of the group):
+    // warp 0 loads the counts and scans them 32 at a time
+    int *offs = reinterpret_cast<int *>(buf + p.cap);   // [nlists + 2]
+    if (warp == 0) {
+        int carry = p.first_phase ? 0 : p.gcnt[qi];
+        if (lane == 0) {
+            offs[0] = 0;
+            offs[1] = carry;
+        }
+        for (uint32_t m0 = 0; m0 < nlists; m0 += 32) {
+            const uint32_t m = m0 + lane;
+            int v = m < nlists ? p.cnt_in[(size_t)cta_of(m) * BN + ql] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, v, o);
+                if (lane >= o) v += t;
+            }
+            if (m < nlists) offs[m + 2] = carry + v;
+            carry += __shfl_sync(kFull, v, 31);
         }
     }
     __syncthreads();
     const int total = offs[nlists + 1];
     if (total <= p.cap) {
-        // common case: everything fits the sort buffer -- gather all lists in parallel, select once
-        for (int i = tid; i < offs[1]; i += kScanThreads) buf[i] = p.glist[(size_t)qi * p.kprime + i];
-        for (uint32_t m = warp; m < nlists; m += kScanWarps) {
-            const int o = offs[m + 1], c = offs[m + 2] - o;
-            const unsigned long long *src = p.cand + ((size_t)cta_of(m) * BN + ql) * CAP;
-            for (int i = lane; i < c; i += 32) buf[o + i] = __ldcg(src + i);
+        // common case: everything fits the sort buffer -- every thread fetches its share of ALL lists at once
+        // (binary search of the entry's list in offs), so the gather costs one memory latency, then one select
+        const int prev = offs[1];
+        for (int i = tid; i < total; i += kScanThreads) {
+            if (i < prev) {
+                buf[i] = p.glist[(size_t)qi * p.kprime + i];
+            } else {
+                uint32_t lo = 0, hi = nlists - 1;   // largest m with offs[m + 1] <= i
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi + 1) >> 1;
+                    if (offs[mid + 1] <= i) lo = mid;
+                    else hi = mid - 1;
+                }
+                buf[i] = __ldcg(p.cand + ((size_t)cta_of(lo) * BN + ql) * CAP + (i - offs[lo + 1]));
+            }
         }
         __syncthreads();
         if (tid == 0) ctl->cnt = total;
     } else {
-        if (!p.first_phase) {   // carry the best keys of the earlier phases
-            const int c = p.gcnt[qi];
-            for (int i = tid; i < c; i += kScanThreads) buf[i] = p.glist[(size_t)qi * p.kprime + i];
-            __syncthreads();
-            if (tid == 0) ctl->cnt = c;
+        // more entries than the sort buffer holds (phase 0, or a candidate-heavy phase): stream them through the
+        // threshold filter in rounds of as many entries as fit next to the kprime survivors
+        const int prev = offs[1];
+        for (int i = tid; i < prev; i += kScanThreads) buf[i] = p.glist[(size_t)qi * p.kprime + i];
+        __syncthreads();
+        if (tid == 0) ctl->cnt = prev;
+        __syncthreads();
+        block_prune(ctl, buf, p.kprime, p.cap, tid);
+        const int round = p.cap - p.kprime;
+        for (int base = prev; base < total; base += round) {
+            const int end = base + round < total ? base + round : total;
+            for (int i = base + tid; i < end; i += kScanThreads) {
+                uint32_t lo = 0, hi = nlists - 1;   // largest m with offs[m + 1] <= i
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi + 1) >> 1;
+                    if (offs[mid + 1] <= i) lo = mid;
+                    else hi = mid - 1;
+                }
+                const unsigned long long key = __ldcg(p.cand + ((size_t)cta_of(lo) * BN + ql) * CAP + (i - offs[lo + 1]));
+                if (key < *(volatile unsigned long long *)&ctl->thrkey) {
+                    const int pos = atomicAdd(&ctl->cnt, 1);
+                    if (pos < p.cap) buf[pos] = key;
+                    else ctl->overflow = 1;
+                }
+            }
             __syncthreads();
             block_prune(ctl, buf, p.kprime, p.cap, tid);
-        }
-        for (uint32_t m = 0; m < nlists; ++m) {
-            const uint32_t cta = cta_of(m);
-            const int c = p.cnt_in[(size_t)cta * BN + ql];
-            const unsigned long long *src = p.cand + ((size_t)cta * BN + ql) * CAP;
-            for (int i0 = 0; i0 < c; i0 += kScanThreads) {
-                const int i = i0 + tid;
-                if (i < c) {
-                    const unsigned long long key = __ldcg(src + i);
-                    if (key < *(volatile unsigned long long *)&ctl->thrkey) {
-                        const int pos = atomicAdd(&ctl->cnt, 1);
-                        if (pos < p.cap) buf[pos] = key;
-                        else ctl->overflow = 1;
-                    }
-                }
-                __syncthreads();
-                if (ctl->cnt > p.water) block_prune(ctl, buf, p.kprime, p.cap, tid);
-            }
         }
     }
     __syncthreads();
@@ -900,7 +925,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             const char *dbg = getenv("VROD_BATCHED_DEBUG");
             p.debug_nocand = dbg && strcmp(dbg, "nocand") == 0;
             static long long *dbg_buf = nullptr;
-            if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 1024 * 8 * sizeof(long long));
+            if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 1024 * 16 * sizeof(long long));
             p.dbg = dbg ? dbg_buf : nullptr;
             if (dbg) g_dbg_buf = dbg_buf;
         }
@@ -981,12 +1006,22 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             if (e != cudaSuccess) return e;
             if (stats) stats->launches += 2;
             if (g_dbg_buf && getenv("VROD_BATCHED_DEBUG")) {
-                static long long h[1024 * 8];
+                static long long h[1024 * 16];
                 cudaStreamSynchronize(st);
-                cudaMemcpy(h, g_dbg_buf, sizeof(long long) * grid * 8, cudaMemcpyDeviceToHost);
+                cudaMemcpy(h, g_dbg_buf, sizeof(long long) * grid * 16, cudaMemcpyDeviceToHost);
                 double a[8] = {0};
                 for (uint32_t c = 0; c < grid; ++c)
-                    for (int jx = 0; jx < 8; ++jx) a[jx] += (double)h[c * 8 + jx] / grid;
+                    for (int jx = 0; jx < 8; ++jx) a[jx] += (double)h[c * 16 + jx] / grid;
+                if (psz == 2) {
+                    double le = 0, pe = 0, wf = 0, wpf = 0, mt = 0;
+                    for (uint32_t c = 0; c < grid; c += 2) {
+                        le += (double)h[c * 16 + 9]; pe += (double)h[(c + 1) * 16 + 9];
+                        wf += (double)h[c * 16 + 6]; wpf += (double)h[c * 16 + 8]; mt += (double)h[c * 16 + 1];
+                    }
+                    const double np = grid / 2.0;
+                    fprintf(stderr, "[batched dbg pair] leader: mma total %.0f wait_full(own) %.0f wait_pfull(peer) %.0f | producer wait_empty leader %.0f peer %.0f\n",
+                            mt / np, wf / np, wpf / np, le / np, pe / np);
+                }
                 fprintf(stderr, "[batched dbg] tiles [%u,%u) avg/CTA: warp2 slow entries %.0f, mma total %.0f, candidates %.0f | epi wait_tfull %.0f prune %.0f | mma wait_tempty %.0f wait_full %.0f "
                                 "| epi total %.0f | tiles/CTA %u\n",
                         t_begin, t_end, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], (t_end - t_begin + cpg_max * psz - 1) / (cpg_max * psz));
