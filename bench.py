@@ -295,12 +295,14 @@ def main():
     for i in range(args.warmup):
         coll.search(q_np[i * batch:(i + 1) * batch], k)
     barrier()
+    se0 = ctx.stats()
     t0 = time.perf_counter()
     for i in range(args.steps):
         j = args.warmup + i
         h_ids, h_dist = coll.search(q_np[j * batch:(j + 1) * batch], k)
     barrier()
     e2e_s = time.perf_counter() - t0
+    se1 = ctx.stats()
     assert np.array_equal(h_ids, last_ids) and np.array_equal(h_dist.view(np.uint32), last_dist.view(np.uint32)), \
         "host-buffer and resident legs disagree"
 
@@ -327,8 +329,9 @@ def main():
                        "l2_policy": f"inputs larger than L2: {algo_bytes / 1e9:.2f} GB scanned per step per GPU vs 126 MB L2",
                        "arithmetic": "f32 scan, exact f64 rerank + guard (bit-identical to the oracle)"},
             "e2e": {"value": args.steps * batch / (e2e_ms / 1e3), "unit": "queries/s",
-                    "h2d_bytes_per_step": int((s1["h2d_bytes"] - s0["h2d_bytes"]) // max(args.steps, 1)) or batch * dim * 4,
-                    "d2h_bytes_per_step": batch * k * 12, "ms_per_step": e2e_ms / args.steps},
+                    "h2d_bytes_per_step": int((se1["h2d_bytes"] - se0["h2d_bytes"]) // max(args.steps, 1)),
+                    "d2h_bytes_per_step": int((se1["d2h_bytes"] - se0["d2h_bytes"]) // max(args.steps, 1)),
+                    "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]),
             "exact_rescans": int(s1["exact_rescans"] - s0["exact_rescans"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -349,8 +352,6 @@ def main():
                                 "kernel": "batched_tile_kernel (tcgen05.mma kind::tf32) + inter-phase batched_finish_kernel",
                                 "algorithmic_flops_per_step": flops, "kernel_ms": kern_avg_ms, "launches_timed": int(kern_n),
                                 "hbm_floor": {"algorithmic_bytes": algo_bytes, "peak_gbs": peak}}
-        # e2e h2d: the timed host leg ran after s1 was read; report the per-step bytes the call copies
-        line["e2e"]["h2d_bytes_per_step"] = batch * ((dim + 3) // 4 * 4) * 4
         # cheap live check of the last answer: sorted, and the claimed rows sit at the claimed distances
         assert np.all(np.diff(last_dist, axis=1) >= 0)
         if world == 1 and not args.no_cpu_baseline:

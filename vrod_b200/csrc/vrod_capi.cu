@@ -724,15 +724,21 @@ static ShardView shard_view(const vrod_collection *c) {
 }
 
 // queries already on the device as [b x ld]; enqueue everything, no synchronisation
+// d_status: per-query guard flags (device).  host_checks: the caller reads d_status after synchronising and
+// rescans the flagged queries itself, so the conditional exact-scan launches are left out (single GPU only).
 static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t b, uint32_t k, uint64_t *d_ids,
-                                  float *d_dist, bool force_exact) {
+                                  float *d_dist, bool force_exact, int *d_status = nullptr, bool host_checks = false,
+                                  bool *used_scan = nullptr) {
     vrod_ctx *ctx = c->ctx;
+    if (!d_status) d_status = ctx_status(ctx);
+    if (ctx->world > 1) host_checks = false;
+    if (used_scan) *used_scan = false;
     const ShardView s = shard_view(c);
     const size_t nhits = (size_t)b * k;
     VROD_CUDA(ctx->hits_local.ensure(nhits * sizeof(Hit)));
     Hit *local = reinterpret_cast<Hit *>(ctx->hits_local.p);
     ScanScratch scr{reinterpret_cast<unsigned long long *>(ctx->blk_cand.p),
-                    reinterpret_cast<unsigned int *>(ctx_ticket(ctx)), ctx_status(ctx), ctx->dev_counters};
+                    reinterpret_cast<unsigned int *>(ctx_ticket(ctx)), d_status, ctx->dev_counters};
     const bool exact_only = force_exact || c->path == 2 || !c->fast_ok;
     // single GPU: the scan kernels write the final arrays themselves, no merge launch
     const bool direct = ctx->world == 1;
@@ -753,7 +759,7 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
     if (batched) {
         BatchedStats bs{};
         cudaEvent_t e0 = ctx->profiling ? ctx->prof_event() : nullptr, e1 = ctx->profiling ? ctx->prof_event() : nullptr;
-        cudaError_t e = launch_batched_search(s, d_q, b, k, ctx->sms, &ctx->batched.p, &ctx->batched.bytes, ctx_status(ctx),
+        cudaError_t e = launch_batched_search(s, d_q, b, k, ctx->sms, &ctx->batched.p, &ctx->batched.bytes, d_status,
                                               local, ctx->stream, &bs, e0, e1);
         if (e != cudaSuccess) return fail(VROD_ECUDA, std::string("batched search: ") + cudaGetErrorString(e));
         ctx->stats.kernel_launches += bs.launches;
@@ -762,15 +768,15 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         // the device, so this path synchronises once (the shard-local rescans involve no collective).
         VROD_CUDA(ctx->status_host.ensure(sizeof(int) * b));
         int *hs = reinterpret_cast<int *>(ctx->status_host.p);
-        VROD_CUDA(cudaMemcpyAsync(hs, ctx_status(ctx), sizeof(int) * b, cudaMemcpyDeviceToHost, ctx->stream));
+        VROD_CUDA(cudaMemcpyAsync(hs, d_status, sizeof(int) * b, cudaMemcpyDeviceToHost, ctx->stream));
         VROD_CUDA(cudaStreamSynchronize(ctx->stream));
         const ScanPlan fp = make_scan_plan(s, k, ctx->sms, false);
         const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
         for (uint32_t qi = 0; qi < b; ++qi) {
             if (!hs[qi]) continue;
             const float *q = d_q + (size_t)qi * s.ld;
-            VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, nullptr, nullptr, ctx->stream));
-            VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, nullptr, nullptr, ctx->stream));
+            VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, d_status + qi, local + (size_t)qi * k, nullptr, nullptr, ctx->stream));
+            VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, d_status + qi, local + (size_t)qi * k, nullptr, nullptr, ctx->stream));
             ctx->stats.kernel_launches += 2;
             ctx->stats.fast_scans++;
         }
@@ -795,7 +801,7 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
                 cudaMemcpyAsync(dbgbuf, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream);
             }
             if (ctx->profiling) VROD_CUDA(cudaEventRecord(ctx->prof_event(), ctx->stream));
-            VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, oid(qi), odd(qi),
+            VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, d_status + qi, local + (size_t)qi * k, oid(qi), odd(qi),
                                        ctx->stream));
             if (scan_dbg) {
                 unsigned long long h[8];
@@ -806,11 +812,15 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
                         (h[5] - h[0]) / 1e3);
             }
             if (ctx->profiling) VROD_CUDA(cudaEventRecord(ctx->prof_event(), ctx->stream));
-            VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, ctx_status(ctx) + qi, local + (size_t)qi * k, oid(qi), odd(qi),
-                                        ctx->stream));
-            ctx->stats.kernel_launches += 2;
+            if (!host_checks) {
+                VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, d_status + qi, local + (size_t)qi * k, oid(qi), odd(qi),
+                                            ctx->stream));
+                ctx->stats.kernel_launches++;
+            }
+            ctx->stats.kernel_launches++;
         }
         ctx->stats.fast_scans += b;
+        if (used_scan) *used_scan = true;
     }
     const Hit *lists = local;
     uint32_t g = 1;
@@ -892,23 +902,51 @@ static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *
         if (nq > 0.0 && (nq < 0x1p-80 || nq > 0x1p100)) unsafe = true;
         if (c->metric == VROD_COSINE && nq == 0.0) unsafe = true;  // all distances are 1: answered by the exact scan
     }
+    // one device buffer [ids | dist | status] so that the results and the guard flags come back in ONE copy
     const size_t nres = (size_t)b * k;
+    const size_t off_dist = nres * sizeof(uint64_t);
+    const size_t off_stat = off_dist + ((nres * sizeof(float) + 15) & ~(size_t)15);
+    const size_t pack = off_stat + (size_t)b * sizeof(int);
     VROD_CUDA(ctx->q_dev.ensure(qbytes));
-    VROD_CUDA(ctx->out_ids.ensure(nres * sizeof(uint64_t)));
-    VROD_CUDA(ctx->out_dist.ensure(nres * sizeof(float)));
-    VROD_CUDA(ctx->ids_host.ensure(nres * sizeof(uint64_t)));
-    VROD_CUDA(ctx->dist_host.ensure(nres * sizeof(float)));
+    VROD_CUDA(ctx->out_ids.ensure(pack));
+    VROD_CUDA(ctx->ids_host.ensure(pack));
+    unsigned char *dpack = reinterpret_cast<unsigned char *>(ctx->out_ids.p);
+    unsigned char *hpack = reinterpret_cast<unsigned char *>(ctx->ids_host.p);
+    uint64_t *d_ids = reinterpret_cast<uint64_t *>(dpack);
+    float *d_dist = reinterpret_cast<float *>(dpack + off_dist);
+    int *d_stat = reinterpret_cast<int *>(dpack + off_stat);
     VROD_CUDA(cudaMemcpyAsync(ctx->q_dev.p, qh, qbytes, cudaMemcpyHostToDevice, ctx->stream));
-    st = search_enqueue(c, reinterpret_cast<const float *>(ctx->q_dev.p), b, k, reinterpret_cast<uint64_t *>(ctx->out_ids.p),
-                        reinterpret_cast<float *>(ctx->out_dist.p), unsafe);
+    bool used_scan = false;
+    st = search_enqueue(c, reinterpret_cast<const float *>(ctx->q_dev.p), b, k, d_ids, d_dist, unsafe, d_stat, true, &used_scan);
     if (st != VROD_OK) return st;
-    VROD_CUDA(cudaMemcpyAsync(ctx->ids_host.p, ctx->out_ids.p, nres * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    VROD_CUDA(cudaMemcpyAsync(ctx->dist_host.p, ctx->out_dist.p, nres * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    VROD_CUDA(cudaMemcpyAsync(hpack, dpack, pack, cudaMemcpyDeviceToHost, ctx->stream));
     VROD_CUDA(cudaStreamSynchronize(ctx->stream));
-    memcpy(out_ids, ctx->ids_host.p, nres * sizeof(uint64_t));
-    memcpy(out_dist, ctx->dist_host.p, nres * sizeof(float));
+    if (used_scan && ctx->world == 1) {
+        // the scans ran without their device-side conditional rescans: answer the flagged queries exactly now
+        const int *hs = reinterpret_cast<const int *>(hpack + off_stat);
+        bool any = false;
+        for (uint32_t qi = 0; qi < b; ++qi) any = any || hs[qi] != 0;
+        if (any) {
+            const ShardView s = shard_view(c);
+            const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
+            ScanScratch scr{reinterpret_cast<unsigned long long *>(ctx->blk_cand.p),
+                            reinterpret_cast<unsigned int *>(ctx_ticket(ctx)), d_stat, ctx->dev_counters};
+            Hit *local = reinterpret_cast<Hit *>(ctx->hits_local.p);
+            for (uint32_t qi = 0; qi < b; ++qi) {
+                if (!hs[qi]) continue;
+                VROD_CUDA(launch_exact_scan(s, reinterpret_cast<const float *>(ctx->q_dev.p) + (size_t)qi * s.ld, k, xp, scr, nullptr,
+                                            local + (size_t)qi * k, reinterpret_cast<unsigned long long *>(d_ids) + (size_t)qi * k,
+                                            d_dist + (size_t)qi * k, ctx->stream));
+                ctx->stats.kernel_launches++;
+            }
+            VROD_CUDA(cudaMemcpyAsync(hpack, dpack, off_stat, cudaMemcpyDeviceToHost, ctx->stream));
+            VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    memcpy(out_ids, hpack, nres * sizeof(uint64_t));
+    memcpy(out_dist, hpack + off_dist, nres * sizeof(float));
     ctx->stats.h2d_bytes += qbytes;
-    ctx->stats.d2h_bytes += nres * (sizeof(uint64_t) + sizeof(float));
+    ctx->stats.d2h_bytes += pack;
     return VROD_OK;
 }
 
