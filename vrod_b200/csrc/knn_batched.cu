@@ -298,6 +298,33 @@ __device__ __noinline__ void append_candidates(uint32_t taddr, int col0, uint32_
         if (!rowok) mask = 0;
         uint32_t colmask = __reduce_or_sync(kFull, mask);
         if (!colmask) continue;
+        if (__popc(colmask) <= 3) {
+            // sparse block (the common case of the large phases: one or two candidates): per column one ballot,
+            // one shared-memory atomic by the first candidate lane, one TMEM re-read of that column
+            while (colmask) {
+                const int jj = __ffs(colmask) - 1;
+                colmask &= colmask - 1;
+                const bool mine = (mask >> jj) & 1u;
+                const unsigned m = __ballot_sync(kFull, mine);
+                const int leader = __ffs(m) - 1;
+                const int q = colbase + jj;
+                int b0 = 0;
+                if (lane == leader) {
+                    b0 = atomicAdd(&ctl->cnt[q], __popc(m));
+                    if (b0 + __popc(m) > PRUNE_AT) *(volatile int *)&ctl->flag = 1;
+                }
+                const float dot = __uint_as_float(tc_ld1(taddr + cb * 32 + jj));   // (a run-time r[jj] would spill the block)
+                tc_wait_ld();
+                b0 = __shfl_sync(kFull, b0, leader);
+                if (mine) {
+                    const int pos = b0 + __popc(m & ((1u << lane) - 1));
+                    const float v = COS ? -(dot * hx) : (hx - dot);
+                    if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
+                    else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
+                }
+            }
+            continue;
+        }
         // transpose the 32x32 candidate bit matrix: lane j learns which rows hit column j and claims that many
         // slots of query j's list -- ONE shared-memory atomic instruction for the whole warp
         unsigned mcol = 0;
