@@ -63,6 +63,12 @@ cudaError_t launch_fill_synthetic(float *rows, uint32_t row0, uint32_t n, uint32
                                   uint64_t seed, cudaStream_t st);
 // [b x dim] -> [b x ld] zero padded
 cudaError_t launch_pad_queries(const float *src, float *dst, uint32_t b, uint32_t dim, uint32_t ld, cudaStream_t st);
+// Fused exchange + merge over NVLink peer memory (knn_scan.cu: exchange_merge_kernel).  The fused path serves
+// searches with b <= kXchgMaxB queries and b*k <= kXchgMaxHits hits on at most kXchgMaxWorld ranks.
+constexpr uint32_t kXchgMaxWorld = 16, kXchgMaxB = 256, kXchgMaxHits = 4096;
+size_t xchg_window_bytes();
+cudaError_t launch_exchange_merge(unsigned char *const *d_windows, uint32_t rank, uint32_t world, uint32_t seq, const Hit *local,
+                                  uint32_t b, uint32_t k, unsigned long long *out_ids, float *out_dist, int *d_err, cudaStream_t st);
 // merge g lists of [b][k] hits (layout [g][b][k]) into ids/dist [b][k] by (dist, id)
 cudaError_t launch_merge_hits(const Hit *lists, uint32_t g, uint32_t b, uint32_t k, unsigned long long *out_ids,
                               float *out_dist, cudaStream_t st);

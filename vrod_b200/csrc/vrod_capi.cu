@@ -148,6 +148,13 @@ struct vrod_ctx {
     PinBuf q_host, ids_host, dist_host, status_host;
     unsigned long long *dev_counters = nullptr;  // [0] exact rescans (counted on the device)
     vrod_stats stats{};
+    // fused NVLink exchange (sharded contexts): every rank's window mapped through CUDA IPC
+    unsigned char *xchg = nullptr;              // this rank's window
+    std::vector<unsigned char *> xchg_peers;    // [world] mapped windows (own pointer at [rank])
+    unsigned char **d_windows = nullptr;        // device copy of the table
+    int *d_xchg_err = nullptr;
+    uint32_t xchg_seq = 0;
+    bool fused_exchange = false;
     // optional kernel timing (vrod_ctx_profile)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
@@ -181,6 +188,8 @@ struct vrod_collection {
 static int *ctx_ticket(vrod_ctx *c) { return reinterpret_cast<int *>(c->small.p); }
 static int *ctx_status(vrod_ctx *c) { return reinterpret_cast<int *>(c->small.p) + 64; }
 constexpr uint32_t kMaxBatch = 1u << 16;
+
+static vrod_status setup_fused_exchange(vrod_ctx *c);
 
 static vrod_status ctx_init(vrod_ctx *c, int device) {
     int ndev = 0;
@@ -257,8 +266,65 @@ static vrod_status vrod_ctx_create_sharded_impl(int device, int rank, int world,
         ncclUniqueId id;
         memcpy(&id, comm_id, sizeof(id));
         VROD_NCCL(g_nccl.CommInitRank(&c->comm, world, id, rank));
+        st = setup_fused_exchange(c.get());
+        if (st != VROD_OK) return st;
     }
     *out = c.release();
+    return VROD_OK;
+}
+
+// Map every rank's exchange window into this process (CUDA IPC over NVLink P2P).  Collective.  On any failure
+// on any rank all ranks fall back to ncclAllGather + merge.
+static vrod_status setup_fused_exchange(vrod_ctx *c) {
+    if (c->world > (int)kXchgMaxWorld || getenv("VROD_NO_P2P_EXCHANGE")) return VROD_OK;
+    const int W = c->world;
+    bool ok = true;
+    cudaIpcMemHandle_t mine{};
+    unsigned char *d_tmp = nullptr;   // [W+1] handles, then [W+1] ok bytes
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    ok = ok && cudaMalloc(&c->xchg, xchg_window_bytes()) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(c->xchg, 0, xchg_window_bytes(), c->stream) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->d_xchg_err, 64) == cudaSuccess && cudaMemsetAsync(c->d_xchg_err, 0, 64, c->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+    ok = ok && cudaIpcGetMemHandle(&mine, c->xchg) == cudaSuccess;
+    VROD_CUDA(cudaMalloc(&d_tmp, (size_t)(W + 1) * (hb + 64)));
+    std::vector<cudaIpcMemHandle_t> all(W);
+    VROD_CUDA(cudaMemcpyAsync(d_tmp + (size_t)W * hb, &mine, hb, cudaMemcpyHostToDevice, c->stream));
+    VROD_NCCL(g_nccl.AllGather(d_tmp + (size_t)W * hb, d_tmp, hb, ncclChar, c->comm, c->stream));
+    VROD_CUDA(cudaMemcpyAsync(all.data(), d_tmp, (size_t)W * hb, cudaMemcpyDeviceToHost, c->stream));
+    VROD_CUDA(cudaStreamSynchronize(c->stream));
+    c->xchg_peers.assign(W, nullptr);
+    for (int r = 0; r < W && ok; ++r) {
+        if (r == c->rank) {
+            c->xchg_peers[r] = c->xchg;
+        } else {
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = false;
+            }
+            c->xchg_peers[r] = reinterpret_cast<unsigned char *>(p);
+        }
+    }
+    if (ok) {
+        ok = cudaMalloc(&c->d_windows, sizeof(unsigned char *) * W) == cudaSuccess &&
+             cudaMemcpyAsync(c->d_windows, c->xchg_peers.data(), sizeof(unsigned char *) * W, cudaMemcpyHostToDevice, c->stream) ==
+                 cudaSuccess;
+    }
+    // agree: fused only if every rank mapped every window
+    unsigned char *okbytes = d_tmp + (size_t)(W + 1) * hb;
+    const unsigned char my_ok = ok ? 1 : 0;
+    std::vector<unsigned char> oks(W);
+    VROD_CUDA(cudaMemcpyAsync(okbytes + W, &my_ok, 1, cudaMemcpyHostToDevice, c->stream));
+    VROD_NCCL(g_nccl.AllGather(okbytes + W, okbytes, 1, ncclChar, c->comm, c->stream));
+    VROD_CUDA(cudaMemcpyAsync(oks.data(), okbytes, W, cudaMemcpyDeviceToHost, c->stream));
+    VROD_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_tmp);
+    bool all_ok = true;
+    for (unsigned char v : oks) all_ok = all_ok && v;
+    c->fused_exchange = all_ok;
+    if (getenv("VROD_VERBOSE"))
+        fprintf(stderr, "[vrod] rank %d/%d: fused NVLink exchange %s\n", c->rank, c->world, all_ok ? "enabled" : "unavailable (NCCL all-gather)");
     return VROD_OK;
 }
 
@@ -276,6 +342,11 @@ extern "C" void vrod_ctx_destroy(vrod_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->colls) collection_free(kv.second);
+    for (size_t r = 0; r < ctx->xchg_peers.size(); ++r)
+        if ((int)r != ctx->rank && ctx->xchg_peers[r]) cudaIpcCloseMemHandle(ctx->xchg_peers[r]);
+    cudaFree(ctx->xchg);
+    cudaFree(ctx->d_windows);
+    cudaFree(ctx->d_xchg_err);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf *dev[] = {&ctx->blk_cand, &ctx->small, &ctx->q_pad, &ctx->q_dev, &ctx->hits_local,
                      &ctx->hits_all, &ctx->out_ids, &ctx->out_dist, &ctx->batched};
@@ -728,7 +799,7 @@ static ShardView shard_view(const vrod_collection *c) {
 // rescans the flagged queries itself, so the conditional exact-scan launches are left out (single GPU only).
 static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t b, uint32_t k, uint64_t *d_ids,
                                   float *d_dist, bool force_exact, int *d_status = nullptr, bool host_checks = false,
-                                  bool *used_scan = nullptr) {
+                                  bool *used_scan = nullptr, int *d_xerr = nullptr) {
     vrod_ctx *ctx = c->ctx;
     if (!d_status) d_status = ctx_status(ctx);
     if (ctx->world > 1) host_checks = false;
@@ -824,6 +895,15 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
     }
     const Hit *lists = local;
     uint32_t g = 1;
+    if (ctx->world > 1 && ctx->fused_exchange && b <= kXchgMaxB && nhits <= kXchgMaxHits) {
+        // one kernel: push the local lists into every rank's window over NVLink, wait for the peers', merge
+        VROD_CUDA(launch_exchange_merge(ctx->d_windows, (uint32_t)ctx->rank, (uint32_t)ctx->world, ++ctx->xchg_seq, local, b, k,
+                                        reinterpret_cast<unsigned long long *>(d_ids), d_dist, d_xerr ? d_xerr : ctx->d_xchg_err,
+                                        ctx->stream));
+        ctx->stats.kernel_launches++;
+        ctx->stats.searches += b;
+        return VROD_OK;
+    }
     if (ctx->world > 1) {
         VROD_CUDA(ctx->hits_all.ensure(nhits * sizeof(Hit) * ctx->world));
         VROD_NCCL(g_nccl.AllGather(local, ctx->hits_all.p, nhits * sizeof(Hit), ncclChar, ctx->comm, ctx->stream));
@@ -906,7 +986,7 @@ static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *
     const size_t nres = (size_t)b * k;
     const size_t off_dist = nres * sizeof(uint64_t);
     const size_t off_stat = off_dist + ((nres * sizeof(float) + 15) & ~(size_t)15);
-    const size_t pack = off_stat + (size_t)b * sizeof(int);
+    const size_t pack = off_stat + ((size_t)b + 1) * sizeof(int);   // + 1: peer-exchange error flag (sharded contexts)
     VROD_CUDA(ctx->q_dev.ensure(qbytes));
     VROD_CUDA(ctx->out_ids.ensure(pack));
     VROD_CUDA(ctx->ids_host.ensure(pack));
@@ -917,10 +997,13 @@ static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *
     int *d_stat = reinterpret_cast<int *>(dpack + off_stat);
     VROD_CUDA(cudaMemcpyAsync(ctx->q_dev.p, qh, qbytes, cudaMemcpyHostToDevice, ctx->stream));
     bool used_scan = false;
-    st = search_enqueue(c, reinterpret_cast<const float *>(ctx->q_dev.p), b, k, d_ids, d_dist, unsafe, d_stat, true, &used_scan);
+    st = search_enqueue(c, reinterpret_cast<const float *>(ctx->q_dev.p), b, k, d_ids, d_dist, unsafe, d_stat, true, &used_scan,
+                        d_stat + b);
     if (st != VROD_OK) return st;
     VROD_CUDA(cudaMemcpyAsync(hpack, dpack, pack, cudaMemcpyDeviceToHost, ctx->stream));
     VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->fused_exchange && reinterpret_cast<const int *>(hpack + off_stat)[b] == 1)
+        return fail(VROD_ENCCL, "peer exchange timed out: a rank did not take part in this search");
     if (used_scan && ctx->world == 1) {
         // the scans ran without their device-side conditional rescans: answer the flagged queries exactly now
         const int *hs = reinterpret_cast<const int *>(hpack + off_stat);
