@@ -742,25 +742,42 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
         if (tid == 0) ctl->cnt = prev;
         __syncthreads();
         block_prune(ctl, buf, p.kprime, p.cap, tid);
-        const int round = p.cap - p.kprime;
+        // rounds of half the free space: after the first select the threshold passes only a few percent of a
+        // round, so most rounds are a plain load + filter and the (latency-bound) sort runs only when the buffer
+        // could overflow in the next round -- sorting every round cost 3x more barrier stages
+        const int round = (p.cap - p.kprime) / 2;
+        constexpr int PER = 4;   // keys a thread fetches back to back (independent loads) before it filters them
         for (int base = prev; base < total; base += round) {
             const int end = base + round < total ? base + round : total;
-            for (int i = base + tid; i < end; i += kScanThreads) {
-                uint32_t lo = 0, hi = nlists - 1;   // largest m with offs[m + 1] <= i
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi + 1) >> 1;
-                    if (offs[mid + 1] <= i) lo = mid;
-                    else hi = mid - 1;
+            for (int i0 = base + tid; i0 < end; i0 += kScanThreads * PER) {
+                unsigned long long keys[PER];
+#pragma unroll
+                for (int e = 0; e < PER; ++e) {
+                    const int i = i0 + e * kScanThreads;
+                    keys[e] = kKeyMax;
+                    if (i < end) {
+                        uint32_t lo = 0, hi = nlists - 1;   // largest m with offs[m + 1] <= i
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi + 1) >> 1;
+                            if (offs[mid + 1] <= i) lo = mid;
+                            else hi = mid - 1;
+                        }
+                        keys[e] = __ldcg(p.cand + ((size_t)cta_of(lo) * BN + ql) * CAP + (i - offs[lo + 1]));
+                    }
                 }
-                const unsigned long long key = __ldcg(p.cand + ((size_t)cta_of(lo) * BN + ql) * CAP + (i - offs[lo + 1]));
-                if (key < *(volatile unsigned long long *)&ctl->thrkey) {
-                    const int pos = atomicAdd(&ctl->cnt, 1);
-                    if (pos < p.cap) buf[pos] = key;
-                    else ctl->overflow = 1;
+                const unsigned long long thr = *(volatile unsigned long long *)&ctl->thrkey;
+#pragma unroll
+                for (int e = 0; e < PER; ++e) {
+                    if (keys[e] < thr) {
+                        const int pos = atomicAdd(&ctl->cnt, 1);
+                        if (pos < p.cap) buf[pos] = keys[e];
+                        else ctl->overflow = 1;
+                    }
                 }
             }
             __syncthreads();
-            block_prune(ctl, buf, p.kprime, p.cap, tid);
+            const bool no_threshold_yet = ctl->thrkey == kKeyMax && ctl->cnt >= p.kprime;
+            if (ctl->cnt > p.cap - round || no_threshold_yet) block_prune(ctl, buf, p.kprime, p.cap, tid);   // uniform
         }
     }
     __syncthreads();
@@ -1056,7 +1073,12 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             if (last) break;
             first = false;
             t_begin = t_end;
-            unsigned long long nxt = (unsigned long long)t_end * 7ull / 2ull;   // 3.5x: new + carried keys mostly fit a 1024-key sort
+            // 3.5x per phase (new + carried keys mostly fit a 1024-key sort); short scans (few tiles per unit) take
+            // bigger steps: there every extra phase costs a finish kernel (~60 us) that the tiles cannot amortise
+            static const double growth_env = getenv("VROD_BATCHED_GROWTH") ? atof(getenv("VROD_BATCHED_GROWTH")) : 0.0;
+            const double growth = growth_env > 1.0 ? growth_env : ((super_tiles / cpg_max) < 256 ? 8.0 : 3.5);
+            unsigned long long nxt = (unsigned long long)((double)t_end * growth);
+            if (nxt <= t_end) nxt = t_end + psz;
             nxt -= nxt % psz;
             t_end = nxt >= ntiles ? ntiles : (uint32_t)nxt;
         }
