@@ -4,12 +4,13 @@ mkdir -p gpurun_out
 for W in cfg3 cfg2; do
   CMD="python bench.py --workload $W --steps 4 --warmup 3 --no-cpu-baseline"
   $CMD > gpurun_out/plain_$W.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$W.csv $CMD > gpurun_out/ncu_launches_$W.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_$W.csv $CMD > gpurun_out/ncu_launches_$W.log 2>&1
 done
 CMD="python bench.py --workload cfg3 --steps 4 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:fast_scan -s 4 -c 1 -f -o gpurun_out/prof_scan_cfg3 $CMD > gpurun_out/ncu_full_cfg3.log 2>&1
+# cfg2: all 8 phase launches of one batch (the 4th batch: 3 warm-up batches x 8 phases = 24 launches skipped)
 CMD="python bench.py --workload cfg2 --steps 4 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:batched_tile -s 27 -c 1 -f -o gpurun_out/prof_tile_cfg2 $CMD > gpurun_out/ncu_full_cfg2.log 2>&1
-tail -2 gpurun_out/ncu_full_cfg3.log gpurun_out/ncu_full_cfg2.log
+ncu --set full --clock-control none --import-source on -k regex:batched_tile -s 24 -c 8 -f -o gpurun_out/prof_tile_cfg2 $CMD > gpurun_out/ncu_full_cfg2.log 2>&1
+tail -n 2 gpurun_out/ncu_full_cfg3.log; tail -n 2 gpurun_out/ncu_full_cfg2.log
