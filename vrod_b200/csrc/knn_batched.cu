@@ -56,6 +56,7 @@ struct BatchedParams {
     int kprime;
     int stream_q;               // 1: the query slabs are streamed with the row slabs (dim > 128: the group does not fit)
     int debug_nocand;           // VROD_BATCHED_DEBUG=nocand: thresholds start at -inf (timing experiments only)
+    int debug_skip;             // timing experiments only: bit 0 = epilogue skips the TMEM reads (noepi), bit 1 = no MMAs issued (nomma)
     long long *dbg;             // VROD_BATCHED_DEBUG set: per-CTA cycle counters [grid][8]
 };
 
@@ -147,11 +148,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-}
-__device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr) {
-    uint32_t r;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-    return r;
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -264,9 +260,16 @@ __device__ __forceinline__ float block_max(const uint32_t (&r)[32], const float 
     return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// Rare pass: the same test per score -> bit mask of the columns this thread's row is a candidate for
+// Rare path: this THREAD's row beat some threshold among the 32 columns it holds in registers.  The thread
+// appends its survivors itself -- one shared-memory atomic per candidate, no warp collectives, no TMEM re-read --
+// so the other lanes and warps are not involved.  The code is kept COMPACT on purpose: a dense mask pass, then a
+// loop over the set bits that picks the score out of the 32 registers with a 5-level select tree (31 selects;
+// a run-time register index would push the block into local memory).  Cold straight-line code is paid for in
+// instruction-cache misses: the fully unrolled per-column form (15 KB) cost ~2500 cycles per entry, and round 1's
+// warp-collective form (TMEM re-read + ballot transpose) ~2000 while holding the accumulator stage.
 template <bool COS>
-__device__ __forceinline__ uint32_t filter_mask(const uint32_t (&r)[32], const float *thr, float hx) {
+__device__ __forceinline__ void thread_append(const uint32_t (&r)[32], const float *thr, float hx, int colbase, uint32_t row, BatchCtl *ctl,
+                                              unsigned long long *cand, int *qflags, uint32_t qbase, uint32_t b) {
     uint32_t m0 = 0, m1 = 0;
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
@@ -279,103 +282,27 @@ __device__ __forceinline__ uint32_t filter_mask(const uint32_t (&r)[32], const f
             else m0 |= hit ? (1u << (j4 * 4 + e)) : 0u;
         }
     }
-    return m0 | m1;
-}
-
-// Rare path, kept out of line so that the hot loop stays small: some row of this warp beat some threshold in
-// this accumulator half.  Re-reads the 4 column blocks from TMEM and appends the survivors to the lists.
-template <bool COS>
-__device__ __noinline__ void append_candidates(uint32_t taddr, int col0, uint32_t anycb, float hx, bool rowok, uint32_t row, BatchCtl *ctl,
-                                               unsigned long long *cand, int *qflags, uint32_t qbase, uint32_t b, int lane) {
+    uint32_t mask = m0 | m1;
 #pragma unroll 1
-    for (int cb = 0; cb < BN / 64; ++cb) {
-        if (!(anycb & (1u << cb))) continue;   // warp-uniform
-        uint32_t r[32];
-        tc_ld32(taddr + cb * 32, r);
-        tc_wait_ld();
-        const int colbase = col0 + cb * 32;
-        uint32_t mask = filter_mask<COS>(r, ctl->thr + colbase, hx);
-        if (!rowok) mask = 0;
-        uint32_t colmask = __reduce_or_sync(kFull, mask);
-        if (!colmask) continue;
-        if (__popc(colmask) <= 3) {
-            // sparse block (the common case of the large phases: one or two candidates): per column one ballot,
-            // one shared-memory atomic by the first candidate lane, one TMEM re-read of that column
-            while (colmask) {
-                const int jj = __ffs(colmask) - 1;
-                colmask &= colmask - 1;
-                const bool mine = (mask >> jj) & 1u;
-                const unsigned m = __ballot_sync(kFull, mine);
-                const int leader = __ffs(m) - 1;
-                const int q = colbase + jj;
-                int b0 = 0;
-                if (lane == leader) {
-                    b0 = atomicAdd(&ctl->cnt[q], __popc(m));
-                    if (b0 + __popc(m) > PRUNE_AT) *(volatile int *)&ctl->flag = 1;
-                }
-                const float dot = __uint_as_float(tc_ld1(taddr + cb * 32 + jj));   // (a run-time r[jj] would spill the block)
-                tc_wait_ld();
-                b0 = __shfl_sync(kFull, b0, leader);
-                if (mine) {
-                    const int pos = b0 + __popc(m & ((1u << lane) - 1));
-                    const float v = COS ? -(dot * hx) : (hx - dot);
-                    if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
-                    else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
-                }
-            }
-            continue;
-        }
-        // transpose the 32x32 candidate bit matrix: lane j learns which rows hit column j and claims that many
-        // slots of query j's list -- ONE shared-memory atomic instruction for the whole warp
-        unsigned mcol = 0;
+    while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        uint32_t s16[16], s8[8], s4[4], s2[2];
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-            const unsigned m = __ballot_sync(kFull, (mask >> jj) & 1u);
-            if (lane == jj) mcol = m;
-        }
-        const int c = __popc(mcol);
-        int base = 0;
-        if (c) {
-            base = atomicAdd(&ctl->cnt[colbase + lane], c);
-            if (base + c > PRUNE_AT) *(volatile int *)&ctl->flag = 1;
-        }
-        if (__popc(colmask) >= 6) {
-            // dense block (early phases: most columns have candidates): walk all 32 columns with the scores
-            // already in registers -- static register indices, no TMEM re-read
+        for (int i = 0; i < 16; ++i) s16[i] = (j & 16) ? r[i + 16] : r[i];
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-                if (colmask & (1u << jj)) {
-                    const int b0 = __shfl_sync(kFull, base, jj);
-                    const unsigned m = __shfl_sync(kFull, mcol, jj);
-                    if ((mask >> jj) & 1u) {
-                        const int q = colbase + jj;
-                        const int pos = b0 + __popc(m & ((1u << lane) - 1));
-                        const float dot = __uint_as_float(r[jj]);
-                        const float v = COS ? -(dot * hx) : (hx - dot);
-                        if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
-                        else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
-                    }
-                }
-            }
-            continue;
-        }
-        while (colmask) {   // sparse block: warp-uniform loop over the few columns that have candidates
-            const int jj = __ffs(colmask) - 1;
-            colmask &= colmask - 1;
-            // each lane re-reads its own score of column jj from TMEM (a run-time register index would push the
-            // whole block into local memory; measured slower)
-            const float dot = __uint_as_float(tc_ld1(taddr + cb * 32 + jj));
-            tc_wait_ld();
-            const int b0 = __shfl_sync(kFull, base, jj);
-            const unsigned m = __shfl_sync(kFull, mcol, jj);
-            if ((mask >> jj) & 1u) {
-                const int q = colbase + jj;
-                const int pos = b0 + __popc(m & ((1u << lane) - 1));
-                const float v = COS ? -(dot * hx) : (hx - dot);
-                if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
-                else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
-            }
-        }
+        for (int i = 0; i < 8; ++i) s8[i] = (j & 8) ? s16[i + 8] : s16[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s4[i] = (j & 4) ? s8[i + 4] : s8[i];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) s2[i] = (j & 2) ? s4[i + 2] : s4[i];
+        const float dot = __uint_as_float((j & 1) ? s2[1] : s2[0]);
+        const int q = colbase + j;
+        const int pos = atomicAdd(&ctl->cnt[q], 1);
+        if (pos >= PRUNE_AT) *(volatile int *)&ctl->flag = 1;
+        const float v = COS ? -(dot * hx) : (hx - dot);
+        if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
+        else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
     }
 }
 
@@ -519,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                     const uint32_t b_addr = p.stream_q ? a_addr + SLAB_A_BYTES : smem_u32(q_s + (size_t)s * SLAB_B);
 #pragma unroll
                     for (int kk = 0; kk < KS / UMMA_K; ++kk) {
+                        if (p.debug_skip & 2) break;
                         const uint64_t ad = umma_desc_sw128(a_addr + kk * UMMA_K * 4), bd = umma_desc_sw128(b_addr + kk * UMMA_K * 4);
                         const uint32_t accum = (s | (uint32_t)kk) != 0 ? 1u : 0u;
                         if constexpr (PSZ == 2) tc_mma_tf32_pair(d_tmem, ad, bd, idesc_tf32(2), accum);
@@ -570,31 +498,35 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * BN + half * (BN / 2);
             // Hot loop: branch-free filter of this warp's 32 rows x 128 columns, 32 columns at a time, the next
-            // TMEM load in flight while the current block is compared.  Not unrolled, rare path out of line:
-            // the body must stay inside the instruction cache (a fully unrolled version was 130 KB of SASS
-            // and ran at ~0.04 IPC on instruction fetch).
+            // TMEM load in flight while the current block is compared.  Not unrolled, rare path marked unlikely
+            // (placed out of line): the body must stay inside the instruction cache (a fully unrolled version
+            // was 130 KB of SASS and ran at ~0.04 IPC on instruction fetch).
             uint32_t ra[32], rb[32];
             const float *thr_h = ctl->thr + half * (BN / 2);
             const float ninf = -__int_as_float(0x7f800000);
-            uint32_t hitcb = 0;   // bit cb: this thread's row beats some threshold among columns [32 cb, 32 cb + 32)
-            tc_ld32(taddr, ra);
-            tc_wait_ld();
-#pragma unroll
-            for (int cb = 0; cb < BN / 64; cb += 2) {
-                tc_ld32(taddr + (cb + 1) * 32, rb);
-                const float wa = block_max<COS>(ra, thr_h + cb * 32, hx, ninf);
+            const int col_h = half * (BN / 2);
+            if (!(p.debug_skip & 1)) {
+                tc_ld32(taddr, ra);
                 tc_wait_ld();
-                if (cb + 2 < BN / 64) tc_ld32(taddr + (cb + 2) * 32, ra);
-                const float wb = block_max<COS>(rb, thr_h + (cb + 1) * 32, hx, ninf);
-                if (cb + 2 < BN / 64) tc_wait_ld();
-                hitcb |= (cand_hit<COS>(wa, hx) ? 1u : 0u) << cb;
-                hitcb |= (cand_hit<COS>(wb, hx) ? 1u : 0u) << (cb + 1);
-            }
-            if (!rowok) hitcb = 0;
-            const uint32_t anycb = __reduce_or_sync(kFull, hitcb);
-            if (anycb) {
-                n_slow++;
-                append_candidates<COS>(taddr, half * (BN / 2), anycb, hx, rowok, row, ctl, cand, p.qflags, g * BN, p.b, lane);
+#pragma unroll 1
+                for (int cb = 0; cb < BN / 64; cb += 2) {
+                    tc_ld32(taddr + (cb + 1) * 32, rb);
+                    const float wa = block_max<COS>(ra, thr_h + cb * 32, hx, ninf);
+                    if (__builtin_expect(cand_hit<COS>(wa, hx) && rowok, 0)) {
+                        n_slow++;
+                        thread_append<COS>(ra, thr_h + cb * 32, hx, col_h + cb * 32, row, ctl, cand, p.qflags, g * BN, p.b);
+                    }
+                    __syncwarp();
+                    tc_wait_ld();
+                    if (cb + 2 < BN / 64) tc_ld32(taddr + (cb + 2) * 32, ra);
+                    const float wb = block_max<COS>(rb, thr_h + (cb + 1) * 32, hx, ninf);
+                    if (__builtin_expect(cand_hit<COS>(wb, hx) && rowok, 0)) {
+                        n_slow++;
+                        thread_append<COS>(rb, thr_h + (cb + 1) * 32, hx, col_h + (cb + 1) * 32, row, ctl, cand, p.qflags, g * BN, p.b);
+                    }
+                    __syncwarp();
+                    if (cb + 2 < BN / 64) tc_wait_ld();
+                }
             }
             // accumulator stage drained: hand it back to the MMA warp (of the leader CTA)
             tc_fence_before();
@@ -967,7 +899,8 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         p.kprime = kprime;
         {
             const char *dbg = getenv("VROD_BATCHED_DEBUG");
-            p.debug_nocand = dbg && strcmp(dbg, "nocand") == 0;
+            p.debug_nocand = dbg && (strcmp(dbg, "nocand") == 0 || strstr(dbg, "noepi") || strstr(dbg, "nomma"));
+            p.debug_skip = dbg ? ((strstr(dbg, "noepi") ? 1 : 0) | (strstr(dbg, "nomma") ? 2 : 0)) : 0;
             static long long *dbg_buf = nullptr;
             if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 1024 * 16 * sizeof(long long));
             p.dbg = dbg ? dbg_buf : nullptr;
@@ -979,7 +912,13 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         const size_t slab_b = (size_t)slab_b_bytes((int)psz);
         const size_t resident = p.stream_q ? 0 : (size_t)nslab * slab_b;
         const size_t stage_bytes = p.stream_q ? (SLAB_A_BYTES + slab_b) : SLAB_A_BYTES;
-        size_t stages = (227 * 1024 - resident - sizeof(BatchCtl) - 1024) / stage_bytes;
+        // (dynamic shared memory starts 1024-byte aligned -- the kernel has no static shared memory and traps
+        // otherwise -- so no alignment slack is reserved: at dim 128 that is what makes the 6th stage fit)
+        size_t stages = (227 * 1024 - resident - sizeof(BatchCtl)) / stage_bytes;
+        {
+            static const int st_env = getenv("VROD_BATCHED_STAGES") ? atoi(getenv("VROD_BATCHED_STAGES")) : 0;
+            if (st_env >= 2 && (size_t)st_env < stages) stages = (size_t)st_env;
+        }
         if (stages > 8) stages = 8;
         if (stages < 2) return cudaErrorInvalidConfiguration;
         p.stages = (uint32_t)stages;
