@@ -161,7 +161,9 @@ VROD_API vrod_status vrod_collection_search_device(vrod_collection *c, const flo
 
 /* Force a path for tests and benches: 0 = automatic (default), 1 = f32 scan + rerank only where the
  * guard holds else exact (same as auto but never the batched path), 2 = always the exact f64 scan,
- * 3 = always the tensor-core batched path. */
+ * 3 = always the tensor-core batched path (bf16 operand mirror of the rows, built on first use; falls back to
+ * feeding the f32 rows as tf32 when the mirror does not fit in device memory), 4 = the batched path with
+ * tf32 operands and no mirror. */
 VROD_API vrod_status vrod_collection_set_path(vrod_collection *c, int path);
 
 VROD_API const char *vrod_last_error(void);

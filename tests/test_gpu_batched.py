@@ -1,5 +1,7 @@
-"""GPU parity tests of the batched-query path (tcgen05 tf32 tiles + exact f64 rerank + guard), forced with
-set_path(3), against the CPU oracle: bit-exact ids and distances, like the scan path."""
+"""GPU parity tests of the batched-query path (tcgen05 tiles + exact f64 rerank + guard) against the CPU oracle:
+bit-exact ids and distances, like the scan path.  set_path(3) forces the batched path in its default operand mode
+(bf16 mirror of the rows with the thresholds folded into the contraction), set_path(4) the tf32 mode that feeds the
+stored f32 rows."""
 import numpy as np
 import pytest
 
@@ -16,11 +18,12 @@ CASES = [  # n, d, metric, k, b
 ]
 
 
+@pytest.mark.parametrize("path", [3, 4], ids=["bf16", "tf32"])
 @pytest.mark.parametrize("n,d,metric,k,b", CASES)
-def test_batched_matches_oracle(ctx, oracle, n, d, metric, k, b):
-    c = ctx.create(f"b{n}_{d}_{metric}_{k}", d, metric, n)
+def test_batched_matches_oracle(ctx, oracle, n, d, metric, k, b, path):
+    c = ctx.create(f"b{n}_{d}_{metric}_{k}_{path}", d, metric, n)
     c.fill_synthetic(n, 300 + d)
-    c.set_path(3)
+    c.set_path(path)
     X = oracle.fill(n, d, 300 + d)
     Q = oracle.fill(b, d, 400 + d)
     s0 = ctx.stats()
@@ -62,6 +65,24 @@ def test_batched_is_chosen_automatically_for_large_batches(ctx, oracle):
     ctx.drop("auto_b3")
     ctx.drop("auto_b")
     ctx.drop("auto_b2")
+
+
+def test_mirror_follows_appends_and_growth(ctx, oracle):
+    """The bf16 mirror is built by the first batched search; rows inserted afterwards (including an insert that
+    makes the collection grow and reallocate) must be in it at the next search."""
+    d, k = 96, 10
+    X = oracle.fill(9000, d, 31)
+    Q = oracle.fill(130, d, 32)
+    for metric in (0, 1):
+        c = ctx.create(f"mir{metric}", d, metric, 4000)
+        c.set_path(3)
+        c.insert(X[:3000])
+        assert_same(*c.search(Q, k), *oracle.search(X[:3000], Q, k, metric), "first build")
+        c.insert(X[3000:3900])
+        assert_same(*c.search(Q, k), *oracle.search(X[:3900], Q, k, metric), "appended rows")
+        c.insert(X[3900:])          # beyond the capacity: the collection grows, the mirror is rebuilt
+        assert_same(*c.search(Q, k), *oracle.search(X, Q, k, metric), "after growth")
+        ctx.drop(c.name)
 
 
 def test_batched_guard_failures_are_rescanned(ctx, oracle):

@@ -19,7 +19,7 @@ def cases(draw):
     k = draw(st.sampled_from([1, 2, 10, 33, 100, 120]))
     b = draw(st.sampled_from([1, 2, 5, 64, 70]))
     metric = draw(st.sampled_from([0, 1]))
-    path = draw(st.sampled_from([0, 1, 2, 3]))      # auto, scan, exact, batched
+    path = draw(st.sampled_from([0, 1, 2, 3, 3, 4]))   # auto, scan, exact, batched (bf16 mirror), batched tf32
     seed = draw(st.integers(min_value=1, max_value=2**31))
     dup = draw(st.sampled_from([0, 0, 3, 40]))      # copies of one row planted elsewhere
     zero = draw(st.booleans())

@@ -9,10 +9,11 @@ from oracle import oracle as O
 ctx = ffi.Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream())
 bad = 0
+BPATH = int(os.environ.get("BPATH", "3"))   # 3 = batched (bf16 mirror), 4 = batched tf32
 def check(n, d, metric, k, b, seed=1):
     global bad
     name = f"c_{n}_{d}_{metric}"
-    c = ctx.create(name, d, metric, max(n, 1)); c.fill_synthetic(n, seed); c.set_path(3)
+    c = ctx.create(name, d, metric, max(n, 1)); c.fill_synthetic(n, seed); c.set_path(BPATH)
     X = O.fill(n, d, seed); Q = O.fill(b, d, seed + 1000)
     s0 = ctx.stats()
     ids, dist = c.search(Q, k)
@@ -37,7 +38,7 @@ for cs in cases:
     check(*cs)
 
 def timeit(n, d, metric, k, b, iters=3):
-    c = ctx.create("t", d, metric, n); c.fill_synthetic(n, 7); c.set_path(3)
+    c = ctx.create("t", d, metric, n); c.fill_synthetic(n, 7); c.set_path(BPATH)
     q = torch.from_numpy(O.fill(b, d, 8)).cuda()
     ids = torch.empty((b, k), dtype=torch.int64, device="cuda"); dist = torch.empty((b, k), dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
@@ -51,7 +52,7 @@ def timeit(n, d, metric, k, b, iters=3):
     kms, kn = ctx.profile_read(); ctx.profile(False)
     s1 = ctx.stats()
     tf = 2.0 * b * n * d / (kms / kn / 1e3) / 1e12
-    print(f"time n={n} d={d} metric={metric} k={k} b={b}: {dt*1e3:.2f} ms/batch {b/dt:.0f} qps; tile kernel {kms/kn:.3f} ms = {tf:.0f} TFLOP/s (tf32); rescanned={s1['fast_scans']-s0['fast_scans']}", flush=True)
+    print(f"time n={n} d={d} metric={metric} k={k} b={b}: {dt*1e3:.2f} ms/batch {b/dt:.0f} qps; tile kernel {kms/kn:.3f} ms = {tf:.0f} TFLOP/s (path {BPATH}); rescanned={s1['fast_scans']-s0['fast_scans']}", flush=True)
     ctx.drop("t")
 if len(sys.argv) > 1 and sys.argv[1] == "prof":
     timeit(1000000, 128, 0, 100, 1024, iters=2)

@@ -19,6 +19,7 @@
 #include "knn_batched.cuh"
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -42,7 +43,15 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM
 constexpr int SLAB_A_BYTES = BM * KS * 4;   // 16 KB: 128 rows x 128 B
 // query slab of one CTA: all BN queries (32 KB) alone, its half (16 KB) in a CTA pair
 __host__ __device__ constexpr int slab_b_bytes(int psz) { return BN / psz * KS * 4; }
-constexpr int MAX_SLABS = 4;                // dim <= 128: the query group stays resident (128 KB)
+constexpr int MAX_SLABS = 4;                // tf32, dim <= 128: the query group stays resident (128 KB)
+// bf16 operand mode ("H"): a K slab is 64 bf16 = the same 128-byte swizzle row, one MMA covers K = 16.  The mirror of
+// a row / a query is [kd data columns | 16 aux columns] (kd = dim rounded up to 16): the aux columns fold the query's
+// threshold and the row's norm term into the contraction (see build_mirror_kernel), so the accumulator already
+// holds the candidate test value.
+constexpr int KS_H = 64;
+constexpr int UMMA_K_H = 16;
+constexpr int AUX_H = 16;
+constexpr int MAX_SLABS_H = 5;              // bf16: (dim + 16) <= 320 columns resident (160 KB)
 
 struct BatchedParams {
     const float *sq_norm, *inv_norm;
@@ -55,6 +64,7 @@ struct BatchedParams {
     int *qflags;                // [b] |= 1 when a list could not be pruned (query is rescanned)
     int kprime;
     int stream_q;               // 1: the query slabs are streamed with the row slabs (dim > 128: the group does not fit)
+    uint32_t ksteps_last;       // MMA K steps in the last slab (the others hold 4)
     int debug_nocand;           // VROD_BATCHED_DEBUG=nocand: thresholds start at -inf (timing experiments only)
     int debug_skip;             // timing experiments only: bit 0 = epilogue skips the TMEM reads (noepi), bit 1 = no MMAs issued (nomma)
     long long *dbg;             // VROD_BATCHED_DEBUG set: per-CTA cycle counters [grid][8]
@@ -137,6 +147,14 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -164,6 +182,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 // kind::tf32, f32 accumulate, A and B K-major, N = 256, M = 128 (one CTA) or 256 (CTA pair: 128 rows per CTA)
 __host__ __device__ constexpr uint32_t idesc_tf32(int psz) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * psz) >> 4) << 24);
+}
+
+// kind::f16 with bf16 A and B, f32 accumulate, both K-major, N = 256, M = 128
+__host__ __device__ constexpr uint32_t idesc_bf16() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 struct BatchCtl {
@@ -260,6 +283,20 @@ __device__ __forceinline__ float block_max(const uint32_t (&r)[32], const float 
     return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
+// bf16 mode: the accumulator already holds D = dot + thr_q - ||x||^2/2 (cosine: dot^ + thr_q), so the hot filter is a
+// bare maximum over the 32 columns (half a FMNMX3 per score) and "candidate" means D > 0.
+__device__ __forceinline__ float block_max_h(const uint32_t (&r)[32]) {
+    float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
+#pragma unroll
+    for (int j4 = 1; j4 < 8; ++j4) {
+        m0 = fmaxf(m0, __uint_as_float(r[j4 * 4 + 0]));
+        m1 = fmaxf(m1, __uint_as_float(r[j4 * 4 + 1]));
+        m2 = fmaxf(m2, __uint_as_float(r[j4 * 4 + 2]));
+        m3 = fmaxf(m3, __uint_as_float(r[j4 * 4 + 3]));
+    }
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
 // Rare path: this THREAD's row beat some threshold among the 32 columns it holds in registers.  The thread
 // appends its survivors itself -- one shared-memory atomic per candidate, no warp collectives, no TMEM re-read --
 // so the other lanes and warps are not involved.  The code is kept COMPACT on purpose: a dense mask pass, then a
@@ -267,19 +304,29 @@ __device__ __forceinline__ float block_max(const uint32_t (&r)[32], const float 
 // a run-time register index would push the block into local memory).  Cold straight-line code is paid for in
 // instruction-cache misses: the fully unrolled per-column form (15 KB) cost ~2500 cycles per entry, and round 1's
 // warp-collective form (TMEM re-read + ballot transpose) ~2000 while holding the accumulator stage.
-template <bool COS>
+// (H = bf16 mode: the register holds D, a candidate is D > 0 and its surrogate is v = thr_q - D.)
+template <bool COS, bool H>
 __device__ __forceinline__ void thread_append(const uint32_t (&r)[32], const float *thr, float hx, int colbase, uint32_t row, BatchCtl *ctl,
                                               unsigned long long *cand, int *qflags, uint32_t qbase, uint32_t b) {
     uint32_t m0 = 0, m1 = 0;
+    if constexpr (H) {
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 th = *reinterpret_cast<const float4 *>(thr + j4 * 4);
-        const float t4[4] = {th.x, th.y, th.z, th.w};
+        for (int j = 0; j < 32; ++j) {
+            const bool hit = __uint_as_float(r[j]) > 0.f;
+            if (j & 1) m1 |= hit ? (1u << j) : 0u;
+            else m0 |= hit ? (1u << j) : 0u;
+        }
+    } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const bool hit = cand_hit<COS>(cand_w<COS>(__uint_as_float(r[j4 * 4 + e]), t4[e], hx), hx);
-            if (e & 1) m1 |= hit ? (1u << (j4 * 4 + e)) : 0u;
-            else m0 |= hit ? (1u << (j4 * 4 + e)) : 0u;
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 th = *reinterpret_cast<const float4 *>(thr + j4 * 4);
+            const float t4[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool hit = cand_hit<COS>(cand_w<COS>(__uint_as_float(r[j4 * 4 + e]), t4[e], hx), hx);
+                if (e & 1) m1 |= hit ? (1u << (j4 * 4 + e)) : 0u;
+                else m0 |= hit ? (1u << (j4 * 4 + e)) : 0u;
+            }
         }
     }
     uint32_t mask = m0 | m1;
@@ -300,7 +347,7 @@ __device__ __forceinline__ void thread_append(const uint32_t (&r)[32], const flo
         const int q = colbase + j;
         const int pos = atomicAdd(&ctl->cnt[q], 1);
         if (pos >= PRUNE_AT) *(volatile int *)&ctl->flag = 1;
-        const float v = COS ? -(dot * hx) : (hx - dot);
+        const float v = H ? (thr[j] - dot) : (COS ? -(dot * hx) : (hx - dot));
         if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
         else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
     }
@@ -312,12 +359,15 @@ __device__ __forceinline__ void thread_append(const uint32_t (&r)[32], const flo
 // peer's idle MMA warp forwards "slab landed" to the leader.  The 1-CTA kernel spends ~2600 instead of 2048
 // cycles per tile in the MMA (12 KB of shared-memory operands per K=8 step); the pair was meant to cut that to
 // 8 KB per CTA but measured slower in round 1.
-template <bool COS, int PSZ>
+// H = bf16 operand mode (PSZ = 1 only): operands are the bf16 mirrors with the folded aux columns, MMA kind::f16.
+template <bool COS, int PSZ, bool H>
 __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                    const __grid_constant__ CUtensorMap tmQ,
                                                                    const BatchedParams p) {
+    static_assert(!(H && PSZ == 2), "the bf16 mode has no CTA-pair variant");
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int SLAB_B = slab_b_bytes(PSZ);
+    constexpr int KSE = H ? KS_H : KS;   // elements per K slab (128 bytes either way)
     // resident mode: [nslab query slabs][stages row slabs]; streamed mode: [stages x (row slab + query slab)]
     const uint32_t stage_bytes = p.stream_q ? (SLAB_A_BYTES + SLAB_B) : SLAB_A_BYTES;
     unsigned char *q_s = smem;
@@ -383,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             auto arm = [&](uint64_t *bar, uint32_t bytes) { mbar_expect_tx(bar, bytes); };
             if (!p.stream_q) {
                 arm(&ctl->qfull, p.nslab * SLAB_B);
-                for (uint32_t s = 0; s < p.nslab; ++s) load(q_s + (size_t)s * SLAB_B, &tmQ, (int)(s * KS), q_row0, &ctl->qfull);
+                for (uint32_t s = 0; s < p.nslab; ++s) load(q_s + (size_t)s * SLAB_B, &tmQ, (int)(s * KSE), q_row0, &ctl->qfull);
             }
             uint32_t stage = 0, phase = 0;
             long long w_empty = 0;
@@ -394,8 +444,8 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
                     if (p.dbg) w_empty += clock64() - te;
                     arm(&ctl->full[stage], stage_bytes);
-                    load(a_s + (size_t)stage * stage_bytes, &tmX, (int)(s * KS), (int)(tile * BM), &ctl->full[stage]);
-                    if (p.stream_q) load(a_s + (size_t)stage * stage_bytes + SLAB_A_BYTES, &tmQ, (int)(s * KS), q_row0, &ctl->full[stage]);
+                    load(a_s + (size_t)stage * stage_bytes, &tmX, (int)(s * KSE), (int)(tile * BM), &ctl->full[stage]);
+                    if (p.stream_q) load(a_s + (size_t)stage * stage_bytes + SLAB_A_BYTES, &tmQ, (int)(s * KSE), q_row0, &ctl->full[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -444,12 +494,14 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(a_s + (size_t)stage * stage_bytes);
                     const uint32_t b_addr = p.stream_q ? a_addr + SLAB_A_BYTES : smem_u32(q_s + (size_t)s * SLAB_B);
+                    const uint32_t nk = s + 1 == p.nslab ? p.ksteps_last : 4u;   // 4 MMA K steps of 32 bytes per slab
 #pragma unroll
-                    for (int kk = 0; kk < KS / UMMA_K; ++kk) {
-                        if (p.debug_skip & 2) break;
-                        const uint64_t ad = umma_desc_sw128(a_addr + kk * UMMA_K * 4), bd = umma_desc_sw128(b_addr + kk * UMMA_K * 4);
-                        const uint32_t accum = (s | (uint32_t)kk) != 0 ? 1u : 0u;
-                        if constexpr (PSZ == 2) tc_mma_tf32_pair(d_tmem, ad, bd, idesc_tf32(2), accum);
+                    for (uint32_t kk = 0; kk < 4; ++kk) {
+                        if ((p.debug_skip & 2) || kk >= nk) break;
+                        const uint64_t ad = umma_desc_sw128(a_addr + kk * 32), bd = umma_desc_sw128(b_addr + kk * 32);
+                        const uint32_t accum = (s | kk) != 0 ? 1u : 0u;
+                        if constexpr (H) tc_mma_bf16(d_tmem, ad, bd, idesc_bf16(), accum);
+                        else if constexpr (PSZ == 2) tc_mma_tf32_pair(d_tmem, ad, bd, idesc_tf32(2), accum);
                         else tc_mma_tf32(d_tmem, ad, bd, idesc_tf32(1), accum);
                     }
                     // frees the slab (in both CTAs) when these MMAs have read it
@@ -481,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
         // sit on the critical path of every tile)
         // (the raw value is kept and scaled only when used, so nothing waits on the load here)
         auto row_factor = [&](uint32_t r) -> float {
-            if (r >= p.n) return 0.f;
+            if (H || r >= p.n) return 0.f;   // bf16 mode: the norm term is inside the contraction
             return COS ? __ldg(p.inv_norm + r) : __ldg(p.sq_norm + r);
         };
         float hx_next = my_tiles ? row_factor(tile_of(0) * BM + quad * 32 + lane) : 0.f;
@@ -511,18 +563,18 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
 #pragma unroll 1
                 for (int cb = 0; cb < BN / 64; cb += 2) {
                     tc_ld32(taddr + (cb + 1) * 32, rb);
-                    const float wa = block_max<COS>(ra, thr_h + cb * 32, hx, ninf);
-                    if (__builtin_expect(cand_hit<COS>(wa, hx) && rowok, 0)) {
+                    const float wa = H ? block_max_h(ra) : block_max<COS>(ra, thr_h + cb * 32, hx, ninf);
+                    if (__builtin_expect((H ? wa > 0.f : cand_hit<COS>(wa, hx)) && rowok, 0)) {
                         n_slow++;
-                        thread_append<COS>(ra, thr_h + cb * 32, hx, col_h + cb * 32, row, ctl, cand, p.qflags, g * BN, p.b);
+                        thread_append<COS, H>(ra, thr_h + cb * 32, hx, col_h + cb * 32, row, ctl, cand, p.qflags, g * BN, p.b);
                     }
                     __syncwarp();
                     tc_wait_ld();
                     if (cb + 2 < BN / 64) tc_ld32(taddr + (cb + 2) * 32, ra);
-                    const float wb = block_max<COS>(rb, thr_h + (cb + 1) * 32, hx, ninf);
-                    if (__builtin_expect(cand_hit<COS>(wb, hx) && rowok, 0)) {
+                    const float wb = H ? block_max_h(rb) : block_max<COS>(rb, thr_h + (cb + 1) * 32, hx, ninf);
+                    if (__builtin_expect((H ? wb > 0.f : cand_hit<COS>(wb, hx)) && rowok, 0)) {
                         n_slow++;
-                        thread_append<COS>(rb, thr_h + (cb + 1) * 32, hx, col_h + (cb + 1) * 32, row, ctl, cand, p.qflags, g * BN, p.b);
+                        thread_append<COS, H>(rb, thr_h + (cb + 1) * 32, hx, col_h + (cb + 1) * 32, row, ctl, cand, p.qflags, g * BN, p.b);
                     }
                     __syncwarp();
                     if (cb + 2 < BN / 64) tc_wait_ld();
@@ -579,6 +631,113 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
 }
 
 // -------------------------------------------------------------------------------------------------
+// bf16 operand mode: mirrors of the rows and of the queries with the folded aux columns
+// -------------------------------------------------------------------------------------------------
+// Mirror layout per row / query: [kd data columns][16 aux columns], bf16, kd = dim rounded up to 16.
+//   rows (A operand)            Euclidean  x_j              | 1 1 1 -h0 -h1 -h2 0...   (h0+h1+h2 = ||x||^2/2 exactly)
+//                               cosine     x_j / ||x||      | 1 1 1  0 ...
+//   queries (B operand)         Euclidean  q_j              | t0 t1 t2 1 1 1 0...      (t0+t1+t2 = thr_q exactly)
+//                               cosine     q_j              | t0 t1 t2 0 ...
+// so the contraction over kd + 16 columns is D = dot~ + thr_q - ||x||^2/2 (cosine: dot^ + thr_q): the candidate
+// test "surrogate < thr_q" is D > 0 and the epilogue needs neither the thresholds nor the row norms.  An f32 splits
+// into three bf16 parts exactly (3 x 8 significant bits); products with 1.0 are exact in the tensor core.
+__device__ __forceinline__ float split3(float v, unsigned short (&t)[3]) {
+    const __nv_bfloat16 a = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(a);
+    const __nv_bfloat16 b = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(b);
+    const __nv_bfloat16 c = __float2bfloat16_rn(r2);
+    t[0] = __bfloat16_as_ushort(a);
+    t[1] = __bfloat16_as_ushort(b);
+    t[2] = __bfloat16_as_ushort(c);
+    return (__bfloat162float(a) + __bfloat162float(b)) + __bfloat162float(c);   // the value the parts stand for
+}
+__device__ __forceinline__ unsigned short bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+constexpr unsigned short kBf16One = 0x3F80;
+
+// rows [row0, row0 + n) of the shard -> mirror.  One warp per row, a lane writes 8 columns (16 bytes) at a time.
+template <bool COS>
+__global__ void __launch_bounds__(256) build_mirror_kernel(const float *__restrict__ rows, const float *__restrict__ sq_norm,
+                                                           const float *__restrict__ inv_norm, uint32_t row0, uint32_t n, uint32_t ld,
+                                                           uint32_t kd, uint32_t ld_h, unsigned short *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t wpg = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += wpg) {
+        const uint32_t r = row0 + i;
+        const float *x = rows + (size_t)r * ld;
+        const float scale = COS ? __ldg(inv_norm + r) : 1.f;
+        unsigned short h[3] = {0, 0, 0};
+        if (!COS) split3(0.5f * __ldg(sq_norm + r), h);
+        for (uint32_t c0 = lane * 8; c0 < ld_h; c0 += 256) {
+            unsigned short v[8];
+#pragma unroll
+            for (int g4 = 0; g4 < 2; ++g4) {
+                const uint32_t c = c0 + g4 * 4;
+                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < ld && c < kd) f = *reinterpret_cast<const float4 *>(x + c);   // ld % 4 == 0; columns >= dim hold zeros
+                v[g4 * 4 + 0] = bf16_bits(f.x * scale);
+                v[g4 * 4 + 1] = bf16_bits(f.y * scale);
+                v[g4 * 4 + 2] = bf16_bits(f.z * scale);
+                v[g4 * 4 + 3] = bf16_bits(f.w * scale);
+            }
+            if (c0 >= kd) {   // aux columns (kd % 16 == 0: an 8-column chunk is all data or all aux)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0;
+                if (c0 == kd) {
+                    v[0] = v[1] = v[2] = kBf16One;
+                    if (!COS) {
+                        v[3] = h[0] ^ 0x8000;
+                        v[4] = h[1] ^ 0x8000;
+                        v[5] = h[2] ^ 0x8000;
+                    }
+                }
+            }
+            uint4 w;
+            w.x = v[0] | ((uint32_t)v[1] << 16);
+            w.y = v[2] | ((uint32_t)v[3] << 16);
+            w.z = v[4] | ((uint32_t)v[5] << 16);
+            w.w = v[6] | ((uint32_t)v[7] << 16);
+            *reinterpret_cast<uint4 *>(out + (size_t)r * ld_h + c0) = w;
+        }
+    }
+}
+
+// Queries of one wave -> mirror, with the START threshold: no finite k'-th key exists yet, so the threshold is a
+// finite cap above every possible surrogate (every row passes) -- an infinite one would poison D = dot + thr - hx.
+//   Euclidean  v = ||x||^2/2 - dot  <=  M/2 + sqrt(M) ||q||   (M = max ||x||^2 of the shard)
+//   cosine     v = -dot/||x||       <=  ||q||
+// One warp per query.
+template <bool COS>
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restrict__ q, uint32_t b, uint32_t ld, uint32_t kd, uint32_t ld_h,
+                                                           const unsigned int *__restrict__ maxnorm_bits, unsigned short *__restrict__ qh,
+                                                           float *__restrict__ gthr, float *__restrict__ qcap) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= b) return;
+    const float *x = q + (size_t)qi * ld;
+    float nq = 0.f;
+    for (uint32_t c = lane; c < ld; c += 32) nq = fmaf(x[c], x[c], nq);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nq += __shfl_xor_sync(kFull, nq, o);
+    const float nqs = sqrtf(nq) * 1.0001f;
+    const float M = __uint_as_float(*maxnorm_bits);
+    const float cap = (COS ? nqs : fmaf(sqrtf(M), nqs, 0.5f * M)) * 1.02f + 1e-30f;
+    unsigned short t[3];
+    const float thr = split3(cap, t);
+    for (uint32_t c = lane; c < ld_h; c += 32) {
+        unsigned short v = 0;
+        if (c < kd) v = c < ld ? bf16_bits(x[c]) : 0;
+        else if (c < kd + 3) v = t[c - kd];
+        else if (!COS && c < kd + 6) v = kBf16One;
+        qh[(size_t)qi * ld_h + c] = v;
+    }
+    if (lane == 0) {
+        gthr[qi] = thr;
+        qcap[qi] = thr;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // finish: one CTA per query -- merge the CTA lists, exact rerank, guard, hits
 // -------------------------------------------------------------------------------------------------
 struct FinishParams {
@@ -599,10 +758,18 @@ struct FinishParams {
     int first_phase;                    // 1: glist is empty
     int *status;
     Hit *out;
-    double eps_dot;         // relative error of the tf32 dot product w.r.t. ||x|| ||q||
+    double eps_dot;         // relative error of the tf32 / bf16 dot product w.r.t. ||x|| ||q||
+    // bf16 operand mode (qh != nullptr): the next phase's threshold goes into the query mirror's aux columns
+    unsigned short *qh;     // [b][ld_h]
+    uint32_t ld_h, kd;
+    const float *qcap;      // [b] the finite start threshold (above every surrogate)
+    double acc_eps;         // f32 accumulation noise of the folded contraction, relative to |dot| + |thr| + |hx|
 };
 
 constexpr int kFinCtl = 128;
+constexpr int kFinCap = 2048;                       // keys the finish kernel's selection buffer holds
+constexpr int kFinPer = kFinCap / kScanThreads;     // keys per thread in block_select
+constexpr int kFinHist = 264;                       // ints: 256 bins + selected bin, rank, size + the threshold key
 
 template <bool COS>
 __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const FinishParams p) {
@@ -625,7 +792,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
     }
     // offsets of this query's lists (previous global list first, then one list per CTA of the group):
     // warp 0 loads the counts and scans them 32 at a time
-    int *offs = reinterpret_cast<int *>(buf + p.cap);   // [nlists + 2]
+    int *hist = reinterpret_cast<int *>(buf + p.cap);   // [kFinHist] block_select scratch
+    int *offs = hist + kFinHist;                        // [nlists + 2]
     if (warp == 0) {
         int carry = p.first_phase ? 0 : p.gcnt[qi];
         if (lane == 0) {
@@ -673,7 +841,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
         __syncthreads();
         if (tid == 0) ctl->cnt = prev;
         __syncthreads();
-        block_prune(ctl, buf, p.kprime, p.cap, tid);
+        block_select<kFinPer>(ctl, buf, p.kprime, p.cap, tid, hist);
         // rounds of half the free space: after the first select the threshold passes only a few percent of a
         // round, so most rounds are a plain load + filter and the (latency-bound) sort runs only when the buffer
         // could overflow in the next round -- sorting every round cost 3x more barrier stages
@@ -709,22 +877,35 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
             }
             __syncthreads();
             const bool no_threshold_yet = ctl->thrkey == kKeyMax && ctl->cnt >= p.kprime;
-            if (ctl->cnt > p.cap - round || no_threshold_yet) block_prune(ctl, buf, p.kprime, p.cap, tid);   // uniform
+            if (ctl->cnt > p.cap - round || no_threshold_yet) block_select<kFinPer>(ctl, buf, p.kprime, p.cap, tid, hist);   // uniform
         }
     }
     __syncthreads();
-    block_prune(ctl, buf, p.kprime, p.cap, tid);
+    block_select<kFinPer>(ctl, buf, p.kprime, p.cap, tid, hist);
 
     const int ncand = ctl->cnt;
     if (!p.final_phase) {
         for (int i = tid; i < ncand; i += kScanThreads) p.glist[(size_t)qi * p.kprime + i] = buf[i];
         if (tid == 0) {
             p.gcnt[qi] = ncand;
-            p.gthr[qi] = ncand == p.kprime ? ord2f((uint32_t)(buf[ncand - 1] >> 32)) : __int_as_float(0x7f800000);
+            // (the kept keys are unsorted: the kprime-th one is the select's threshold key)
+            float thr = ncand == p.kprime ? ord2f((uint32_t)(ctl->thrkey >> 32)) : __int_as_float(0x7f800000);
+            if (p.qh) {   // bf16 mode: finite thresholds only, folded into the query mirror as three exact parts
+                const float cap = p.qcap[qi];
+                if (!(thr < cap)) thr = cap;
+                unsigned short t[3];
+                thr = split3(thr, t);
+                unsigned short *aux = p.qh + (size_t)qi * p.ld_h + p.kd;
+                aux[0] = t[0];
+                aux[1] = t[1];
+                aux[2] = t[2];
+            }
+            p.gthr[qi] = thr;
         }
         return;
     }
-    if (tid == 0) ctl->u_val = ncand > 0 ? ord2f((uint32_t)(buf[ncand - 1] >> 32)) : 0.f;
+    // u = the largest kept approximate key: the select's threshold key, or the tail of the (sorted) short list
+    if (tid == 0) ctl->u_val = ncand == p.kprime ? ord2f((uint32_t)(ctl->thrkey >> 32)) : (ncand > 0 ? ord2f((uint32_t)(buf[ncand - 1] >> 32)) : 0.f);
     __syncthreads();
     rerank_candidates<COS>(buf, ncand, p.rows4, q4, (int)p.ld4, ctl->nq, warp, lane);
     __syncthreads();
@@ -760,11 +941,13 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
                 lb = -1.f;
             } else if constexpr (COS) {
                 // v = -dot~ * inv~ ;  |v - (-dot/||x||)| <= (eps_dot + 3*2^-24) * ||q||
-                const double E = (p.eps_dot + 3.0e-7) * nqs + 1.2e-7 * fabs(u);
+                double E = (p.eps_dot + 3.0e-7) * nqs + 1.2e-7 * fabs(u);
+                if (p.qh) E += p.acc_eps * (1.01 * nqs + (double)p.qcap[qi] + fabs(u));
                 lb = nqs > 0.0 ? __double2float_rd(1.0 + (u - E) / nqs - 1.0e-12) : -1.f;
             } else {
                 // v = hx~ - dot~ ;  |v - (||x||^2/2 - dot)| <= eps_dot*||x||max*||q|| + 2^-23*(||x||max^2/2 + |u|)
-                const double E = (p.eps_dot + 2.4e-7) * __dsqrt_rn(xn_max) * nqs + 2.4e-7 * (0.5 * xn_max + fabs(u));
+                double E = (p.eps_dot + 2.4e-7) * __dsqrt_rn(xn_max) * nqs + 2.4e-7 * (0.5 * xn_max + fabs(u));
+                if (p.qh) E += p.acc_eps * (__dsqrt_rn(xn_max) * nqs + 0.5 * xn_max + (double)p.qcap[qi] + fabs(u));
                 double s = 2.0 * (u - E) + nq;
                 s -= 1.0e-12 * (fabs(s) + nq);
                 lb = s > 0.0 ? __double2float_rd(__dsqrt_rd(s)) : 0.f;
@@ -796,15 +979,15 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2D f32 tensor [rows][ld], box = {32 floats, box_rows}, 128-byte swizzle, zero fill out of bounds
-bool make_map(CUtensorMap *m, const float *base, uint64_t rows, uint32_t ld, uint32_t box_rows) {
+// 2D tensor [rows][ld] of f32 (bf16 = false) or bf16, box = {one 128-byte swizzle row, box_rows}, zero fill out of bounds
+bool make_map(CUtensorMap *m, const void *base, bool bf16, uint64_t rows, uint32_t ld, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn || rows == 0) return false;
     cuuint64_t dims[2] = {ld, rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {KS, box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)(bf16 ? KS_H : KS), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+    return fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -819,6 +1002,17 @@ int next_pow2i(int v) {
 
 }  // namespace
 
+uint32_t mirror_kd(uint32_t dim) { return (dim + 15u) & ~15u; }
+uint32_t mirror_ld(uint32_t dim) { return mirror_kd(dim) + AUX_H; }
+
+cudaError_t launch_build_mirror(const ShardView &s, unsigned short *rows_h, uint32_t row0, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t blocks = (n + 7) / 8 < 148u * 16u ? (n + 7) / 8 : 148u * 16u;
+    auto fn = s.metric ? build_mirror_kernel<true> : build_mirror_kernel<false>;
+    fn<<<blocks, 256, 0, st>>>(s.rows, s.sq_norm, s.inv_norm, row0, n, s.ld, mirror_kd(s.dim), mirror_ld(s.dim), rows_h);
+    return cudaGetLastError();
+}
+
 bool batched_supported(const ShardView &s, uint32_t b, uint32_t k) {
     if (s.n == 0 || b == 0) return false;
     if (s.ld > 4096) return false;
@@ -829,21 +1023,27 @@ bool batched_supported(const ShardView &s, uint32_t b, uint32_t k) {
 cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t b, uint32_t k, int sm_count, void **scratch,
                                   size_t *scratch_bytes, int *status, Hit *out, cudaStream_t st, BatchedStats *stats,
                                   cudaEvent_t ev_start, cudaEvent_t ev_stop) {
-    const uint32_t nslab = (s.ld + KS - 1) / KS;
+    // operand mode: bf16 mirrors with folded thresholds when the collection has a mirror, else the stored f32 rows as tf32
+    const bool H = s.rows_h != nullptr;
+    const uint32_t kd = mirror_kd(s.dim), ld_h = mirror_ld(s.dim);
+    const uint32_t nslab = H ? (ld_h + KS_H - 1) / KS_H : (s.ld + KS - 1) / KS;
+    const uint32_t ksteps_last = H ? (ld_h - (nslab - 1) * KS_H) / UMMA_K_H : (s.ld - (nslab - 1) * KS + UMMA_K - 1) / UMMA_K;
     const uint32_t ntiles = (s.n + BM - 1) / BM;
     uint32_t qgroups = (b + BN - 1) / BN;
     // one CTA per SM; query groups beyond the SM count are handled in waves
     cudaError_t e = cudaSuccess;
     int kprime = next_pow2i((int)(2 * k + 16));
     if (kprime < 64) kprime = 64;
-    const double eps_dot = ldexp(1.0, -9) * 1.01 + (double)s.ld * ldexp(1.0, -22);
+    // |dot~ - dot| <= eps_dot ||x|| ||q||: tf32 truncates both operands to 10 mantissa bits (2 x 2^-10); the bf16
+    // mirrors are rounded to nearest (2 x 2^-9); plus the f32 accumulation inside an MMA step
+    const double eps_dot = H ? ldexp(1.0, -8) * 1.01 + (double)ld_h * ldexp(1.0, -22) : ldexp(1.0, -9) * 1.01 + (double)s.ld * ldexp(1.0, -22);
 
     // One CTA per unit (cta_group::1) by default.  VROD_BATCHED_PAIR=1 selects the CTA-pair kernel (cta_group::2,
     // M = 256): it passes the same parity tests but measured SLOWER on B200 in round 1 (8.1 vs 5.6 ms per batch at
     // configs[2]: the MMA issue time per tile did not drop and the leader waits for operand slabs ~50 % of the
     // time), so it stays an experiment until that is understood.
     static const bool want_pair = getenv("VROD_BATCHED_PAIR") != nullptr;
-    const uint32_t psz = (want_pair && !(sm_count & 1)) ? 2u : 1u;
+    const uint32_t psz = (want_pair && !H && !(sm_count & 1)) ? 2u : 1u;
     const uint32_t max_units = (uint32_t)sm_count / psz;
     const uint32_t super_tiles = (ntiles + psz - 1) / psz;
 
@@ -863,7 +1063,8 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         const size_t cnt_bytes = (size_t)grid * BN * sizeof(int);
         const size_t flag_bytes = (((size_t)bq * sizeof(int)) + 255) & ~(size_t)255;
         const size_t glist_bytes = (size_t)bq * kprime * sizeof(unsigned long long);
-        const size_t need = cand_bytes + cnt_bytes + 3 * flag_bytes + glist_bytes + 256;
+        const size_t qh_bytes = H ? ((((size_t)bq * ld_h * sizeof(unsigned short)) + 255) & ~(size_t)255) : 0;
+        const size_t need = cand_bytes + cnt_bytes + 4 * flag_bytes + glist_bytes + qh_bytes + 256;
         if (*scratch_bytes < need) {
             if (*scratch) cudaFree(*scratch);
             *scratch = nullptr;
@@ -878,12 +1079,21 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         int *qflags = reinterpret_cast<int *>(base + cand_bytes + cnt_bytes);
         int *gcnt = reinterpret_cast<int *>(base + cand_bytes + cnt_bytes + flag_bytes);
         float *gthr = reinterpret_cast<float *>(base + cand_bytes + cnt_bytes + 2 * flag_bytes);
-        unsigned long long *glist = reinterpret_cast<unsigned long long *>(base + cand_bytes + cnt_bytes + 3 * flag_bytes);
+        float *qcap = reinterpret_cast<float *>(base + cand_bytes + cnt_bytes + 3 * flag_bytes);
+        unsigned long long *glist = reinterpret_cast<unsigned long long *>(base + cand_bytes + cnt_bytes + 4 * flag_bytes);
+        unsigned short *qh = reinterpret_cast<unsigned short *>(base + cand_bytes + cnt_bytes + 4 * flag_bytes + glist_bytes);
         e = cudaMemsetAsync(qflags, 0, flag_bytes, st);
         if (e != cudaSuccess) return e;
 
         CUtensorMap tmX, tmQ;
-        if (!make_map(&tmX, s.rows, s.n, s.ld, BM) || !make_map(&tmQ, qw, bq, s.ld, BN / psz)) return cudaErrorInvalidValue;
+        if (H) {
+            if (!make_map(&tmX, s.rows_h, true, s.n, ld_h, BM) || !make_map(&tmQ, qh, true, bq, ld_h, BN)) return cudaErrorInvalidValue;
+            auto prep = s.metric ? prep_queries_kernel<true> : prep_queries_kernel<false>;
+            prep<<<(bq + 7) / 8, 256, 0, st>>>(qw, bq, s.ld, kd, ld_h, s.maxnorm_bits, qh, gthr, qcap);
+            if (stats) stats->launches += 1;
+        } else if (!make_map(&tmX, s.rows, false, s.n, s.ld, BM) || !make_map(&tmQ, qw, false, bq, s.ld, BN / psz)) {
+            return cudaErrorInvalidValue;
+        }
 
         BatchedParams p{};
         p.sq_norm = s.sq_norm;
@@ -891,6 +1101,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         p.n = s.n;
         p.b = bq;
         p.nslab = nslab;
+        p.ksteps_last = ksteps_last;
         p.qgroups = groups;
         p.units = units;
         p.cand = cand;
@@ -908,7 +1119,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         }
         // dim <= 128: the query group is resident (nslab x 32 KB) and only row slabs stream; larger dims stream the
         // query slab next to every row slab (48 KB stages, L2-bandwidth bound: DESIGN.md)
-        p.stream_q = nslab > MAX_SLABS ? 1 : 0;
+        p.stream_q = nslab > (uint32_t)(H ? MAX_SLABS_H : MAX_SLABS) ? 1 : 0;
         const size_t slab_b = (size_t)slab_b_bytes((int)psz);
         const size_t resident = p.stream_q ? 0 : (size_t)nslab * slab_b;
         const size_t stage_bytes = p.stream_q ? (SLAB_A_BYTES + slab_b) : SLAB_A_BYTES;
@@ -924,8 +1135,9 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         p.stages = (uint32_t)stages;
         const size_t smem = resident + stages * stage_bytes + sizeof(BatchCtl);
         void (*tile_fn)(const CUtensorMap, const CUtensorMap, const BatchedParams) =
-            psz == 2 ? (s.metric ? batched_tile_kernel<true, 2> : batched_tile_kernel<false, 2>)
-                     : (s.metric ? batched_tile_kernel<true, 1> : batched_tile_kernel<false, 1>);
+            H          ? (s.metric ? batched_tile_kernel<true, 1, true> : batched_tile_kernel<false, 1, true>)
+            : psz == 2 ? (s.metric ? batched_tile_kernel<true, 2, false> : batched_tile_kernel<false, 2, false>)
+                       : (s.metric ? batched_tile_kernel<true, 1, false> : batched_tile_kernel<false, 1, false>);
         e = cudaFuncSetAttribute(tile_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         cudaLaunchConfig_t cfg{};
@@ -950,7 +1162,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         f.k = k;
         f.id_base = s.id_base;
         f.kprime = kprime;
-        f.cap = 2048;
+        f.cap = kFinCap;
         f.water = f.cap - kScanThreads;
         f.qgroups = groups;
         f.units = units;
@@ -965,7 +1177,12 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         f.status = status + (size_t)g0 * BN;
         f.out = out + (size_t)g0 * BN * k;
         f.eps_dot = eps_dot;
-        const size_t fsmem = kFinCtl + (size_t)f.cap * sizeof(unsigned long long) + ((size_t)cpg_max * psz + 2) * sizeof(int);
+        f.qh = H ? qh : nullptr;
+        f.ld_h = ld_h;
+        f.kd = kd;
+        f.qcap = qcap;
+        f.acc_eps = H ? (double)(ld_h / UMMA_K_H + 2) * ldexp(1.0, -23) : 0.0;
+        const size_t fsmem = kFinCtl + (size_t)f.cap * sizeof(unsigned long long) + ((size_t)kFinHist + (size_t)cpg_max * psz + 2) * sizeof(int);
         auto fin_fn = s.metric ? batched_finish_kernel<true> : batched_finish_kernel<false>;
 
         // Phases over the row tiles: 1 tile per CTA first, then each phase 3.5x the rows seen so far (phase
@@ -979,7 +1196,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             const bool last = t_end >= ntiles;
             p.tile_begin = t_begin;
             p.tile_end = t_end;
-            p.thr_init = first ? nullptr : gthr;
+            p.thr_init = (first && !H) ? nullptr : gthr;   // bf16 mode starts from the finite caps of prep_queries_kernel
             e = cudaLaunchKernelEx(&cfg, tile_fn, tmX, tmQ, p);
             if (e != cudaSuccess) return e;
             f.first_phase = first ? 1 : 0;

@@ -183,6 +183,11 @@ struct vrod_collection {
     int *flags = nullptr;     // device: bit0 non-finite value seen, bit1 value outside the f32 scan's safe range
     bool fast_ok = true;
     int path = 0;
+    // bf16 operand mirror for the batched path (knn_batched.cu), built lazily by the first batched search and
+    // extended when rows were appended since; rows [0, mirror_rows) are valid
+    unsigned short *rows_h = nullptr;
+    uint64_t mirror_rows = 0;
+    bool mirror_failed = false;   // the mirror did not fit: the batched path feeds the f32 rows as tf32 instead
 };
 
 static int *ctx_ticket(vrod_ctx *c) { return reinterpret_cast<int *>(c->small.p); }
@@ -334,6 +339,7 @@ static void collection_free(vrod_collection *c) {
     cudaFree(c->inv_norm);
     cudaFree(c->sq_norm);
     cudaFree(c->flags);
+    cudaFree(c->rows_h);
     delete c;
 }
 
@@ -546,7 +552,7 @@ extern "C" vrod_status vrod_collection_set_path(vrod_collection *c, int path) {
     return guarded([&]() -> vrod_status { return vrod_collection_set_path_impl(c, path); });
 }
 static vrod_status vrod_collection_set_path_impl(vrod_collection *c, int path) {
-    if (!c || path < 0 || path > 3) return fail(VROD_EINVAL, "bad path");
+    if (!c || path < 0 || path > 4) return fail(VROD_EINVAL, "bad path");
     c->path = path;
     return VROD_OK;
 }
@@ -568,6 +574,7 @@ static void shard_overlap(const vrod_collection *c, uint64_t g0, uint64_t n, uin
 // after new rows landed in [loc0, loc0+cnt): norms + validation
 static vrod_status finish_append(vrod_collection *c, uint64_t loc0, uint64_t cnt, bool check_flags) {
     vrod_ctx *ctx = c->ctx;
+    if (c->mirror_rows > loc0) c->mirror_rows = loc0;
     VROD_CUDA(launch_row_norms(c->rows, (uint32_t)loc0, (uint32_t)cnt, c->ld, c->inv_norm, c->sq_norm, c->flags, ctx->stream));
     if (cnt) ctx->stats.kernel_launches++;
     if (check_flags) {
@@ -605,6 +612,10 @@ static vrod_status collection_grow(vrod_collection *c, uint64_t need) {
         return fail(e == cudaErrorMemoryAllocation ? VROD_ENOMEM : VROD_ECUDA, std::string("growing the collection: ") + cudaGetErrorString(e));
     }
     cudaFree(c->rows); cudaFree(c->inv_norm); cudaFree(c->sq_norm);
+    cudaFree(c->rows_h);   // sized by the old capacity: rebuilt by the next batched search
+    c->rows_h = nullptr;
+    c->mirror_rows = 0;
+    c->mirror_failed = false;
     c->rows = rows; c->inv_norm = inv; c->sq_norm = sq;
     c->capacity = cap;
     c->shard_rows = cap;
@@ -826,11 +837,32 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         const double t_batched = 250e-6 + groups * ((double)s.n / 128.0) * 1.37e-6 * ((double)s.ld / 128.0) / (double)ctx->sms;
         prefer_batched = (double)b * t_scan > t_batched;
     }
-    const bool batched = !exact_only && batched_supported(s, b, k) && (c->path == 3 || (c->path == 0 && prefer_batched));
+    const bool batched = !exact_only && batched_supported(s, b, k) && (c->path == 3 || c->path == 4 || (c->path == 0 && prefer_batched));
     if (batched) {
+        ShardView sb = s;
+        if (c->path != 4 && !c->mirror_failed) {
+            // bf16 operand mirror: allocate once for the shard's capacity, convert the rows appended since the last time
+            if (!c->rows_h) {
+                const cudaError_t me = cudaMalloc(&c->rows_h, (size_t)c->shard_rows * mirror_ld(c->dim) * sizeof(unsigned short));
+                if (me != cudaSuccess) {
+                    cudaGetLastError();
+                    c->rows_h = nullptr;
+                    c->mirror_failed = true;
+                }
+                c->mirror_rows = 0;
+            }
+            if (c->rows_h) {
+                if (c->mirror_rows < c->local) {
+                    VROD_CUDA(launch_build_mirror(s, c->rows_h, (uint32_t)c->mirror_rows, (uint32_t)(c->local - c->mirror_rows), ctx->stream));
+                    ctx->stats.kernel_launches++;
+                    c->mirror_rows = c->local;
+                }
+                sb.rows_h = c->rows_h;
+            }
+        }
         BatchedStats bs{};
         cudaEvent_t e0 = ctx->profiling ? ctx->prof_event() : nullptr, e1 = ctx->profiling ? ctx->prof_event() : nullptr;
-        cudaError_t e = launch_batched_search(s, d_q, b, k, ctx->sms, &ctx->batched.p, &ctx->batched.bytes, d_status,
+        cudaError_t e = launch_batched_search(sb, d_q, b, k, ctx->sms, &ctx->batched.p, &ctx->batched.bytes, d_status,
                                               local, ctx->stream, &bs, e0, e1);
         if (e != cudaSuccess) return fail(VROD_ECUDA, std::string("batched search: ") + cudaGetErrorString(e));
         ctx->stats.kernel_launches += bs.launches;
