@@ -54,6 +54,21 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def measured_bf16_peak():
+    """Dense bf16 tensor peak from MEASURED_PEAKS.json: the SUSTAINED figure (the batched kernels are timed inside
+    a long run of back-to-back batches), with the burst figure beside it; else the profiling recipe's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        if "bf16_tflops_sustained" in d:
+            return float(d["bf16_tflops_sustained"]), float(d.get("bf16_tflops", d["bf16_tflops_sustained"])), \
+                "measured (MEASURED_PEAKS.json bf16_tflops_sustained: torch.matmul bf16 8192^3 back to back)"
+        if "bf16_tflops" in d:
+            return float(d["bf16_tflops"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    return 2250.0, 2250.0, "fallback (B200_PROFILING.md: 2.25 PFLOP/s dense bf16 nominal)"
+
+
 def ncu_traffic(workload):
     """dram bytes per scan launch from the committed ncu capture (profiles/roofline_traffic.json), else None."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -204,6 +219,8 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override the row count (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batched-kind", default="bf16", choices=["bf16", "tf32"],
+                    help="operand mode of the batched (tensor-core) path: bf16 mirror (default) or the f32 rows as tf32")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -238,6 +255,8 @@ def main():
     rows, dim, metric, k, batch, label = WORKLOADS[args.workload]
     coll = ctx.create("bench", dim, metric, rows)
     coll.fill_synthetic(rows, DATA_SEED)
+    if batch > 1 and args.batched_kind == "tf32":
+        coll.set_path(4)
     base, local_rows = coll.shard()
 
     # queries: one fresh Philox draw per step (never a row of X), generated by the library's own
@@ -343,15 +362,23 @@ def main():
         if used_batched:
             # batched path: a dense contraction, 2*B*N_local*d flops per step; the bracketed time is
             # the whole phased tile-kernel sequence (tiles + inter-phase merges) of one batch
-            tf32_peak = measure_tf32_peak()
             flops = 2.0 * batch * local_rows * dim
             ach = flops / (kern_avg_ms / 1e3) / 1e12
-            line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
-                                "frac": ach / tf32_peak, "traffic": traffic,
-                                "peak_source": "measured here: torch.matmul 8192^3 TF32, best of 10 (burst); the kernel's MMA kind is tf32",
-                                "kernel": "batched_tile_kernel (tcgen05.mma kind::tf32) + inter-phase batched_finish_kernel",
+            if args.batched_kind == "tf32":
+                tpeak, tburst = measure_tf32_peak(), None
+                tsrc = "measured here: torch.matmul 8192^3 TF32, best of 10 (burst); the kernel's MMA kind is tf32"
+                kname = "batched_tile_kernel (tcgen05.mma kind::tf32 on the stored f32 rows) + inter-phase batched_finish_kernel"
+            else:
+                tpeak, tburst, tsrc = measured_bf16_peak()
+                kname = ("batched_tile_kernel (tcgen05.mma kind::f16, bf16 mirror of the rows, thresholds folded into the "
+                         "contraction) + inter-phase batched_finish_kernel")
+            line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s",
+                                "frac": ach / tpeak, "traffic": traffic, "peak_source": tsrc, "peak_burst": tburst,
+                                "kernel": kname,
                                 "algorithmic_flops_per_step": flops, "kernel_ms": kern_avg_ms, "launches_timed": int(kern_n),
                                 "hbm_floor": {"algorithmic_bytes": algo_bytes, "peak_gbs": peak}}
+            line["config"]["arithmetic"] = (f"{args.batched_kind} tensor-core pass, exact f64 rerank + guard "
+                                            "(bit-identical to the oracle)")
         # cheap live check of the last answer: sorted, and the claimed rows sit at the claimed distances
         assert np.all(np.diff(last_dist, axis=1) >= 0)
         if world == 1 and not args.no_cpu_baseline:

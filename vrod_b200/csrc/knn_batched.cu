@@ -563,7 +563,8 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
 #pragma unroll 1
                 for (int cb = 0; cb < BN / 64; cb += 2) {
                     tc_ld32(taddr + (cb + 1) * 32, rb);
-                    const float wa = H ? block_max_h(ra) : block_max<COS>(ra, thr_h + cb * 32, hx, ninf);
+                    float wa = H ? block_max_h(ra) : block_max<COS>(ra, thr_h + cb * 32, hx, ninf);
+                    if (p.debug_skip & 4) wa = __uint_as_float(ra[0] & ra[31] & 0x80000000u) - 1.f;   // ldonly: no scan of the block
                     if (__builtin_expect((H ? wa > 0.f : cand_hit<COS>(wa, hx)) && rowok, 0)) {
                         n_slow++;
                         thread_append<COS, H>(ra, thr_h + cb * 32, hx, col_h + cb * 32, row, ctl, cand, p.qflags, g * BN, p.b);
@@ -571,7 +572,8 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                     __syncwarp();
                     tc_wait_ld();
                     if (cb + 2 < BN / 64) tc_ld32(taddr + (cb + 2) * 32, ra);
-                    const float wb = H ? block_max_h(rb) : block_max<COS>(rb, thr_h + (cb + 1) * 32, hx, ninf);
+                    float wb = H ? block_max_h(rb) : block_max<COS>(rb, thr_h + (cb + 1) * 32, hx, ninf);
+                    if (p.debug_skip & 4) wb = __uint_as_float(rb[0] & rb[31] & 0x80000000u) - 1.f;
                     if (__builtin_expect((H ? wb > 0.f : cand_hit<COS>(wb, hx)) && rowok, 0)) {
                         n_slow++;
                         thread_append<COS, H>(rb, thr_h + (cb + 1) * 32, hx, col_h + (cb + 1) * 32, row, ctl, cand, p.qflags, g * BN, p.b);
@@ -710,7 +712,7 @@ __global__ void __launch_bounds__(256) build_mirror_kernel(const float *__restri
 template <bool COS>
 __global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restrict__ q, uint32_t b, uint32_t ld, uint32_t kd, uint32_t ld_h,
                                                            const unsigned int *__restrict__ maxnorm_bits, unsigned short *__restrict__ qh,
-                                                           float *__restrict__ gthr, float *__restrict__ qcap) {
+                                                           float *__restrict__ gthr, float *__restrict__ qcap, float cap_sign) {
     const int lane = threadIdx.x & 31;
     const uint32_t qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= b) return;
@@ -721,7 +723,8 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restri
     for (int o = 16; o > 0; o >>= 1) nq += __shfl_xor_sync(kFull, nq, o);
     const float nqs = sqrtf(nq) * 1.0001f;
     const float M = __uint_as_float(*maxnorm_bits);
-    const float cap = (COS ? nqs : fmaf(sqrtf(M), nqs, 0.5f * M)) * 1.02f + 1e-30f;
+    // (cap_sign = -1 only in the VROD_BATCHED_DEBUG timing modes: no row is ever a candidate)
+    const float cap = cap_sign * ((COS ? nqs : fmaf(sqrtf(M), nqs, 0.5f * M)) * 1.02f + 1e-30f);
     unsigned short t[3];
     const float thr = split3(cap, t);
     for (uint32_t c = lane; c < ld_h; c += 32) {
@@ -1089,7 +1092,9 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         if (H) {
             if (!make_map(&tmX, s.rows_h, true, s.n, ld_h, BM) || !make_map(&tmQ, qh, true, bq, ld_h, BN)) return cudaErrorInvalidValue;
             auto prep = s.metric ? prep_queries_kernel<true> : prep_queries_kernel<false>;
-            prep<<<(bq + 7) / 8, 256, 0, st>>>(qw, bq, s.ld, kd, ld_h, s.maxnorm_bits, qh, gthr, qcap);
+            const char *dbg = getenv("VROD_BATCHED_DEBUG");
+            const bool nocand = dbg && (strstr(dbg, "nocand") || strstr(dbg, "noepi") || strstr(dbg, "nomma") || strstr(dbg, "ldonly"));
+            prep<<<(bq + 7) / 8, 256, 0, st>>>(qw, bq, s.ld, kd, ld_h, s.maxnorm_bits, qh, gthr, qcap, nocand ? -1.f : 1.f);
             if (stats) stats->launches += 1;
         } else if (!make_map(&tmX, s.rows, false, s.n, s.ld, BM) || !make_map(&tmQ, qw, false, bq, s.ld, BN / psz)) {
             return cudaErrorInvalidValue;
@@ -1110,8 +1115,8 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         p.kprime = kprime;
         {
             const char *dbg = getenv("VROD_BATCHED_DEBUG");
-            p.debug_nocand = dbg && (strcmp(dbg, "nocand") == 0 || strstr(dbg, "noepi") || strstr(dbg, "nomma"));
-            p.debug_skip = dbg ? ((strstr(dbg, "noepi") ? 1 : 0) | (strstr(dbg, "nomma") ? 2 : 0)) : 0;
+            p.debug_nocand = dbg && (strcmp(dbg, "nocand") == 0 || strstr(dbg, "noepi") || strstr(dbg, "nomma") || strstr(dbg, "ldonly"));
+            p.debug_skip = dbg ? ((strstr(dbg, "noepi") ? 1 : 0) | (strstr(dbg, "nomma") ? 2 : 0) | (strstr(dbg, "ldonly") ? 4 : 0)) : 0;
             static long long *dbg_buf = nullptr;
             if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 1024 * 16 * sizeof(long long));
             p.dbg = dbg ? dbg_buf : nullptr;

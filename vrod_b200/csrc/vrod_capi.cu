@@ -827,14 +827,15 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
     auto oid = [&](uint32_t qi) { return direct ? reinterpret_cast<unsigned long long *>(d_ids) + (size_t)qi * k : nullptr; };
     auto odd = [&](uint32_t qi) { return direct ? d_dist + (size_t)qi * k : nullptr; };
     // automatic choice between b single-query scans and one batched (tensor-core) pass: a crude cost model from the
-    // round-1 measurements -- a scan costs ~25 us + its HBM bytes at 6.5 TB/s, a batched pass ~250 us of phase and
-    // launch overhead + 1.37 us per (128-row tile x 128 dims x query group of 256) spread over the SMs
+    // round-1 measurements -- a scan costs ~25 us + its HBM bytes at 6.5 TB/s, a batched pass ~200 us of phase and
+    // launch overhead + 1.45 us per (128-row tile x 144 bf16 columns x query group of 256) spread over the SMs
+    // (configs[2]: 2111 tiles per SM in 3.2 ms)
     bool prefer_batched = false;
     if (b >= 2) {
         const double bytes = (double)s.n * s.ld * 4.0;
         const double t_scan = 25e-6 + bytes / 6.5e12;
         const double groups = (double)((b + 255) / 256);
-        const double t_batched = 250e-6 + groups * ((double)s.n / 128.0) * 1.37e-6 * ((double)s.ld / 128.0) / (double)ctx->sms;
+        const double t_batched = 200e-6 + groups * ((double)s.n / 128.0) * 1.45e-6 * ((double)mirror_ld(s.dim) / 144.0) / (double)ctx->sms;
         prefer_batched = (double)b * t_scan > t_batched;
     }
     const bool batched = !exact_only && batched_supported(s, b, k) && (c->path == 3 || c->path == 4 || (c->path == 0 && prefer_batched));
