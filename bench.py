@@ -40,6 +40,8 @@ WORKLOADS = {
     "cfg1": (1_000_000, 768, 1, 10, 1, "configs[1]: 1Mx768 f32 cosine, single-query exact top-10"),
     "cfg0": (10_000, 128, 0, 10, 1, "configs[0]: 10kx128 f32 Euclidean, single-query exact top-10"),
     "cfg2": (10_000_000, 128, 0, 100, 1024, "configs[2]: 10Mx128 f32 L2, 1024 queries, exact top-100"),
+    "cfg3b": (100_000_000, 128, 0, 10, 1024, "configs[3] collection with the north_star's batched load: 100Mx128 f32 L2, "
+                                             "1024 queries, exact top-10, row-sharded over the GPUs"),
 }
 DATA_SEED, QUERY_SEED = 0x5EED0001, 0x5EED0002
 METRIC_NAME = "queries/sec, exact top-k kNN"

@@ -41,6 +41,22 @@ def main():
         assert_same(*c.search(Q[:2], k), ids[:2], dd[:2], "exact path, sharded")
         ctx.drop(c.name)
 
+    # batched (tensor-core) path on every shard, both operand modes, then the exchange + merge of b x k hits
+    for (n, d, metric, k, b, path) in [(300_000, 128, 0, 10, 300, 3), (120_000, 96, 1, 100, 257, 3), (150_000, 128, 0, 10, 64, 4)]:
+        c = ctx.create(f"sb{n}_{path}", d, metric, n)
+        c.fill_synthetic(n, 46)
+        c.set_path(path)
+        Q = O.fill(b, d, 47)
+        s0 = ctx.stats()
+        ids, dd = c.search(Q, k)
+        assert ctx.stats()["batched_tiles"] > s0["batched_tiles"], "the tensor-core path did not run"
+        if rank == 0:                                     # (every rank holds the same global answer; one oracle run is enough)
+            assert_same(ids, dd, *O.search(O.fill(n, d, 46), Q, k, metric), f"sharded batched n={n} path={path}")
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (ids.tobytes(), dd.tobytes()))
+        assert all(g == gathered[0] for g in gathered), "ranks disagree on the global answer"
+        ctx.drop(c.name)
+
     # INSERT: every rank passes the same rows; ties across the shard boundary break by id
     n, d = 30_000, 96
     X = O.fill(n, d, 43)

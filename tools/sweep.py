@@ -45,10 +45,10 @@ for d in (64, 128, 384, 768, 1536):
                 if path == "scan":
                     r["scan_gbs"] = N * d * 4 / ms / 1e6 * b; r["frac_of_measured_hbm"] = r["scan_gbs"] / PEAK / b
                 else:
-                    r["tflops_tf32"] = 2.0 * b * N * d / ms / 1e9
+                    r["tflops"] = 2.0 * b * N * d / ms / 1e9
                 rows.append(r)
                 print(f"d={d:5d} {r['metric'][:3]} k={k:3d} b={b:3d} {path:7s} {ms*1e3:9.1f} us/batch {r['qps']:10.0f} qps "
-                      + (f"{r['frac_of_measured_hbm']*100:5.1f}% of HBM peak" if path == 'scan' else f"{r['tflops_tf32']:6.0f} TFLOP/s tf32")
+                      + (f"{r['frac_of_measured_hbm']*100:5.1f}% of HBM peak" if path == 'scan' else f"{r['tflops']:6.0f} TFLOP/s")
                       + ("" if ok else "  PARITY MISMATCH"), flush=True)
         ctx.drop("sw")
         del X

@@ -845,13 +845,15 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
         if (tid == 0) ctl->cnt = prev;
         __syncthreads();
         block_select<kFinPer>(ctl, buf, p.kprime, p.cap, tid, hist);
-        // rounds of half the free space: after the first select the threshold passes only a few percent of a
-        // round, so most rounds are a plain load + filter and the (latency-bound) sort runs only when the buffer
-        // could overflow in the next round -- sorting every round cost 3x more barrier stages
-        const int round = (p.cap - p.kprime) / 2;
+        // rounds of as many entries as the buffer has room for: after the first select the threshold passes only a
+        // small part of a round, so most rounds are a plain load + filter and the select runs only when the buffer
+        // is more than half full (or has no threshold yet)
         constexpr int PER = 4;   // keys a thread fetches back to back (independent loads) before it filters them
-        for (int base = prev; base < total; base += round) {
-            const int end = base + round < total ? base + round : total;
+        int base = prev;
+        while (base < total) {
+            const int room = p.cap - ctl->cnt;   // uniform: read between two barriers
+            __syncthreads();
+            const int end = base + room < total ? base + room : total;
             for (int i0 = base + tid; i0 < end; i0 += kScanThreads * PER) {
                 unsigned long long keys[PER];
 #pragma unroll
@@ -879,8 +881,9 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
                 }
             }
             __syncthreads();
+            base = end;
             const bool no_threshold_yet = ctl->thrkey == kKeyMax && ctl->cnt >= p.kprime;
-            if (ctl->cnt > p.cap - round || no_threshold_yet) block_select<kFinPer>(ctl, buf, p.kprime, p.cap, tid, hist);   // uniform
+            if (base < total && (ctl->cnt > p.cap / 2 || no_threshold_yet)) block_select<kFinPer>(ctl, buf, p.kprime, p.cap, tid, hist);   // uniform
         }
     }
     __syncthreads();
