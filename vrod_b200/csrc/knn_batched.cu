@@ -297,24 +297,28 @@ __device__ __forceinline__ float block_max_h(const uint32_t (&r)[32]) {
     return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// Rare path: this THREAD's row beat some threshold among the 32 columns it holds in registers.  The thread
-// appends its survivors itself -- one shared-memory atomic per candidate, no warp collectives, no TMEM re-read --
-// so the other lanes and warps are not involved.  The code is kept COMPACT on purpose: a dense mask pass, then a
-// loop over the set bits that picks the score out of the 32 registers with a 5-level select tree (31 selects;
-// a run-time register index would push the block into local memory).  Cold straight-line code is paid for in
-// instruction-cache misses: the fully unrolled per-column form (15 KB) cost ~2500 cycles per entry, and round 1's
-// warp-collective form (TMEM re-read + ballot transpose) ~2000 while holding the accumulator stage.
+// Rare path, entered by the whole warp when ANY of its rows beat some threshold among the 32 columns of the block
+// held in registers (`hit` = this thread's row did).
+//  * dense block (every row x every column passes: the start phase, where the thresholds are still above every
+//    surrogate): lane j claims 32 slots of column j's list with one shared-memory atomic for the whole warp, then
+//    the 32 columns are written as 32 coalesced 256-byte stores (static register indices);
+//  * otherwise each hitting THREAD appends its own survivors -- one shared-memory atomic per candidate, no TMEM
+//    re-read -- with deliberately COMPACT code: a dense mask pass, then a loop over the set bits that picks the score
+//    out of the 32 registers with a 5-level select tree (31 selects; a run-time register index would push the block
+//    into local memory).  Cold straight-line code is paid for in instruction-cache misses: a fully unrolled
+//    per-column form (15 KB) cost ~2500 cycles per entry, and round 1's first form (TMEM re-read + ballot
+//    transpose) ~2000 while holding the accumulator stage.
 // (H = bf16 mode: the register holds D, a candidate is D > 0 and its surrogate is v = thr_q - D.)
 template <bool COS, bool H>
-__device__ __forceinline__ void thread_append(const uint32_t (&r)[32], const float *thr, float hx, int colbase, uint32_t row, BatchCtl *ctl,
-                                              unsigned long long *cand, int *qflags, uint32_t qbase, uint32_t b) {
+__device__ __forceinline__ void warp_append(const uint32_t (&r)[32], bool hit, const float *thr, float hx, int colbase, uint32_t row,
+                                            BatchCtl *ctl, unsigned long long *cand, int *qflags, uint32_t qbase, uint32_t b, int lane) {
     uint32_t m0 = 0, m1 = 0;
     if constexpr (H) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const bool hit = __uint_as_float(r[j]) > 0.f;
-            if (j & 1) m1 |= hit ? (1u << j) : 0u;
-            else m0 |= hit ? (1u << j) : 0u;
+            const bool h = __uint_as_float(r[j]) > 0.f;
+            if (j & 1) m1 |= h ? (1u << j) : 0u;
+            else m0 |= h ? (1u << j) : 0u;
         }
     } else {
 #pragma unroll
@@ -323,13 +327,27 @@ __device__ __forceinline__ void thread_append(const uint32_t (&r)[32], const flo
             const float t4[4] = {th.x, th.y, th.z, th.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const bool hit = cand_hit<COS>(cand_w<COS>(__uint_as_float(r[j4 * 4 + e]), t4[e], hx), hx);
-                if (e & 1) m1 |= hit ? (1u << (j4 * 4 + e)) : 0u;
-                else m0 |= hit ? (1u << (j4 * 4 + e)) : 0u;
+                const bool h = cand_hit<COS>(cand_w<COS>(__uint_as_float(r[j4 * 4 + e]), t4[e], hx), hx);
+                if (e & 1) m1 |= h ? (1u << (j4 * 4 + e)) : 0u;
+                else m0 |= h ? (1u << (j4 * 4 + e)) : 0u;
             }
         }
     }
-    uint32_t mask = m0 | m1;
+    uint32_t mask = hit ? (m0 | m1) : 0u;
+    if (__all_sync(kFull, mask == 0xffffffffu)) {
+        const int base = atomicAdd(&ctl->cnt[colbase + lane], 32);
+        if (base + 32 > PRUNE_AT) *(volatile int *)&ctl->flag = 1;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int pos = __shfl_sync(kFull, base, j) + lane;
+            const float dot = __uint_as_float(r[j]);
+            const float v = H ? (thr[j] - dot) : (COS ? -(dot * hx) : (hx - dot));
+            const int q = colbase + j;
+            if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
+            else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
+        }
+        return;
+    }
 #pragma unroll 1
     while (mask) {
         const int j = __ffs(mask) - 1;
@@ -351,6 +369,7 @@ __device__ __forceinline__ void thread_append(const uint32_t (&r)[32], const flo
         if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
         else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
     }
+    __syncwarp();   // the caller continues with warp-aligned TMEM instructions
 }
 
 // PSZ = 1 (default): one CTA per unit (tcgen05 cta_group::1, M = 128).  PSZ = 2 (experiment, VROD_BATCHED_PAIR=1):
@@ -565,20 +584,20 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                     tc_ld32(taddr + (cb + 1) * 32, rb);
                     float wa = H ? block_max_h(ra) : block_max<COS>(ra, thr_h + cb * 32, hx, ninf);
                     if (p.debug_skip & 4) wa = __uint_as_float(ra[0] & ra[31] & 0x80000000u) - 1.f;   // ldonly: no scan of the block
-                    if (__builtin_expect((H ? wa > 0.f : cand_hit<COS>(wa, hx)) && rowok, 0)) {
+                    const bool hita = (H ? wa > 0.f : cand_hit<COS>(wa, hx)) && rowok;
+                    if (__builtin_expect(__any_sync(kFull, hita), 0)) {
                         n_slow++;
-                        thread_append<COS, H>(ra, thr_h + cb * 32, hx, col_h + cb * 32, row, ctl, cand, p.qflags, g * BN, p.b);
+                        warp_append<COS, H>(ra, hita, thr_h + cb * 32, hx, col_h + cb * 32, row, ctl, cand, p.qflags, g * BN, p.b, lane);
                     }
-                    __syncwarp();
                     tc_wait_ld();
                     if (cb + 2 < BN / 64) tc_ld32(taddr + (cb + 2) * 32, ra);
                     float wb = H ? block_max_h(rb) : block_max<COS>(rb, thr_h + (cb + 1) * 32, hx, ninf);
                     if (p.debug_skip & 4) wb = __uint_as_float(rb[0] & rb[31] & 0x80000000u) - 1.f;
-                    if (__builtin_expect((H ? wb > 0.f : cand_hit<COS>(wb, hx)) && rowok, 0)) {
+                    const bool hitb = (H ? wb > 0.f : cand_hit<COS>(wb, hx)) && rowok;
+                    if (__builtin_expect(__any_sync(kFull, hitb), 0)) {
                         n_slow++;
-                        thread_append<COS, H>(rb, thr_h + (cb + 1) * 32, hx, col_h + (cb + 1) * 32, row, ctl, cand, p.qflags, g * BN, p.b);
+                        warp_append<COS, H>(rb, hitb, thr_h + (cb + 1) * 32, hx, col_h + (cb + 1) * 32, row, ctl, cand, p.qflags, g * BN, p.b, lane);
                     }
-                    __syncwarp();
                     if (cb + 2 < BN / 64) tc_wait_ld();
                 }
             }
@@ -761,6 +780,8 @@ struct FinishParams {
     int first_phase;                    // 1: glist is empty
     int *status;
     Hit *out;
+    unsigned long long *out_ids;   // optional: final [b][k] ids / distances (single-GPU contexts skip the merge kernel)
+    float *out_dist;
     double eps_dot;         // relative error of the tf32 / bf16 dot product w.r.t. ||x|| ||q||
     // bf16 operand mode (qh != nullptr): the next phase's threshold goes into the query mirror's aux columns
     unsigned short *qh;     // [b][ld_h]
@@ -845,45 +866,45 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
         if (tid == 0) ctl->cnt = prev;
         __syncthreads();
         block_select<kFinPer>(ctl, buf, p.kprime, p.cap, tid, hist);
-        // rounds of as many entries as the buffer has room for: after the first select the threshold passes only a
-        // small part of a round, so most rounds are a plain load + filter and the select runs only when the buffer
-        // is more than half full (or has no threshold yet)
-        constexpr int PER = 4;   // keys a thread fetches back to back (independent loads) before it filters them
-        int base = prev;
-        while (base < total) {
+        // rounds of as many whole LISTS as the buffer has room for (a list holds at most CAP = cap/2 keys and a
+        // select runs whenever the buffer is more than half full, so at least one list always fits).  A warp takes
+        // a list at a time, its lanes read consecutive keys (4 independent loads each) -- no per-key search of the
+        // owning list.  After the first select the threshold passes only a small part of a round, so most rounds
+        // are a plain load + filter.
+        static_assert(CAP * 2 <= kFinCap, "a full CTA list must fit the free half of the selection buffer");
+        uint32_t m0 = 0;
+        while (m0 < nlists) {
             const int room = p.cap - ctl->cnt;   // uniform: read between two barriers
             __syncthreads();
-            const int end = base + room < total ? base + room : total;
-            for (int i0 = base + tid; i0 < end; i0 += kScanThreads * PER) {
-                unsigned long long keys[PER];
+            uint32_t lo = m0 + 1, hi = nlists;   // largest m1 in (m0, nlists] with offs[m1 + 1] - offs[m0 + 1] <= room
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (offs[mid + 1] - offs[m0 + 1] <= room) lo = mid;
+                else hi = mid - 1;
+            }
+            const uint32_t m1 = lo;
+            const unsigned long long thr = *(volatile unsigned long long *)&ctl->thrkey;
+            for (uint32_t m = m0 + warp; m < m1; m += kScanWarps) {
+                const int n_m = offs[m + 2] - offs[m + 1];
+                const unsigned long long *src = p.cand + ((size_t)cta_of(m) * BN + ql) * CAP;
+                for (int j0 = lane; j0 < n_m; j0 += 128) {
+                    unsigned long long keys[4];
 #pragma unroll
-                for (int e = 0; e < PER; ++e) {
-                    const int i = i0 + e * kScanThreads;
-                    keys[e] = kKeyMax;
-                    if (i < end) {
-                        uint32_t lo = 0, hi = nlists - 1;   // largest m with offs[m + 1] <= i
-                        while (lo < hi) {
-                            const uint32_t mid = (lo + hi + 1) >> 1;
-                            if (offs[mid + 1] <= i) lo = mid;
-                            else hi = mid - 1;
+                    for (int e = 0; e < 4; ++e) keys[e] = j0 + 32 * e < n_m ? __ldcg(src + j0 + 32 * e) : kKeyMax;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (keys[e] < thr) {
+                            const int pos = atomicAdd(&ctl->cnt, 1);
+                            if (pos < p.cap) buf[pos] = keys[e];
+                            else ctl->overflow = 1;
                         }
-                        keys[e] = __ldcg(p.cand + ((size_t)cta_of(lo) * BN + ql) * CAP + (i - offs[lo + 1]));
-                    }
-                }
-                const unsigned long long thr = *(volatile unsigned long long *)&ctl->thrkey;
-#pragma unroll
-                for (int e = 0; e < PER; ++e) {
-                    if (keys[e] < thr) {
-                        const int pos = atomicAdd(&ctl->cnt, 1);
-                        if (pos < p.cap) buf[pos] = keys[e];
-                        else ctl->overflow = 1;
                     }
                 }
             }
             __syncthreads();
-            base = end;
+            m0 = m1;
             const bool no_threshold_yet = ctl->thrkey == kKeyMax && ctl->cnt >= p.kprime;
-            if (base < total && (ctl->cnt > p.cap / 2 || no_threshold_yet)) block_select<kFinPer>(ctl, buf, p.kprime, p.cap, tid, hist);   // uniform
+            if (m0 < nlists && (ctl->cnt > p.cap / 2 || no_threshold_yet)) block_select<kFinPer>(ctl, buf, p.kprime, p.cap, tid, hist);   // uniform
         }
     }
     __syncthreads();
@@ -933,6 +954,10 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
         }
         h.pad = 0;
         p.out[(size_t)qi * p.k + i] = h;
+        if (p.out_ids) {
+            p.out_ids[(size_t)qi * p.k + i] = h.id;
+            p.out_dist[(size_t)qi * p.k + i] = h.dist;
+        }
     }
     if (tid == 0) {
         int bad = ctl->overflow | (p.qflags[qi] & 1);
@@ -1027,8 +1052,8 @@ bool batched_supported(const ShardView &s, uint32_t b, uint32_t k) {
 }
 
 cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t b, uint32_t k, int sm_count, void **scratch,
-                                  size_t *scratch_bytes, int *status, Hit *out, cudaStream_t st, BatchedStats *stats,
-                                  cudaEvent_t ev_start, cudaEvent_t ev_stop) {
+                                  size_t *scratch_bytes, int *status, Hit *out, unsigned long long *out_ids, float *out_dist,
+                                  cudaStream_t st, BatchedStats *stats, cudaEvent_t ev_start, cudaEvent_t ev_stop) {
     // operand mode: bf16 mirrors with folded thresholds when the collection has a mirror, else the stored f32 rows as tf32
     const bool H = s.rows_h != nullptr;
     const uint32_t kd = mirror_kd(s.dim), ld_h = mirror_ld(s.dim);
@@ -1184,6 +1209,8 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         f.gthr = gthr;
         f.status = status + (size_t)g0 * BN;
         f.out = out + (size_t)g0 * BN * k;
+        f.out_ids = out_ids ? out_ids + (size_t)g0 * BN * k : nullptr;
+        f.out_dist = out_dist ? out_dist + (size_t)g0 * BN * k : nullptr;
         f.eps_dot = eps_dot;
         f.qh = H ? qh : nullptr;
         f.ld_h = ld_h;

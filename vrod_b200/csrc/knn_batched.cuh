@@ -24,9 +24,11 @@ bool batched_supported(const ShardView &s, uint32_t b, uint32_t k);
 
 // Enqueue the batched search of b queries (d_q: b x ld) on `st`.  `scratch`/`scratch_bytes` is a
 // device buffer the callee may grow.  status[qi] = 1 marks a query whose guard failed (the caller
-// rescans it); out receives b x k hits.  ev_start/ev_stop, when given, bracket the tile kernel.
+// rescans it); out receives b x k hits and, when out_ids/out_dist are not null, the final ids / distances as well
+// (single-GPU contexts: no merge kernel needed).  ev_start/ev_stop, when given, bracket the tile kernels.
 cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t b, uint32_t k, int sm_count,
-                                  void **scratch, size_t *scratch_bytes, int *status, Hit *out, cudaStream_t st,
-                                  BatchedStats *stats, cudaEvent_t ev_start = nullptr, cudaEvent_t ev_stop = nullptr);
+                                  void **scratch, size_t *scratch_bytes, int *status, Hit *out, unsigned long long *out_ids,
+                                  float *out_dist, cudaStream_t st, BatchedStats *stats, cudaEvent_t ev_start = nullptr,
+                                  cudaEvent_t ev_stop = nullptr);
 
 }  // namespace vrod

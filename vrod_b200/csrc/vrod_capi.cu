@@ -864,7 +864,7 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         BatchedStats bs{};
         cudaEvent_t e0 = ctx->profiling ? ctx->prof_event() : nullptr, e1 = ctx->profiling ? ctx->prof_event() : nullptr;
         cudaError_t e = launch_batched_search(sb, d_q, b, k, ctx->sms, &ctx->batched.p, &ctx->batched.bytes, d_status,
-                                              local, ctx->stream, &bs, e0, e1);
+                                              local, oid(0), odd(0), ctx->stream, &bs, e0, e1);
         if (e != cudaSuccess) return fail(VROD_ECUDA, std::string("batched search: ") + cudaGetErrorString(e));
         ctx->stats.kernel_launches += bs.launches;
         ctx->stats.batched_tiles += bs.tiles;
@@ -879,8 +879,8 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         for (uint32_t qi = 0; qi < b; ++qi) {
             if (!hs[qi]) continue;
             const float *q = d_q + (size_t)qi * s.ld;
-            VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, d_status + qi, local + (size_t)qi * k, nullptr, nullptr, ctx->stream));
-            VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, d_status + qi, local + (size_t)qi * k, nullptr, nullptr, ctx->stream));
+            VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, d_status + qi, local + (size_t)qi * k, oid(qi), odd(qi), ctx->stream));
+            VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, d_status + qi, local + (size_t)qi * k, oid(qi), odd(qi), ctx->stream));
             ctx->stats.kernel_launches += 2;
             ctx->stats.fast_scans++;
         }
@@ -943,7 +943,7 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         lists = reinterpret_cast<const Hit *>(ctx->hits_all.p);
         g = (uint32_t)ctx->world;
     }
-    if (!direct || batched) {
+    if (!direct) {
         VROD_CUDA(launch_merge_hits(lists, g, b, k, reinterpret_cast<unsigned long long *>(d_ids), d_dist, ctx->stream));
         ctx->stats.kernel_launches++;
     }
