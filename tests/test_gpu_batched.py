@@ -126,3 +126,32 @@ def test_batched_config2_shape_spot_check(ctx, oracle):
     sid, sdist = c.search(Q[other], k)
     assert_same(ids[other], dist[other], sid, sdist)
     ctx.drop("cfg2b")
+
+
+def test_batched_falls_back_to_tf32_without_a_mirror(tmp_path):
+    """When the bf16 mirror cannot be allocated (forced here with VROD_NO_MIRROR=1, read once per process) path 3
+    still answers through the tensor cores -- with the f32 rows as tf32 operands -- and the results do not change."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import numpy as np\n"
+        "from vrod_b200 import ffi\n"
+        "from oracle import oracle as O\n"
+        "ctx = ffi.Context(0)\n"
+        "c = ctx.create('nm', 128, 0, 50000); c.fill_synthetic(50000, 3); c.set_path(3)\n"
+        "Q = O.fill(200, 128, 4)\n"
+        "s0 = ctx.stats(); ids, dist = c.search(Q, 10); s1 = ctx.stats()\n"
+        "assert s1['batched_tiles'] > s0['batched_tiles']\n"
+        "rid, rdist = O.search(O.fill(50000, 128, 3), Q, 10, 0)\n"
+        "assert np.array_equal(ids, rid) and np.array_equal(dist.view(np.uint32), rdist.view(np.uint32))\n"
+        "print('NO_MIRROR_OK', s1['kernel_launches'] - s0['kernel_launches'])\n"
+    )
+    outs = {}
+    for name, env in (("mirror", {}), ("nomirror", {"VROD_NO_MIRROR": "1"})):
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "NO_MIRROR_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[name] = int(r.stdout.split("NO_MIRROR_OK")[1].split()[0])
+    # the mirror mode launches two kernels more (build_mirror, prep_queries): proof that the modes differed
+    assert outs["mirror"] == outs["nomirror"] + 2, outs

@@ -844,7 +844,10 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         if (c->path != 4 && !c->mirror_failed) {
             // bf16 operand mirror: allocate once for the shard's capacity, convert the rows appended since the last time
             if (!c->rows_h) {
-                const cudaError_t me = cudaMalloc(&c->rows_h, (size_t)c->shard_rows * mirror_ld(c->dim) * sizeof(unsigned short));
+                // VROD_NO_MIRROR=1 behaves like a failed allocation (tests of the fallback; memory-tight deployments)
+                static const bool no_mirror = getenv("VROD_NO_MIRROR") != nullptr;
+                const cudaError_t me = no_mirror ? cudaErrorMemoryAllocation
+                                                 : cudaMalloc(&c->rows_h, (size_t)c->shard_rows * mirror_ld(c->dim) * sizeof(unsigned short));
                 if (me != cudaSuccess) {
                     cudaGetLastError();
                     c->rows_h = nullptr;
