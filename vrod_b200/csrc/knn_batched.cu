@@ -1264,8 +1264,10 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             if (last) break;
             first = false;
             t_begin = t_end;
-            // 3.5x per phase (new + carried keys mostly fit a 1024-key sort); short scans (few tiles per unit) take
-            // bigger steps: there every extra phase costs a finish kernel (~60 us) that the tiles cannot amortise
+            // 3.5x per phase (measured best of 3.5 / 5 / 7 / 10 at configs[2]: new + carried keys fit the 2048-key
+            // select); short scans (few tiles per unit) take bigger steps: there every extra phase costs a tile launch
+            // and a finish kernel (~60 us) that the tiles cannot amortise.  (8x steps only while the phases are tiny,
+            // 3.5x afterwards, measured the same as plain 3.5x at configs[2].)
             static const double growth_env = getenv("VROD_BATCHED_GROWTH") ? atof(getenv("VROD_BATCHED_GROWTH")) : 0.0;
             const double growth = growth_env > 1.0 ? growth_env : ((super_tiles / cpg_max) < 256 ? 8.0 : 3.5);
             unsigned long long nxt = (unsigned long long)((double)t_end * growth);
