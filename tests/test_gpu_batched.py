@@ -13,6 +13,8 @@ CASES = [  # n, d, metric, k, b
     (1000, 128, 0, 10, 4), (50000, 128, 0, 10, 300), (50000, 128, 1, 100, 256), (100, 128, 0, 10, 7),
     (20000, 64, 0, 10, 513), (20000, 100, 1, 10, 64), (30000, 32, 0, 100, 100), (200000, 128, 0, 100, 1024),
     (300000, 96, 1, 10, 1000), (129, 8, 0, 1, 3), (4000, 128, 1, 120, 33),
+    # fewer rows than k (padded answers), a single row
+    (5, 16, 1, 10, 70), (1, 128, 0, 3, 65),
     # dims above 128: the query slabs are streamed with the row slabs
     (30000, 384, 1, 10, 256), (20000, 768, 1, 10, 70), (9000, 1536, 0, 100, 300), (15000, 200, 0, 10, 40), (5000, 260, 1, 5, 9),
 ]
@@ -83,6 +85,35 @@ def test_mirror_follows_appends_and_growth(ctx, oracle):
         c.insert(X[3900:])          # beyond the capacity: the collection grows, the mirror is rebuilt
         assert_same(*c.search(Q, k), *oracle.search(X, Q, k, metric), "after growth")
         ctx.drop(c.name)
+
+
+@pytest.mark.parametrize("path", [3, 4], ids=["bf16", "tf32"])
+@pytest.mark.parametrize("metric", [0, 1], ids=["euclidean", "cosine"])
+def test_batched_awkward_inputs(ctx, oracle, metric, path):
+    """Zero rows, a zero query, a query outside the fast paths' range, an exact hit, and row norms spread over six
+    orders of magnitude (the bf16 mode's folded threshold loses its resolution for the small rows: those queries
+    must fail the guard and be rescanned, not answered wrongly).  The two out-of-range queries are answered by the
+    exact scan on their own: the rest of the batch still goes through the tensor cores."""
+    n, d, k, b = 20000, 64, 10, 130
+    rng = np.random.default_rng(7)
+    X = oracle.fill(n, d, 51)
+    X *= (10.0 ** rng.uniform(-3, 3, size=(n, 1))).astype(np.float32)
+    X[17] = 0.0
+    X[4000:4003] = 0.0
+    Q = oracle.fill(b, d, 52)
+    Q[0] = 0.0
+    Q[1] = X[123]
+    Q[2:40] *= np.float32(1e-3)          # queries among the small rows
+    Q[40:60] *= np.float32(300.0)
+    Q[61] *= np.float32(1e25)
+    c = ctx.create(f"awk{metric}_{path}", d, metric, n)
+    c.insert(X)
+    c.set_path(path)
+    s0 = ctx.stats()
+    ids, dist = c.search(Q, k)
+    assert ctx.stats()["batched_tiles"] > s0["batched_tiles"]
+    assert_same(ids, dist, *oracle.search(X, Q, k, metric), f"metric={metric} path={path}")
+    ctx.drop(c.name)
 
 
 def test_batched_guard_failures_are_rescanned(ctx, oracle):

@@ -1002,22 +1002,30 @@ static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *
     const size_t qbytes = (size_t)b * c->ld * sizeof(float);
     VROD_CUDA(ctx->q_host.ensure(qbytes));
     float *qh = reinterpret_cast<float *>(ctx->q_host.p);
-    bool unsafe = false;
+    // queries outside the range the f32 / tensor-core passes' error bounds cover are answered by the exact f64 scan:
+    // each on its own on a single GPU (the rest of the batch keeps its fast path), the whole call on sharded contexts
+    // (every rank must enqueue the same collectives)
+    std::vector<unsigned char> unsafe_q(b, 0);
+    uint32_t n_unsafe = 0;
     for (uint32_t i = 0; i < b; ++i) {
         const float *src = queries + (size_t)i * c->dim;
         float *dst = qh + (size_t)i * c->ld;
         double nq = 0.0;
+        bool u = false;
         for (uint32_t j = 0; j < c->dim; ++j) {
             const float v = src[j];
             if (!isfinite(v)) return fail(VROD_EINVAL, "query contains NaN or infinity");
-            if (fabsf(v) > 0x1p40f) unsafe = true;
+            if (fabsf(v) > 0x1p40f) u = true;
             nq += (double)v * (double)v;
             dst[j] = v;
         }
         for (uint32_t j = c->dim; j < c->ld; ++j) dst[j] = 0.f;
-        if (nq > 0.0 && (nq < 0x1p-80 || nq > 0x1p100)) unsafe = true;
-        if (c->metric == VROD_COSINE && nq == 0.0) unsafe = true;  // all distances are 1: answered by the exact scan
+        if (nq > 0.0 && (nq < 0x1p-80 || nq > 0x1p100)) u = true;
+        if (c->metric == VROD_COSINE && nq == 0.0) u = true;  // all distances are 1: answered by the exact scan
+        unsafe_q[i] = u ? 1 : 0;
+        n_unsafe += u ? 1 : 0;
     }
+    const bool unsafe = n_unsafe != 0 && (ctx->world > 1 || n_unsafe == b);   // the whole call goes the exact way
     // one device buffer [ids | dist | status] so that the results and the guard flags come back in ONE copy
     const size_t nres = (size_t)b * k;
     const size_t off_dist = nres * sizeof(uint64_t);
@@ -1040,11 +1048,15 @@ static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *
     VROD_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->fused_exchange && reinterpret_cast<const int *>(hpack + off_stat)[b] == 1)
         return fail(VROD_ENCCL, "peer exchange timed out: a rank did not take part in this search");
-    if (used_scan && ctx->world == 1) {
-        // the scans ran without their device-side conditional rescans: answer the flagged queries exactly now
-        const int *hs = reinterpret_cast<const int *>(hpack + off_stat);
+    if (ctx->world == 1 && !unsafe && (used_scan || n_unsafe)) {
+        // the scans ran without their device-side conditional rescans: answer the flagged queries exactly now,
+        // and with them the queries that were out of range for the fast paths
+        int *hs = reinterpret_cast<int *>(hpack + off_stat);
         bool any = false;
-        for (uint32_t qi = 0; qi < b; ++qi) any = any || hs[qi] != 0;
+        for (uint32_t qi = 0; qi < b; ++qi) {
+            hs[qi] = (used_scan && hs[qi] != 0) || unsafe_q[qi] ? 1 : 0;
+            any = any || hs[qi] != 0;
+        }
         if (any) {
             const ShardView s = shard_view(c);
             const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
