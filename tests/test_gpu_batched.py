@@ -186,3 +186,39 @@ def test_batched_falls_back_to_tf32_without_a_mirror(tmp_path):
         outs[name] = int(r.stdout.split("NO_MIRROR_OK")[1].split()[0])
     # the mirror mode launches two kernels more (build_mirror, prep_queries): proof that the modes differed
     assert outs["mirror"] == outs["nomirror"] + 2, outs
+
+
+def _stress_rows(kind, n, d, rng):
+    if kind == "clusters":      # tight clusters: neighbours closer than the tensor-core pass can resolve
+        c = rng.standard_normal((max(n // 200, 2), d)).astype(np.float32)
+        X = c[rng.integers(0, len(c), n)] + (rng.standard_normal((n, d)) * 0.01).astype(np.float32)
+    elif kind == "normalized":  # unit vectors, as an embedding model emits them
+        X = rng.standard_normal((n, d)).astype(np.float32)
+        X /= np.linalg.norm(X, axis=1, keepdims=True).astype(np.float32)
+    elif kind == "grid":        # small integers: many exactly equal distances, the (dist, id) tie-break decides
+        X = rng.integers(-3, 4, size=(n, d)).astype(np.float32)
+    elif kind == "sparse":
+        X = (rng.standard_normal((n, d)) * (rng.random((n, d)) < 0.05)).astype(np.float32)
+    else:                       # rank 4
+        X = (rng.standard_normal((n, 4)) @ rng.standard_normal((4, d))).astype(np.float32)
+    return np.ascontiguousarray(X, dtype=np.float32)
+
+
+@pytest.mark.parametrize("kind", ["clusters", "normalized", "grid", "sparse", "lowrank"])
+def test_batched_on_stress_distributions(ctx, oracle, kind):
+    """Data that stresses the guard (tools/soak_batched.py runs the long version): whatever the tensor-core pass
+    cannot prove is rescanned, the answer is the oracle's bit for bit on both metrics and both operand modes."""
+    rng = np.random.default_rng(sum(kind.encode()))
+    n, d, b, k = 30000, 96, 140, 20
+    X = _stress_rows(kind, n, d, rng)
+    Q = _stress_rows(kind, b, d, rng)
+    Q[: b // 2] = X[rng.integers(0, n, b // 2)]
+    for metric, path in ((0, 3), (1, 3), (0, 4)):
+        c = ctx.create(f"st_{kind}_{metric}_{path}", d, metric, n)
+        c.insert(X)
+        c.set_path(path)
+        s0 = ctx.stats()
+        ids, dist = c.search(Q, k)
+        assert ctx.stats()["batched_tiles"] > s0["batched_tiles"]
+        assert_same(ids, dist, *oracle.search(X, Q, k, metric), f"{kind} metric={metric} path={path}")
+        ctx.drop(c.name)
