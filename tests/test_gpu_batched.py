@@ -222,3 +222,23 @@ def test_batched_on_stress_distributions(ctx, oracle, kind):
         assert ctx.stats()["batched_tiles"] > s0["batched_tiles"]
         assert_same(ids, dist, *oracle.search(X, Q, k, metric), f"{kind} metric={metric} path={path}")
         ctx.drop(c.name)
+
+
+def test_auto_path_stops_paying_for_a_pass_that_proves_nothing(ctx, oracle):
+    """Tight clusters under the Euclidean metric: the tensor-core pass cannot prove any query of the batch, all are
+    rescanned.  The automatic path choice learns that share and answers the next batches with scans alone."""
+    rng = np.random.default_rng(5)
+    n, d, b, k = 60000, 64, 96, 10
+    X = _stress_rows("clusters", n, d, rng)
+    Q = X[rng.integers(0, n, b)] + np.float32(1e-4)
+    c = ctx.create("learn", d, 0, n)
+    c.insert(X)
+    want = oracle.search(X, Q, k, 0)
+    tiles = []
+    for _ in range(4):
+        s0 = ctx.stats()
+        assert_same(*c.search(Q, k), *want, "clustered, automatic path")
+        tiles.append(ctx.stats()["batched_tiles"] - s0["batched_tiles"])
+    assert tiles[0] > 0, "the first batch should have tried the tensor cores"
+    assert tiles[-1] == 0, f"later batches should be answered by scans alone: {tiles}"
+    ctx.drop("learn")

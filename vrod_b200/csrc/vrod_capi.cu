@@ -188,6 +188,10 @@ struct vrod_collection {
     unsigned short *rows_h = nullptr;
     uint64_t mirror_rows = 0;
     bool mirror_failed = false;   // the mirror did not fit: the batched path feeds the f32 rows as tf32 instead
+    // share of the queries of recent batched searches whose guard failed (they were rescanned one by one): the
+    // automatic path choice discounts the batched pass by it, so that data the tensor-core pass cannot resolve
+    // (tight clusters under the Euclidean metric) stops paying for a pass that proves nothing
+    double rescan_share = 0.0;
 };
 
 static int *ctx_ticket(vrod_ctx *c) { return reinterpret_cast<int *>(c->small.p); }
@@ -836,7 +840,8 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         const double t_scan = 25e-6 + bytes / 6.5e12;
         const double groups = (double)((b + 255) / 256);
         const double t_batched = 200e-6 + groups * ((double)s.n / 128.0) * 1.45e-6 * ((double)mirror_ld(s.dim) / 144.0) / (double)ctx->sms;
-        prefer_batched = (double)b * t_scan > t_batched;
+        prefer_batched = (1.0 - c->rescan_share) * (double)b * t_scan > t_batched;
+        if (!prefer_batched) c->rescan_share *= 0.995;   // forget slowly: the batched pass is probed again later
     }
     const bool batched = !exact_only && batched_supported(s, b, k) && (c->path == 3 || c->path == 4 || (c->path == 0 && prefer_batched));
     if (batched) {
@@ -879,6 +884,12 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         VROD_CUDA(cudaStreamSynchronize(ctx->stream));
         const ScanPlan fp = make_scan_plan(s, k, ctx->sms, false);
         const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
+        uint32_t flagged = 0;
+        for (uint32_t qi = 0; qi < b; ++qi) flagged += hs[qi] ? 1u : 0u;
+        {   // rises at once, falls slowly
+            const double share = (double)flagged / (double)b, ema = 0.5 * c->rescan_share + 0.5 * share;
+            c->rescan_share = share > ema ? share : ema;
+        }
         for (uint32_t qi = 0; qi < b; ++qi) {
             if (!hs[qi]) continue;
             const float *q = d_q + (size_t)qi * s.ld;
