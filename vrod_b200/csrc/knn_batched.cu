@@ -3,16 +3,23 @@
 // For a batch of queries the scan IS a dense contraction: S = X . Q^T (rows x queries).  One CTA per SM
 // owns a fixed group of BN = 256 queries (resident in shared memory, 128B-swizzled, loaded once by TMA)
 // and streams its share of the collection's row tiles (BM = 128 rows) through a multi-stage TMA ->
-// mbarrier -> tcgen05.mma (kind::tf32, operands are the stored f32 rows, no second copy) pipeline into a
-// double-buffered TMEM accumulator (2 x 256 columns).  Four epilogue warps read the accumulator with
-// tcgen05.ld and NEVER materialise the rows x queries score matrix: each score is turned into a
-// surrogate v (L2: ||x||^2/2 - dot, cosine: -dot/||x||), compared against the query's running threshold,
-// and the rare survivors are appended to a per-(CTA, query) candidate list in global memory.  When a
-// list nears capacity the epilogue warps prune it (sample-sort-count selection in registers) and tighten
-// the threshold.  batched_finish_kernel then merges the lists of all CTAs of a query, re-evaluates the
-// best k' candidates in canonical f64 (the same arithmetic as the oracle), sorts them by (dist, id) and
-// PROVES with the tf32 error bound that no dropped row can belong to the top k; a query whose proof
-// fails is flagged and answered by the single-query scan (knn_scan.cu).
+// mbarrier -> tcgen05.mma pipeline into a double-buffered TMEM accumulator (2 x 256 columns).  Eight
+// epilogue warps read the accumulator with tcgen05.ld and NEVER materialise the rows x queries score
+// matrix: a branch-free maximum over each thread's 32 scores tells whether its row beats any query's
+// running threshold, and the rare survivors are appended -- straight from the registers -- to a
+// per-(CTA, query) candidate list in global memory.
+//
+// Two operand modes.  Default: bf16 mirrors of the rows and of the query batch (kind::f16) whose 16 aux
+// columns fold the threshold and the row-norm term into the contraction, so the accumulator holds
+// D = dot + thr_q - ||x||^2/2 and "candidate" is D > 0.  Fallback / set_path(4): the stored f32 rows as
+// tf32 operands (kind::tf32, no second copy), thresholds applied in the epilogue.
+//
+// The row tiles are processed in phases; between phases batched_finish_kernel merges the lists of all
+// CTAs of a query (radix select) into the exact global k'-th surrogate = every CTA's next threshold.
+// In the last phase it re-evaluates the best k' candidates in canonical f64 (the same arithmetic as the
+// oracle), sorts them by (dist, id) and PROVES with the operand-rounding error bound that no dropped row
+// can belong to the top k; a query whose proof fails is flagged and answered by the single-query scan
+// (knn_scan.cu).
 //
 // Stands for the reference's SearchCommand::execute (src/command/types.rs:114-119, empty) when the
 // argument carries many queries; nothing of it exists upstream.
