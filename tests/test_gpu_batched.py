@@ -206,7 +206,7 @@ def _stress_rows(kind, n, d, rng):
 
 @pytest.mark.parametrize("kind", ["clusters", "normalized", "grid", "sparse", "lowrank"])
 def test_batched_on_stress_distributions(ctx, oracle, kind):
-    """Data that stresses the guard (tools/soak_batched.py runs the long version): whatever the tensor-core pass
+    """Data that stresses the guard (tests/tools/soak_batched.py runs the long version): whatever the tensor-core pass
     cannot prove is rescanned, the answer is the oracle's bit for bit on both metrics and both operand modes."""
     rng = np.random.default_rng(sum(kind.encode()))
     n, d, b, k = 30000, 96, 140, 20

@@ -1,6 +1,6 @@
 """Development aid: batched (tensor-core) path parity + timing on one GPU."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from vrod_b200 import ffi

@@ -1,6 +1,6 @@
 """Quick parity + timing sweep on one GPU (development aid; the graded tests are tests/test_gpu_*.py)."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from vrod_b200 import ffi

@@ -2,7 +2,7 @@
 normalised embeddings, integer grids (exact distance ties), sparse and low-rank rows.  Every case is compared
 bit for bit with the CPU oracle; prints how many queries each case had to rescan."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from vrod_b200 import ffi
 from oracle import oracle as O

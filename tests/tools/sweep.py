@@ -2,14 +2,14 @@
 Every cell is parity-checked against the oracle on a few queries, then timed with queries and results resident
 (CUDA events on the library's stream).  Writes gpurun_out/sweep.json and prints a table."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from vrod_b200 import ffi
 from oracle import oracle as O
 
 N = int(os.environ.get("SWEEP_ROWS", 1_000_000))
-PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
-    os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+    os.path.join(os.path.dirname(__file__), "..", "..", "MEASURED_PEAKS.json")) else 6650.0
 ctx = ffi.Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream())
 rows = []
