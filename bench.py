@@ -151,23 +151,29 @@ def cpu_oracle_leg(rows, dim, metric, k, steps, warmup, budget_s=20.0, batch=1):
     seeded collection, min(batch, 4) queries per step, all host threads.  qps is scaled to the full row count."""
     from oracle import oracle as O
     O.build()
+    # all the host cores this process may run on, stated explicitly: torchrun exports OMP_NUM_THREADS=1 to its
+    # workers, which would otherwise make the N>1 reference arm a single-threaded run
+    try:
+        nthreads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        nthreads = os.cpu_count() or 1
     sample = min(rows, max(10_000, (1 << 30) // (dim * 4)))     # <= 1 GiB of rows on the host
     qb = min(batch, 4)
     X = O.fill(sample, dim, DATA_SEED)
     Q = O.fill(max(steps + warmup, 1) * qb, dim, QUERY_SEED)
     for i in range(warmup):
-        O.search(X, Q[i * qb:(i + 1) * qb], k, metric)
+        O.search(X, Q[i * qb:(i + 1) * qb], k, metric, nthreads=nthreads)
     t_used, times = 0.0, []
     for i in range(steps):
         t0 = time.perf_counter()
-        O.search(X, Q[(warmup + i) * qb:(warmup + i + 1) * qb], k, metric)
+        O.search(X, Q[(warmup + i) * qb:(warmup + i + 1) * qb], k, metric, nthreads=nthreads)
         dt = time.perf_counter() - t0
         times.append(dt)
         t_used += dt
         if t_used > budget_s and len(times) >= 3:
             break
     per_query_full = statistics.mean(times) / qb * (rows / sample)
-    return {"value": 1.0 / per_query_full, "unit": "queries/s", "cores": O.max_threads(), "kind": "port",
+    return {"value": 1.0 / per_query_full, "unit": "queries/s", "cores": nthreads, "kind": "port",
             "sample": f"first {sample} of {rows} rows x {dim} (same Philox stream), {len(times)} steps of {qb} top-{k} "
                       f"queries by oracle/knn_oracle.c (canonical f64), time scaled by {rows / sample:g} to the full collection",
             "ms_per_step_sample": statistics.mean(times) * 1e3, "steps": len(times)}

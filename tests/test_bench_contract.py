@@ -28,3 +28,14 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--rows", "20000"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_uses_all_host_cores_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm (rank 0 of an N>1 launch) must still be
+    the all-cores CPU run that the N=1 arm is, and say how many threads it used."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
+                        "--warmup", "1", "--rows", "20000"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
