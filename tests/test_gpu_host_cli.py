@@ -98,3 +98,30 @@ def test_database_directory_persists_across_processes(tmp_path, oracle):
     assert cli("-d", str(db), "-e", "DROP", "-a", "words").returncode == 0
     assert sorted(os.listdir(db)) == ["vr_config", "vr_wal"]
     assert cli("-d", str(db), "-e", "LISTCOLLECTIONS").stdout.strip() == ""
+
+
+def test_cli_search_with_a_file_of_queries(tmp_path, oracle):
+    """SEARCH coll 'k;@FILE': one query per line of FILE in the record format; the host layer hands them to the
+    library as ONE call (200 queries over 30k rows: the batched tensor-core path) and prints the hits per query."""
+    n, d, k, b = 30000, 32, 5, 200
+    X = oracle.fill(n, d, 61)
+    Q = oracle.fill(b, d, 62)
+    rows, queries = tmp_path / "rows.txt", tmp_path / "queries.txt"
+    with open(rows, "w") as f:
+        for i in range(n):
+            f.write("%s;w%d\n" % (",".join("%.9g" % x for x in X[i]), i))
+    with open(queries, "w") as f:
+        for i in range(b):
+            f.write("%s;q%d\n" % (",".join("%.9g" % x for x in Q[i]), i))
+    script = f"CREATE - words;;euclidean\nBULKINSERT words {rows}\nSEARCH words {k};@{queries}\n"
+    r = subprocess.run([CLI, "--script", "-"], input=script, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = r.stdout.splitlines()[2:]
+    assert len(out) == b * (k + 1)
+    rid, rdist = oracle.search(X, Q, k, 0)
+    for qi in range(b):
+        block = out[qi * (k + 1):(qi + 1) * (k + 1)]
+        assert block[0] == f"# query {qi}\tq{qi}"
+        ids, dist, ws = parse_hits(block[1:])
+        assert_same(ids, dist, rid[qi], rdist[qi], f"query {qi}")
+        assert ws == [f"w{int(i)}" for i in rid[qi]]

@@ -192,38 +192,58 @@ void BulkInsertCommand::execute() const {
 }
 
 // SEARCH -c coll -a k;f32,f32,...      <- reference src/command/types.rs:114-119 (empty body)
+// SEARCH -c coll -a k;@FILE            many queries at once: FILE holds one query per line in the record format
+//                                      (`f32,...[;label]`, src/utils/embeddings.rs:61); they go to the library as ONE
+//                                      vrod_collection_search call, i.e. through the batched tensor-core path
 void SearchCommand::execute() const {
     if (!collection_name || !arg) return set_error(db, "SEARCH needs a collection and a 'k;f32,f32,...' argument");
     const size_t semi = arg->find(';');
-    if (semi == std::string::npos) return set_error(db, "SEARCH argument must be 'k;f32,f32,...'");
+    if (semi == std::string::npos) return set_error(db, "SEARCH argument must be 'k;f32,f32,...' or 'k;@FILE'");
     char *stop = nullptr;
     const long k = std::strtol(arg->c_str(), &stop, 10);
     if (stop != arg->c_str() + semi || k <= 0 || k > (long)VROD_MAX_K)
         return set_error(db, "SEARCH: k must be an integer in [1, " + std::to_string(VROD_MAX_K) + "]");
     std::vector<float> q;
+    std::vector<std::string> labels;
     std::string err;
-    if (!parse_vector(arg->substr(semi + 1), &q, &err)) return set_error(db, "SEARCH: " + err);
+    uint32_t qdim = 0;
+    const std::string rest = arg->substr(semi + 1);
+    const bool many = !rest.empty() && rest[0] == '@';
+    if (many) {
+        if (!read_records_file(rest.substr(1), &q, &labels, &qdim, &err)) return set_error(db, "SEARCH: " + err);
+    } else {
+        if (!parse_vector(rest, &q, &err)) return set_error(db, "SEARCH: " + err);
+        qdim = (uint32_t)q.size();
+    }
     vrod_collection *c = resolve(db, *collection_name, std::nullopt, 0);
     if (!c) return;
     uint32_t dim = 0;
     vrod_collection_info(c, &dim, nullptr, nullptr, nullptr);
-    if (dim != q.size())
-        return set_error(db, "SEARCH: query has " + std::to_string(q.size()) + " components, collection has " + std::to_string(dim));
-    CommandResult res;
-    res.ids.resize((size_t)k);
-    res.dist.resize((size_t)k);
-    if (!api(db, vrod_collection_search(c, q.data(), 1, (uint32_t)k, res.ids.data(), res.dist.data()))) return;
+    if (dim != qdim)
+        return set_error(db, "SEARCH: query has " + std::to_string(qdim) + " components, collection has " + std::to_string(dim));
+    const size_t b = q.size() / dim;
+    if (b > 65536) return set_error(db, "SEARCH: more than 65536 queries in one file");
+    std::vector<uint64_t> ids(b * (size_t)k);
+    std::vector<float> dist(b * (size_t)k);
+    if (!api(db, vrod_collection_search(c, q.data(), (uint32_t)b, (uint32_t)k, ids.data(), dist.data()))) return;
     const auto &pl = db->payloads[*collection_name];
-    size_t valid = 0;
-    while (valid < res.ids.size() && res.ids[valid] != VROD_PAD_ID) ++valid;
-    res.ids.resize(valid);
-    res.dist.resize(valid);
-    for (size_t i = 0; i < valid; ++i) {
-        res.payload.push_back(res.ids[i] < pl.size() ? pl[res.ids[i]] : std::string());
-        // rank <TAB> id <TAB> distance (round-trip precision) <TAB> payload
-        std::printf("%zu\t%llu\t%.9g\t%s\n", i + 1, (unsigned long long)res.ids[i], (double)res.dist[i], res.payload[i].c_str());
+    CommandResult res;
+    for (size_t qi = 0; qi < b; ++qi) {
+        // many queries: a header line per query -- "# query <index> <label>" -- then its hits
+        if (many) std::printf("# query %zu\t%s\n", qi, qi < labels.size() ? labels[qi].c_str() : "");
+        for (size_t i = 0; i < (size_t)k; ++i) {
+            const uint64_t id = ids[qi * (size_t)k + i];
+            if (id == VROD_PAD_ID) break;   // fewer than k rows: the tail is padding
+            const float d = dist[qi * (size_t)k + i];
+            const std::string word = id < pl.size() ? pl[id] : std::string();
+            // rank <TAB> id <TAB> distance (round-trip precision) <TAB> payload
+            std::printf("%zu\t%llu\t%.9g\t%s\n", i + 1, (unsigned long long)id, (double)d, word.c_str());
+            res.ids.push_back(id);
+            res.dist.push_back(d);
+            res.payload.push_back(word);
+        }
     }
-    db->last = std::move(res);
+    db->last = std::move(res);   // all hits in query order (a single query: its k hits)
 }
 
 void TruncateWalCommand::execute() const { unsupported(db, "TRUNCATEWAL"); }

@@ -44,7 +44,7 @@ VROD_DECLARE_COMMAND(InsertCommand)             // types.rs:56-67   arg = f32,f3
 VROD_DECLARE_COMMAND(BulkInsertCommand)         // types.rs:69-80   arg = path of a records file
 VROD_DECLARE_COMMAND(UpdateCommand)             // types.rs:82-93   out of scope
 VROD_DECLARE_COMMAND(DeleteCommand)             // types.rs:95-106  out of scope
-VROD_DECLARE_COMMAND(SearchCommand)             // types.rs:108-119 arg = k;f32,f32,...   <- the hot path
+VROD_DECLARE_COMMAND(SearchCommand)             // types.rs:108-119 arg = k;f32,f32,... | k;@FILE   <- the hot path
 VROD_DECLARE_COMMAND(SearchSimilarCommand)      // types.rs:121-132 out of scope (unspecified upstream)
 VROD_DECLARE_COMMAND(ReindexCommand)            // types.rs:134-144 out of scope (exact scan has no index)
 VROD_DECLARE_COMMAND(UnrecognizedCommand)       // types.rs:146-154
