@@ -970,7 +970,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
         int bad = ctl->overflow | (p.qflags[qi] & 1);
         if (p.n > (uint32_t)ncand) {
             const int kk = (int)p.k < ncand ? (int)p.k : ncand;
-            const float T = ord2f((uint32_t)(buf[kk - 1] >> 32));
+            // (no candidate at all -- e.g. a query the tensor-core pass could not represent: flagged below, kk < k)
+            const float T = kk > 0 ? ord2f((uint32_t)(buf[kk - 1] >> 32)) : __int_as_float(0x7f800000);
             const double u = (double)ctl->u_val;
             const double xn_max = (double)__uint_as_float(*p.maxnorm_bits) * (1.0 + 1.2e-7);
             const double nq = ctl->nq, nqs = __dsqrt_rn(nq);
