@@ -62,3 +62,79 @@ def test_adversarial_operands_approach_but_respect_the_budget(kind):
     bound = eps_dot(kind, d) * X.double().norm() * Q.double().norm()
     ratio = ((approx - exact).abs() / bound).item()
     assert 0.9 < ratio < 1.0, (kind, ratio)
+
+
+def _split3_sum(v):
+    a = to_bf16(v)
+    b = to_bf16(v - a)
+    c = to_bf16(v - a - b)
+    return (a + b) + c
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+@pytest.mark.parametrize("d", [24, 128, 384])
+def test_folded_surrogate_stays_within_the_guard_budget(metric, d):
+    """The whole budget of batched_finish_kernel's guard in the bf16 mode: the surrogate the tile kernel computes
+    from the folded contraction, v' = thr - D with D = dot~ + thr - ||x||^2/2 (cosine: D = dot^ + thr), stays within
+    E of the exact surrogate (||x||^2/2 - dot, cosine -dot/||x||) for every row and every threshold between the
+    smallest surrogate and the start cap."""
+    g = torch.Generator().manual_seed(d)
+    n, b = 2048, 32
+    ld_h = (d + 15) // 16 * 16 + 16
+    eps = eps_dot("bf16", d)
+    acc_eps = (ld_h // 16 + 2) * 2.0 ** -23
+    for scale in (1.0, 30.0, 0.01):
+        X = torch.randn(n, d, generator=g) * scale * (10.0 ** (torch.rand(n, 1, generator=g) * 2 - 1))
+        Q = torch.randn(b, d, generator=g) * scale
+        nx = (X.double() ** 2).sum(1)
+        nq = (Q.double() ** 2).sum(1).sqrt()
+        M = nx.max().float().double()
+        if metric == "euclidean":
+            hx = (0.5 * nx).float()                                             # f32 of the canonical f64 norm, halved
+            cap = ((0.5 * M + M.sqrt() * nq * 1.0001) * 1.02 + 1e-30).float()
+            exact = 0.5 * nx[:, None] - X.double() @ Q.double().T
+            dot = to_bf16(X) @ to_bf16(Q).T
+        else:
+            inv = (1.0 / nx.sqrt()).float()
+            cap = (nq * 1.0001 * 1.02 + 1e-30).float()
+            exact = -(X.double() @ Q.double().T) / nx.sqrt()[:, None]
+            dot = to_bf16(X * inv[:, None]) @ to_bf16(Q).T
+        for frac in (1.0, 0.5, 0.0):                                            # thresholds from the cap down to the best row
+            lo = exact.min(dim=0).values.float()
+            thr = _split3_sum(lo + (cap - lo) * frac)[None, :]                  # what the three aux parts stand for
+            D = (dot + thr) - hx[:, None] if metric == "euclidean" else dot + thr   # f32, one of the possible orders
+            v = thr - D
+            u = v.double().abs()
+            if metric == "euclidean":
+                E = (eps + 2.4e-7) * M.sqrt() * nq[None, :] + 2.4e-7 * (0.5 * M + u) \
+                    + acc_eps * (M.sqrt() * nq[None, :] + 0.5 * M + cap.double()[None, :] + u)
+            else:
+                E = (eps + 3.0e-7) * nq[None, :] + 1.2e-7 * u + acc_eps * (1.01 * nq[None, :] + cap.double()[None, :] + u)
+            ratio = ((v.double() - exact).abs() / E).max().item()
+            assert ratio < 1.0, (metric, d, scale, frac, ratio)
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+@pytest.mark.parametrize("d", [24, 128, 768])
+def test_tf32_surrogate_stays_within_the_guard_budget(metric, d):
+    """The same for the tf32 mode, where the epilogue forms v = ||x||^2/2 - dot~ (cosine: -dot~ * 1/||x||) itself."""
+    g = torch.Generator().manual_seed(1000 + d)
+    n, b = 2048, 32
+    eps = eps_dot("tf32", d)
+    for scale in (1.0, 30.0, 0.01):
+        X = torch.randn(n, d, generator=g) * scale * (10.0 ** (torch.rand(n, 1, generator=g) * 2 - 1))
+        Q = torch.randn(b, d, generator=g) * scale
+        nx = (X.double() ** 2).sum(1)
+        nq = (Q.double() ** 2).sum(1).sqrt()
+        M = nx.max().float().double()
+        dot = to_tf32_truncated(X) @ to_tf32_truncated(Q).T
+        if metric == "euclidean":
+            v = (0.5 * nx.float())[:, None] - dot
+            exact = 0.5 * nx[:, None] - X.double() @ Q.double().T
+            E = (eps + 2.4e-7) * M.sqrt() * nq[None, :] + 2.4e-7 * (0.5 * M + v.double().abs())
+        else:
+            v = -(dot * (1.0 / nx.sqrt()).float()[:, None])
+            exact = -(X.double() @ Q.double().T) / nx.sqrt()[:, None]
+            E = (eps + 3.0e-7) * nq[None, :] + 1.2e-7 * v.double().abs()
+        ratio = ((v.double() - exact).abs() / E).max().item()
+        assert ratio < 1.0, (metric, d, scale, ratio)
