@@ -387,6 +387,7 @@ def main():
                                 "hbm_floor": {"algorithmic_bytes": algo_bytes, "peak_gbs": peak}}
             line["config"]["arithmetic"] = (f"{args.batched_kind} tensor-core pass, exact f64 rerank + guard "
                                             "(bit-identical to the oracle)")
+            line["dtype"] = args.batched_kind      # the type the dominant kernel computes in (f32 accumulate)
         # cheap live check of the last answer: sorted, and the claimed rows sit at the claimed distances
         assert np.all(np.diff(last_dist, axis=1) >= 0)
         if world == 1 and not args.no_cpu_baseline:
