@@ -138,3 +138,64 @@ def test_tf32_surrogate_stays_within_the_guard_budget(metric, d):
             E = (eps + 3.0e-7) * nq[None, :] + 1.2e-7 * v.double().abs()
         ratio = ((v.double() - exact).abs() / E).max().item()
         assert ratio < 1.0, (metric, d, scale, ratio)
+
+
+# fast_scan_kernel variants (vrod_b200/csrc/knn_scan.cu, kVariants): dim -> (lanes per row, float4 chunks per lane)
+SCAN_VARIANTS = {32: (8, 1), 64: (16, 1), 128: (32, 1), 256: (32, 2), 384: (32, 3), 512: (32, 4), 768: (32, 6),
+                 1024: (32, 8), 1536: (32, 12)}
+
+
+def scan_eps(ld, cosine):
+    """make_scan_plan's budget of the f32 pass (relative for L2, absolute on the cosine similarity)."""
+    u = 2.0 ** -24
+    eps = 1.5 * ((ld + 31) // 32 * 4 + 12) * u + ld * 2.0 ** -50
+    return eps + 4 * u if cosine else eps
+
+
+def test_scan_budget_covers_the_reduction_depth():
+    """Every product enters the row sum through: 1 subtraction (L2), 1 fma, the rest of its lane's fma chain
+    (4 * chunks per lane), log2(lanes) butterfly adds -- one rounding each, all relative to partial sums that are
+    bounded by SUM |terms|.  (1 + u)^depth - 1 must fit the budget with room for the cosine path's inverse norm."""
+    u = 2.0 ** -24
+    for d, (lpr, ch) in SCAN_VARIANTS.items():
+        depth = 1 + 4 * ch + int(np.log2(lpr))
+        assert (1 + u) ** depth - 1 < scan_eps(d, False) / 1.4, (d, depth)
+    for d in (4, 20, 100, 200, 1000, 4096):                 # generic variant: 32 lanes, run-time chunk loop
+        ld = (d + 3) // 4 * 4
+        depth = 1 + 4 * ((ld // 4 + 31) // 32) + 5
+        assert (1 + u) ** depth - 1 < scan_eps(ld, False) / 1.4, (d, depth)
+
+
+@pytest.mark.parametrize("cosine", [False, True], ids=["euclidean", "cosine"])
+@pytest.mark.parametrize("d", [32, 64, 128, 768, 1536])
+def test_scan_order_emulation_stays_within_the_budget(d, cosine):
+    """f32 emulation of the kernel's summation order (lane chains, then the butterfly; numpy has no fma, so every
+    term carries one rounding MORE than on the GPU) against f64."""
+    lpr, ch = SCAN_VARIANTS[d]
+    rng = np.random.default_rng(d)
+    n = 4000
+    X = rng.uniform(-1, 1, (n, d)).astype(np.float32)
+    q = rng.uniform(-1, 1, d).astype(np.float32)
+    Xr = X.reshape(n, ch, lpr, 4)                            # element (chunk c of lane l, component e) = 4 * (l + lpr * c) + e
+    qr = q.reshape(ch, lpr, 4)
+    acc = np.zeros((n, lpr), dtype=np.float32)
+    for c in range(ch):
+        for e in range(4):
+            if cosine:
+                term = Xr[:, c, :, e] * qr[c, :, e]
+            else:
+                a = Xr[:, c, :, e] - qr[c, :, e]
+                term = a * a
+            acc = (acc + term).astype(np.float32)
+    h = lpr // 2
+    while h >= 1:                                            # butterfly: lane l adds lane l ^ h
+        acc = (acc[:, :h] + acc[:, h:2 * h]).astype(np.float32)
+        h //= 2
+    got = acc[:, 0].astype(np.float64)
+    X64, q64 = X.astype(np.float64), q.astype(np.float64)
+    if cosine:
+        err = np.abs(got - X64 @ q64) / (np.linalg.norm(X64, axis=1) * np.linalg.norm(q64))
+    else:
+        exact = ((X64 - q64) ** 2).sum(1)
+        err = np.abs(got - exact) / exact
+    assert err.max() < scan_eps(d, cosine), (d, cosine, err.max(), scan_eps(d, cosine))
