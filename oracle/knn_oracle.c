@@ -258,6 +258,16 @@ ORACLE_API void vrod_oracle_merge(const uint64_t *ids, const float *dist, uint32
     free(fin);
 }
 
+/* OpenMP team size for the calls that take no nthreads argument (vrod_oracle_fill): torchrun exports
+ * OMP_NUM_THREADS=1 to its workers, bench.py's rank 0 sets the real core count back with this. */
+ORACLE_API void vrod_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORACLE_API int vrod_oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -46,6 +46,8 @@ def lib():
         L.vrod_oracle_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                         C.c_void_p]
         L.vrod_oracle_max_threads.restype = C.c_int
+        L.vrod_oracle_set_threads.argtypes = [C.c_int]
+        L.vrod_oracle_set_threads.restype = None
         _lib = L
     return _lib
 
@@ -108,3 +110,23 @@ def merge(ids, dist):
 
 def max_threads():
     return int(lib().vrod_oracle_max_threads())
+
+
+def set_threads(n):
+    """OpenMP team size of fill() and of search(nthreads=0); see vrod_oracle_set_threads."""
+    lib().vrod_oracle_set_threads(int(n))
+
+
+def search_chunked(n, d, seed, queries, k, metric, chunk=4_000_000, nthreads=0):
+    """Exact top-k over the synthetic collection (n x d, `seed`) WITHOUT holding it: the Philox stream is replayed
+    in `chunk`-row pieces and the per-chunk lists are merged under the same (dist, id) order."""
+    queries = np.ascontiguousarray(queries, dtype=np.float32)
+    if queries.ndim == 1:
+        queries = queries[None, :]
+    parts_i, parts_d = [], []
+    for lo in range(0, n, chunk):
+        X = fill(min(chunk, n - lo), d, seed, row0=lo)
+        pi, pd = search(X, queries, k, metric, id_base=lo, nthreads=nthreads)
+        parts_i.append(pi)
+        parts_d.append(pd)
+    return merge(np.stack(parts_i), np.stack(parts_d))

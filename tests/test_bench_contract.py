@@ -21,6 +21,24 @@ def test_reference_arm_prints_the_contract_line():
     assert d["unit"] == "queries/s" and d["value"] > 0 and "workload" in d["config"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    # the line's ms_per_step is what was MEASURED (one bounded sample per step); the scale to the full collection is separate
+    assert d["steps"] * d["ms_per_step"] / 1e3 < 60 and d["sample_scale"] >= 1.0
+    assert abs(d["value"] * d["ms_per_step"] * d["sample_scale"] / 1e3 - 1.0) < 1e-6      # one query per step at batch 1
+
+
+def test_both_arms_print_the_same_config_keys():
+    sys.path.insert(0, ROOT)
+    import bench
+    for n in (1, 8):
+        cfg = bench.workload_config("cfg3", n)
+        assert cfg["rows"] == 100_000_000 and cfg["rows_per_gpu"] == 100_000_000 // n and cfg["batch"] == 1 and cfg["k"] == 10
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--rows", "20000"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    w = list(bench.WORKLOADS["cfg3"])
+    w[0] = 20000
+    bench.WORKLOADS["cfg3"] = tuple(w)
+    assert d["config"] == bench.workload_config("cfg3", 1)      # the vrod arm builds its config with the same call
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -594,6 +594,16 @@ static vrod_status finish_append(vrod_collection *c, uint64_t loc0, uint64_t cnt
     return VROD_OK;
 }
 
+// Sharded contexts: every rank sees the whole batch but validates (on the device) only the rows of its own
+// range, so a rank that owns none of a batch's bad rows would accept what the owning rank rejects and the ranks'
+// counts would drift apart.  All ranks therefore check the whole host buffer first (exponent all ones = inf/NaN).
+static bool host_rows_finite(const float *rows, size_t n) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(rows);
+    uint32_t bad = 0;
+    for (size_t i = 0; i < n; ++i) bad |= ((w[i] & 0x7f800000u) == 0x7f800000u) ? 1u : 0u;
+    return bad == 0;
+}
+
 // single-GPU collections: make room for at least `need` rows (capacity at least doubles)
 static vrod_status collection_grow(vrod_collection *c, uint64_t need) {
     vrod_ctx *ctx = c->ctx;
@@ -601,9 +611,17 @@ static vrod_status collection_grow(vrod_collection *c, uint64_t need) {
     if (cap >= 0xFFFFFFFFull) cap = 0xFFFFFFFEull;
     if (cap < need) return fail(VROD_ENOMEM, "more than 2^32-2 rows on one GPU");
     float *rows = nullptr, *inv = nullptr, *sq = nullptr;
-    cudaError_t e = cudaMalloc(&rows, (size_t)cap * c->ld * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&inv, (size_t)cap * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&sq, (size_t)cap * sizeof(float));
+    cudaError_t e = cudaSuccess;
+    for (int attempt = 0; attempt < 2; ++attempt) {   // doubled capacity first, exactly `need` rows if that does not fit
+        e = cudaMalloc(&rows, (size_t)cap * c->ld * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&inv, (size_t)cap * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&sq, (size_t)cap * sizeof(float));
+        if (e != cudaErrorMemoryAllocation || cap == need) break;
+        cudaGetLastError();
+        cudaFree(rows); cudaFree(inv); cudaFree(sq);
+        rows = inv = sq = nullptr;
+        cap = need;
+    }
     if (e == cudaSuccess && c->local) {
         e = cudaMemcpyAsync(rows, c->rows, (size_t)c->local * c->ld * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(inv, c->inv_norm, (size_t)c->local * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
@@ -644,6 +662,8 @@ static vrod_status vrod_collection_insert_impl(vrod_collection *c, const float *
         vrod_status gs = collection_grow(c, c->count + n);
         if (gs != VROD_OK) return gs;
     }
+    if (ctx->world > 1 && !host_rows_finite(rows, (size_t)n * c->dim))
+        return fail(VROD_EINVAL, "rows contain NaN or infinity");   // decided identically on every rank (same rows)
     uint64_t loc0, cnt, off;
     shard_overlap(c, c->count, n, &loc0, &cnt, &off);
     if (cnt) {
