@@ -3,6 +3,9 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 HOSTCXX   := /usr/bin/g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -std=c++17 -O3 -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC,-fvisibility=hidden -I/usr/include
+ifdef DEBUG_KERNELS
+NVFLAGS   += -DVROD_KERNEL_DEBUG    # development stamps / timing modes (VROD_BATCHED_DEBUG, VROD_SCAN_DEBUG): never in production
+endif
 CSRC      := vrod_b200/csrc
 OBJS      := $(CSRC)/knn_scan.o $(CSRC)/knn_batched.o $(CSRC)/vrod_capi.o
 LIB       := vrod_b200/libvrod_knn.so

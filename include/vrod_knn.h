@@ -91,6 +91,18 @@ VROD_API vrod_status vrod_comm_unique_id(void *out);
 VROD_API vrod_status vrod_ctx_create_sharded(int device, int rank, int world, const void *comm_id,
                                              vrod_ctx **out);
 
+/* ONE process, n_devices GPUs: the shape the reference's caller needs -- a single-threaded
+ * process holding Rc<RefCell<Database>> (src/command/types.rs:10; fn main, src/main.rs:42).  Every collection of
+ * the context is row-sharded over the devices (device i of the list holds shard i, contiguous id ranges); the
+ * calling thread drives all devices (one stream per device), the per-device top-k lists meet on the first device
+ * through direct NVLink peer access (fused push + merge kernel; peer copies for large batches or when the devices
+ * have no peer access) and only that device is read by the host.  All collection calls work on such a context
+ * with GLOBAL meaning (read_rows takes global row indices, shard reports base 0 and every row); the device-pointer
+ * search does not (VROD_EINVAL).  n_devices == 1 is vrod_ctx_create(device_ids[0]). */
+VROD_API vrod_status vrod_ctx_create_multi(const int *device_ids, int n_devices, vrod_ctx **out);
+/* Number of GPUs behind the context (1 unless it came from vrod_ctx_create_multi). */
+VROD_API int vrod_ctx_devices(vrod_ctx *ctx);
+
 VROD_API void vrod_ctx_destroy(vrod_ctx *ctx);
 VROD_API vrod_status vrod_ctx_synchronize(vrod_ctx *ctx);
 /* The cudaStream_t every kernel and copy of this context is issued on (for event timing). */
@@ -108,7 +120,8 @@ VROD_API int vrod_ctx_world(vrod_ctx *ctx);
 /* ---- collections (Database surface) ---------------------------------------------------- */
 
 /* CREATE: `capacity_rows` is the GLOBAL row capacity; a sharded context keeps ceil(capacity/world)
- * rows per rank.  dim >= 1. */
+ * rows per rank.  dim >= 1.  Names are 1..200 characters of [A-Za-z0-9_.-], not "." or ".." (they become file
+ * names and whitespace-delimited config tokens in the Database layer). */
 VROD_API vrod_status vrod_collection_create(vrod_ctx *ctx, const char *name, uint32_t dim, vrod_metric metric,
                                             uint64_t capacity_rows, vrod_collection **out);
 VROD_API vrod_status vrod_collection_get(vrod_ctx *ctx, const char *name, vrod_collection **out);
@@ -153,9 +166,13 @@ VROD_API vrod_status vrod_collection_shard(vrod_collection *c, uint64_t *id_base
 VROD_API vrod_status vrod_collection_search(vrod_collection *c, const float *queries, uint32_t b, uint32_t k,
                                             uint64_t *out_ids, float *out_dist);
 
-/* Same, with queries and outputs already resident in device memory of the context's GPU.  The work
- * is enqueued on vrod_ctx_stream() and the call returns without synchronising; queries must have
- * been validated (finite) by the caller. */
+/* Same, with queries and outputs already resident in device memory of the context's GPU.  The work is enqueued on
+ * vrod_ctx_stream(); single-query scans return without synchronising, a batch answered by the tensor-core pass
+ * synchronises once (its guard flags are read on the host).  Precondition (checked by the host-buffer call, NOT
+ * here): queries are finite, |q_j| <= 2^40 and 2^-40 <= ||q|| <= 2^50, and not all-zero under the cosine metric --
+ * outside that range the f32 / bf16 error bounds of the fast passes do not hold; use vrod_collection_search or
+ * vrod_collection_set_path(c, 2).  A peer that never takes part in a sharded search is reported by
+ * vrod_ctx_synchronize (VROD_ENCCL). */
 VROD_API vrod_status vrod_collection_search_device(vrod_collection *c, const float *d_queries, uint32_t b,
                                                    uint32_t k, uint64_t *d_out_ids, float *d_out_dist);
 

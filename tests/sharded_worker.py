@@ -70,6 +70,35 @@ def main():
     assert_same(ids, dd, *O.search(X, X[3], 5, 0))
     ctx.drop("ins")
 
+    # a batch with ONE non-finite value lands on one rank only: every rank must reject it (and keep its count), or the
+    # ranks' ids drift apart for every later insert
+    c = ctx.create("bad", d, 0, n)
+    c.insert(X[:1000])
+    bad = X[1000:1100].copy()
+    bad[0, 0] = np.inf
+    try:
+        c.insert(bad)
+        raise AssertionError("a batch with an infinity was accepted")
+    except ffi.VrodError as e:
+        assert e.status == ffi.EINVAL
+    assert c.info()["count"] == 1000
+    assert c.insert(X[1000:]) == 1000
+    assert_same(*c.search(X[n - 1], 3), *O.search(X, X[n - 1], 3, 0))
+    ctx.drop("bad")
+
+    # large batches leave the fused exchange for ncclAllGather + merge; alternating the two paths with different (b, k)
+    # shifts the packed result layout over stale words -- no call may report a spurious exchange time-out
+    c = ctx.create("alt", 128, 0, 60_000)
+    c.fill_synthetic(60_000, 48)
+    Xa = O.fill(60_000, 128, 48)
+    for (b, k) in [(3, 10), (1024, 10), (1, 1), (300, 100), (7, 3), (1024, 1), (2, 100)]:
+        Q = O.fill(b, 128, 49 + b)
+        ids, dd = c.search(Q, k)
+        if rank == 0:
+            assert_same(ids, dd, *O.search(Xa, Q, k, 0), f"alternating exchange paths b={b} k={k}")
+    ctx.synchronize()
+    ctx.drop("alt")
+
     # resident (device-pointer) entry point, also collective
     c = ctx.create("dev", 128, 0, 200_000)
     c.fill_synthetic(200_000, 44)

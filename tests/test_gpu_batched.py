@@ -242,3 +242,26 @@ def test_auto_path_stops_paying_for_a_pass_that_proves_nothing(ctx, oracle):
     assert tiles[0] > 0, "the first batch should have tried the tensor cores"
     assert tiles[-1] == 0, f"later batches should be answered by scans alone: {tiles}"
     ctx.drop("learn")
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_many_queries_few_rows_keeps_the_tensor_core_answers(ctx, oracle, metric):
+    """b >= 8192 with k ~ 100 on ~100k rows: few row tiles per CTA and 8x phase growth make the per-(CTA, query) lists
+    pass their prune mark INSIDE a phase.  In bf16 mode the prune must not touch the threshold that is folded into the
+    contraction (the surrogate of a later candidate is recovered as thr_folded - D): round 1 overwrote it, every later
+    candidate was understated, and most of the batch failed its proof and was rescanned one query at a time."""
+    n, d, b, k = 100_000, 64, 8192, 100
+    c = ctx.create(f"manyq{metric}", d, metric, n)
+    c.fill_synthetic(n, 77)
+    c.set_path(3)
+    X = oracle.fill(n, d, 77)
+    Q = oracle.fill(b, d, 78)
+    s0 = ctx.stats()
+    ids, dist = c.search(Q, k)
+    s1 = ctx.stats()
+    assert s1["batched_tiles"] > s0["batched_tiles"]
+    rescanned = s1["fast_scans"] - s0["fast_scans"]
+    assert rescanned <= b // 100, f"{rescanned} of {b} queries fell back to single scans"
+    sel = np.r_[0:64, b - 64:b]                     # the oracle checks a slice (k = 100 over 100k rows x 8192 queries is slow)
+    assert_same(ids[sel], dist[sel], *oracle.search(X, Q[sel], k, metric), "many queries, few rows")
+    ctx.drop(c.name)

@@ -12,8 +12,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("exchange", ["fused", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_search_matches_oracle(world):
+def test_sharded_search_matches_oracle(world, exchange):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, have {torch.cuda.device_count()}")
@@ -23,5 +24,7 @@ def test_sharded_search_matches_oracle(world):
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "sharded_worker.py")]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    env = dict(os.environ, VROD_NO_P2P_EXCHANGE="1") if exchange == "nccl" else dict(os.environ)
+    env.pop("VROD_NO_P2P_EXCHANGE", None) if exchange == "fused" else None
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and f"SHARDED_OK world {world}" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -208,6 +208,10 @@ struct BatchCtl {
 // ---- epilogue: prune one (CTA, query) list with one warp ------------------------------------------
 // Keep the entries <= t where t is the smallest sampled key with at least kprime entries at or below
 // it (verified by an exact count), compact them to the front, tighten the threshold.
+// H (bf16 mode): ctl->thr[q] is the threshold FOLDED into the contraction (the accumulator holds D = dot + thr - hx and
+// warp_append recovers the surrogate as thr - D), so it must stay what the query mirror carries: the prune then only
+// compacts the list and candidates keep arriving at the phase threshold until the next phase tightens it.
+template <bool H>
 __device__ __forceinline__ void prune_list(unsigned long long *cq, int q, BatchCtl *ctl, int kprime, int lane, int *fail) {
     const int c = ctl->cnt[q];
     if (c <= kprime) return;
@@ -243,7 +247,7 @@ __device__ __forceinline__ void prune_list(unsigned long long *cq, int q, BatchC
         if (lane == 0) {
             *fail = 1;
             ctl->cnt[q] = 0;
-            ctl->thr[q] = -__int_as_float(0x7f800000);
+            if (!H) ctl->thr[q] = -__int_as_float(0x7f800000);
         }
         return;
     }
@@ -257,7 +261,7 @@ __device__ __forceinline__ void prune_list(unsigned long long *cq, int q, BatchC
     }
     if (lane == 0) {
         ctl->cnt[q] = base;
-        ctl->thr[q] = ord2f((uint32_t)(t >> 32));
+        if (!H) ctl->thr[q] = ord2f((uint32_t)(t >> 32));
     }
 }
 
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < BN; i += kThreads) {
-        const bool live = g * BN + i < p.b && !p.debug_nocand;
+        const bool live = g * BN + i < p.b && !(kDbg && p.debug_nocand);
         const float t0 = (live && p.thr_init) ? p.thr_init[g * BN + i] : __int_as_float(0x7f800000);
         ctl->thr[i] = live ? t0 : -__int_as_float(0x7f800000);
         ctl->cnt[i] = 0;
@@ -466,16 +470,16 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             for (uint32_t i = 0; i < my_tiles; ++i) {
                 const uint32_t tile = tile_of(i);
                 for (uint32_t s = 0; s < p.nslab; ++s) {
-                    const long long te = p.dbg ? clock64() : 0;
+                    const long long te = (kDbg && p.dbg) ? clock64() : 0;
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
-                    if (p.dbg) w_empty += clock64() - te;
+                    if (kDbg && p.dbg) w_empty += clock64() - te;
                     arm(&ctl->full[stage], stage_bytes);
                     load(a_s + (size_t)stage * stage_bytes, &tmX, (int)(s * KSE), (int)(tile * BM), &ctl->full[stage]);
                     if (p.stream_q) load(a_s + (size_t)stage * stage_bytes + SLAB_A_BYTES, &tmQ, (int)(s * KSE), q_row0, &ctl->full[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
-            if (p.dbg) p.dbg[blockIdx.x * 16 + 9] = w_empty;
+            if (kDbg && p.dbg) p.dbg[blockIdx.x * 16 + 9] = w_empty;
         }
     } else if (warp == 1) {
         // ===== peer CTA of a pair: forward "my slab has landed" to the leader, one remote arrive per slab =====
@@ -500,22 +504,22 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             }
             uint32_t stage = 0, phase = 0;
             long long w_tempty = 0, w_full = 0, w_pfull = 0;
-            const long long tstart = clock64();
+            const long long tstart = kDbg ? clock64() : 0;
             for (uint32_t i = 0; i < my_tiles; ++i) {
                 const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
-                long long t0 = p.dbg ? clock64() : 0;
+                long long t0 = (kDbg && p.dbg) ? clock64() : 0;
                 mbar_wait(&ctl->tempty[acc], aphase ^ 1);
-                if (p.dbg) w_tempty += clock64() - t0;
+                if (kDbg && p.dbg) w_tempty += clock64() - t0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + acc * BN;
                 for (uint32_t s = 0; s < p.nslab; ++s) {
-                    t0 = p.dbg ? clock64() : 0;
+                    t0 = (kDbg && p.dbg) ? clock64() : 0;
                     mbar_wait(&ctl->full[stage], phase);
-                    if (p.dbg) w_full += clock64() - t0;
+                    if (kDbg && p.dbg) w_full += clock64() - t0;
                     if constexpr (PSZ == 2) {
-                        t0 = p.dbg ? clock64() : 0;
+                        t0 = (kDbg && p.dbg) ? clock64() : 0;
                         mbar_wait(&ctl->pfull[stage], phase);
-                        if (p.dbg) w_pfull += clock64() - t0;
+                        if (kDbg && p.dbg) w_pfull += clock64() - t0;
                     }
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(a_s + (size_t)stage * stage_bytes);
@@ -523,7 +527,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                     const uint32_t nk = s + 1 == p.nslab ? p.ksteps_last : 4u;   // 4 MMA K steps of 32 bytes per slab
 #pragma unroll
                     for (uint32_t kk = 0; kk < 4; ++kk) {
-                        if ((p.debug_skip & 2) || kk >= nk) break;
+                        if ((kDbg && (p.debug_skip & 2)) || kk >= nk) break;
                         const uint64_t ad = umma_desc_sw128(a_addr + kk * 32), bd = umma_desc_sw128(b_addr + kk * 32);
                         const uint32_t accum = (s | kk) != 0 ? 1u : 0u;
                         if constexpr (H) tc_mma_bf16(d_tmem, ad, bd, idesc_bf16(), accum);
@@ -539,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 if constexpr (PSZ == 2) tc_commit_pair(&ctl->tfull[acc]);
                 else tc_commit(&ctl->tfull[acc]);
             }
-            if (p.dbg) {
+            if (kDbg && p.dbg) {
                 p.dbg[blockIdx.x * 16 + 5] = w_tempty;
                 p.dbg[blockIdx.x * 16 + 6] = w_full;
                 p.dbg[blockIdx.x * 16 + 8] = w_pfull;
@@ -554,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
         unsigned long long *cand = p.cand + (size_t)blockIdx.x * BN * CAP;
         int fail = 0;
         long long w_tfull = 0, w_prune = 0, n_slow = 0;
-        const long long tstart = clock64();
+        const long long tstart = kDbg ? clock64() : 0;
         // per-row factor of the NEXT tile is fetched one tile ahead (its global-load latency would otherwise
         // sit on the critical path of every tile)
         // (the raw value is kept and scaled only when used, so nothing waits on the load here)
@@ -570,9 +574,9 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             const bool rowok = row < p.n;
             const float hx = COS ? hx_next : 0.5f * hx_next;
             if (i + 1 < my_tiles) hx_next = row_factor(tile_of(i + 1) * BM + quad * 32 + lane);
-            long long t0 = p.dbg ? clock64() : 0;
+            long long t0 = (kDbg && p.dbg) ? clock64() : 0;
             mbar_wait(&ctl->tfull[acc], aphase);
-            if (p.dbg) w_tfull += clock64() - t0;
+            if (kDbg && p.dbg) w_tfull += clock64() - t0;
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * BN + half * (BN / 2);
             // Hot loop: branch-free filter of this warp's 32 rows x 128 columns, 32 columns at a time, the next
@@ -583,26 +587,26 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             const float *thr_h = ctl->thr + half * (BN / 2);
             const float ninf = -__int_as_float(0x7f800000);
             const int col_h = half * (BN / 2);
-            if (!(p.debug_skip & 1)) {
+            if (!(kDbg && (p.debug_skip & 1))) {
                 tc_ld32(taddr, ra);
                 tc_wait_ld();
 #pragma unroll 1
                 for (int cb = 0; cb < BN / 64; cb += 2) {
                     tc_ld32(taddr + (cb + 1) * 32, rb);
                     float wa = H ? block_max_h(ra) : block_max<COS>(ra, thr_h + cb * 32, hx, ninf);
-                    if (p.debug_skip & 4) wa = __uint_as_float(ra[0] & ra[31] & 0x80000000u) - 1.f;   // ldonly: no scan of the block
+                    if (kDbg && (p.debug_skip & 4)) wa = __uint_as_float(ra[0] & ra[31] & 0x80000000u) - 1.f;   // ldonly: no scan of the block
                     const bool hita = (H ? wa > 0.f : cand_hit<COS>(wa, hx)) && rowok;
                     if (__builtin_expect(__any_sync(kFull, hita), 0)) {
-                        n_slow++;
+                        if (kDbg) n_slow++;
                         warp_append<COS, H>(ra, hita, thr_h + cb * 32, hx, col_h + cb * 32, row, ctl, cand, p.qflags, g * BN, p.b, lane);
                     }
                     tc_wait_ld();
                     if (cb + 2 < BN / 64) tc_ld32(taddr + (cb + 2) * 32, ra);
                     float wb = H ? block_max_h(rb) : block_max<COS>(rb, thr_h + (cb + 1) * 32, hx, ninf);
-                    if (p.debug_skip & 4) wb = __uint_as_float(rb[0] & rb[31] & 0x80000000u) - 1.f;
+                    if (kDbg && (p.debug_skip & 4)) wb = __uint_as_float(rb[0] & rb[31] & 0x80000000u) - 1.f;
                     const bool hitb = (H ? wb > 0.f : cand_hit<COS>(wb, hx)) && rowok;
                     if (__builtin_expect(__any_sync(kFull, hitb), 0)) {
-                        n_slow++;
+                        if (kDbg) n_slow++;
                         warp_append<COS, H>(rb, hitb, thr_h + (cb + 1) * 32, hx, col_h + (cb + 1) * 32, row, ctl, cand, p.qflags, g * BN, p.b, lane);
                     }
                     if (cb + 2 < BN / 64) tc_wait_ld();
@@ -620,9 +624,9 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             if ((i + 1) % kCheckEvery != 0) continue;
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (*(volatile int *)&ctl->flag) {
-                t0 = clock64();
+                t0 = kDbg ? clock64() : 0;
                 for (int q = ew; q < BN; q += kEpiWarps) {
-                    if (ctl->cnt[q] > PRUNE_AT / 2) prune_list(cand + (size_t)q * CAP, q, ctl, p.kprime, lane, &fail);
+                    if (ctl->cnt[q] > PRUNE_AT / 2) prune_list<H>(cand + (size_t)q * CAP, q, ctl, p.kprime, lane, &fail);
                     if (fail) {
                         if (lane == 0 && g * BN + q < p.b) atomicOr(p.qflags + g * BN + q, 1);
                         fail = 0;
@@ -631,10 +635,10 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (ew == 0 && lane == 0) ctl->flag = 0;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                w_prune += clock64() - t0;
+                if (kDbg) w_prune += clock64() - t0;
             }
         }
-        if (p.dbg && ew == 0 && lane == 0) {
+        if (kDbg && p.dbg && ew == 0 && lane == 0) {
             p.dbg[blockIdx.x * 16 + 7] = clock64() - tstart;
             p.dbg[blockIdx.x * 16 + 0] = n_slow;
 
@@ -1130,7 +1134,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         if (H) {
             if (!make_map(&tmX, s.rows_h, true, s.n, ld_h, BM) || !make_map(&tmQ, qh, true, bq, ld_h, BN)) return cudaErrorInvalidValue;
             auto prep = s.metric ? prep_queries_kernel<true> : prep_queries_kernel<false>;
-            const char *dbg = getenv("VROD_BATCHED_DEBUG");
+            const char *dbg = kDbg ? getenv("VROD_BATCHED_DEBUG") : nullptr;
             const bool nocand = dbg && (strstr(dbg, "nocand") || strstr(dbg, "noepi") || strstr(dbg, "nomma") || strstr(dbg, "ldonly"));
             prep<<<(bq + 7) / 8, 256, 0, st>>>(qw, bq, s.ld, kd, ld_h, s.maxnorm_bits, qh, gthr, qcap, nocand ? -1.f : 1.f);
             if (stats) stats->launches += 1;
@@ -1151,7 +1155,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         p.cnt_out = cnt;
         p.qflags = qflags;
         p.kprime = kprime;
-        {
+        if (kDbg) {
             const char *dbg = getenv("VROD_BATCHED_DEBUG");
             p.debug_nocand = dbg && (strcmp(dbg, "nocand") == 0 || strstr(dbg, "noepi") || strstr(dbg, "nomma") || strstr(dbg, "ldonly"));
             p.debug_skip = dbg ? ((strstr(dbg, "noepi") ? 1 : 0) | (strstr(dbg, "nomma") ? 2 : 0) | (strstr(dbg, "ldonly") ? 4 : 0)) : 0;
@@ -1250,7 +1254,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             e = cudaGetLastError();
             if (e != cudaSuccess) return e;
             if (stats) stats->launches += 2;
-            if (g_dbg_buf && getenv("VROD_BATCHED_DEBUG")) {
+            if (kDbg && g_dbg_buf && getenv("VROD_BATCHED_DEBUG")) {
                 static long long h[1024 * 16];
                 cudaStreamSynchronize(st);
                 cudaMemcpy(h, g_dbg_buf, sizeof(long long) * grid * 16, cudaMemcpyDeviceToHost);

@@ -13,6 +13,15 @@ constexpr int kScanWarps = kScanThreads / 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint64_t kKeyMax = 0xFFFFFFFFFFFFFFFFull;
 
+// Development instrumentation (cycle / globaltimer stamps, "skip the MMA / the epilogue" timing experiments) is
+// compiled in only by `make DEBUG_KERNELS=1`: the production kernels carry none of it (every use is guarded by
+// this constant, so the branches and the clock reads fold away).
+#ifdef VROD_KERNEL_DEBUG
+constexpr bool kDbg = true;
+#else
+constexpr bool kDbg = false;
+#endif
+
 // ---- order-preserving float <-> uint32 (so (value, row) packs into one comparable u64) --------
 __device__ __forceinline__ uint32_t f2ord(float v) {
     uint32_t b = __float_as_uint(v);

@@ -74,7 +74,7 @@ __device__ __forceinline__ bool finish_and_merge(CandCtl *ctl, unsigned long lon
     __syncthreads();
     if (!ctl->is_last) return false;
     __threadfence();
-    if (p.dbg && tid == 0) p.dbg[2] = gtimer();
+    if (kDbg && p.dbg && tid == 0) p.dbg[2] = gtimer();
 
     // ---- last CTA: merge gridDim.x sorted lists, walking them by depth ----
     if (tid == 0) {
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) fast_scan_kernel(const ScanPa
 #pragma unroll
         for (int c = 0; c < CH; ++c) qv[c] = __ldg(p.q4 + ls + LPR * c);
     }
-    if (p.dbg && tid == 0) atomicMin(p.dbg + 0, gtimer());
+    if (kDbg && p.dbg && tid == 0) atomicMin(p.dbg + 0, gtimer());
     __syncthreads();
 
     const int water = p.water;
@@ -254,9 +254,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) fast_scan_kernel(const ScanPa
         }
     }
 
-    if (p.dbg && tid == 0) atomicMax(p.dbg + 1, gtimer());
+    if (kDbg && p.dbg && tid == 0) atomicMax(p.dbg + 1, gtimer());
     if (!finish_and_merge(ctl, buf, p, tid)) return;
-    if (p.dbg && tid == 0) p.dbg[3] = gtimer();
+    if (kDbg && p.dbg && tid == 0) p.dbg[3] = gtimer();
 
     // ---- last CTA: exact rerank of the survivors in canonical f64, guard, output ----
     const int ncand = ctl->cnt;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) fast_scan_kernel(const ScanPa
     __syncthreads();
     rerank_candidates<COS>(buf, ncand, p.rows4, p.q4, (int)p.ld4, ctl->nq, warp, lane);
     __syncthreads();
-    if (p.dbg && tid == 0) p.dbg[4] = gtimer();
+    if (kDbg && p.dbg && tid == 0) p.dbg[4] = gtimer();
     {
         int P = 32;
         while (P < ncand) P <<= 1;
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) fast_scan_kernel(const ScanPa
     }
     write_hits(buf, ncand, p, tid);
     if (tid == 0) {
-        if (p.dbg) p.dbg[5] = gtimer();
+        if (kDbg && p.dbg) p.dbg[5] = gtimer();
         int bad = ctl->overflow;
         if (p.n > (uint32_t)ncand) {
             // rows were dropped: every dropped row has surrogate >= u_val.  Bound its exact distance
@@ -517,10 +517,15 @@ __global__ void __launch_bounds__(kScanThreads) merge_hits_kernel(const Hit *lis
 // This replaces ncclAllGather + merge_hits_kernel (two launches, ~20-30 us of latency at 8 GPUs) with one launch
 // whose transfers overlap per query.  Searches are collective and sequence numbers advance in lockstep; two slots
 // suffice because a rank cannot start pushing search s+2 before every peer has merged search s.
+// root == kXchgAllRanks: all-to-all as above (one process per GPU: every rank returns the global answer).
+// root == r (single-process multi-GPU contexts, where the host reads the answer from device r only): the ranks push
+// into rank r's window alone and only rank r waits and merges; the host does not issue search s+1 before it has
+// read the answer of search s, which is what keeps the two slots sufficient there.
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanThreads) exchange_merge_kernel(unsigned char *const *windows, uint32_t rank, uint32_t world,
                                                                       uint32_t seq, const Hit *local, uint32_t b, uint32_t k,
-                                                                      unsigned long long *out_ids, float *out_dist, int *err) {
+                                                                      unsigned long long *out_ids, float *out_dist, int *err,
+                                                                      uint32_t root) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem);
     const int tid = threadIdx.x;
@@ -533,15 +538,26 @@ __global__ void __launch_bounds__(kScanThreads) exchange_merge_kernel(unsigned c
     auto data_of = [&](unsigned char *w, uint32_t r) {
         return reinterpret_cast<Hit *>(w + flags_bytes) + ((size_t)slot * kXchgMaxWorld + r) * kXchgMaxHits + (size_t)qi * k;
     };
+    const bool all = root == kXchgAllRanks;
     if (qi == 0 && tid == 0) *err = 0;   // a time-out (>= 2.5 s later) sets it to 1
     // (1) push
-    for (uint32_t i = tid; i < world * k; i += kScanThreads) {
-        const uint32_t r = i / k, j = i % k;
-        data_of(windows[r], rank)[j] = local[(size_t)qi * k + j];
+    if (all) {
+        for (uint32_t i = tid; i < world * k; i += kScanThreads) {
+            const uint32_t r = i / k, j = i % k;
+            data_of(windows[r], rank)[j] = local[(size_t)qi * k + j];
+        }
+    } else {
+        Hit *dst = data_of(windows[root], rank);
+        for (uint32_t j = tid; j < k; j += kScanThreads) dst[j] = local[(size_t)qi * k + j];
     }
     __threadfence_system();
     __syncthreads();
-    if (tid < (int)world) *(volatile unsigned int *)flag_of(windows[tid], rank) = seq;
+    if (all) {
+        if (tid < (int)world) *(volatile unsigned int *)flag_of(windows[tid], rank) = seq;
+    } else {
+        if (tid == 0) *(volatile unsigned int *)flag_of(windows[root], rank) = seq;
+        if (rank != root) return;
+    }
     // (2) wait for every peer's push of this query into MY window
     unsigned char *mine = windows[rank];
     if (tid < (int)world) {
@@ -783,14 +799,15 @@ size_t xchg_window_bytes() {
 }
 
 cudaError_t launch_exchange_merge(unsigned char *const *d_windows, uint32_t rank, uint32_t world, uint32_t seq, const Hit *local,
-                                  uint32_t b, uint32_t k, unsigned long long *out_ids, float *out_dist, int *d_err, cudaStream_t st) {
+                                  uint32_t b, uint32_t k, unsigned long long *out_ids, float *out_dist, int *d_err, uint32_t root,
+                                  cudaStream_t st) {
     if (b == 0) return cudaSuccess;
     const size_t smem = (size_t)next_pow2((int)(world * k) < 32 ? 32 : (int)(world * k)) * sizeof(unsigned long long);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    exchange_merge_kernel<<<b, kScanThreads, smem, st>>>(d_windows, rank, world, seq, local, b, k, out_ids, out_dist, d_err);
+    exchange_merge_kernel<<<b, kScanThreads, smem, st>>>(d_windows, rank, world, seq, local, b, k, out_ids, out_dist, d_err, root);
     return cudaGetLastError();
 }
 

@@ -68,8 +68,10 @@ cudaError_t launch_pad_queries(const float *src, float *dst, uint32_t b, uint32_
 // searches with b <= kXchgMaxB queries and b*k <= kXchgMaxHits hits on at most kXchgMaxWorld ranks.
 constexpr uint32_t kXchgMaxWorld = 16, kXchgMaxB = 256, kXchgMaxHits = 4096;
 size_t xchg_window_bytes();
+constexpr uint32_t kXchgAllRanks = 0xffffffffu;   // root: every rank merges; else only rank `root` receives and merges
 cudaError_t launch_exchange_merge(unsigned char *const *d_windows, uint32_t rank, uint32_t world, uint32_t seq, const Hit *local,
-                                  uint32_t b, uint32_t k, unsigned long long *out_ids, float *out_dist, int *d_err, cudaStream_t st);
+                                  uint32_t b, uint32_t k, unsigned long long *out_ids, float *out_dist, int *d_err, uint32_t root,
+                                  cudaStream_t st);
 // merge g lists of [b][k] hits (layout [g][b][k]) into ids/dist [b][k] by (dist, id)
 cudaError_t launch_merge_hits(const Hit *lists, uint32_t g, uint32_t b, uint32_t k, unsigned long long *out_ids,
                               float *out_dist, cudaStream_t st);

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "knn_batched.cuh"
+#include "knn_device.cuh"
 #include "knn_scan.cuh"
 
 using namespace vrod;
@@ -138,6 +139,72 @@ struct PinBuf {
     }
 };
 
+// Scan-versus-batched cost model of the automatic path choice.  Seeded with figures measured on one box in round 1
+// (a scan = ~25 us + its bytes at 6.5 TB/s; a batched pass = ~200 us of phase and launch overhead + 1.45 us per
+// 128-row tile x 144 bf16 columns x 256-query group, spread over the SMs), then corrected by what THIS context
+// measures: every 16th search brackets its scan launch / batched pass with two events of its own; once they have
+// completed (polled at a later search, never waited for) the elapsed time is folded into the matching term.  The
+// boxes of this pool differed by 1537..1965 MHz under load, which the seeds alone would not follow.
+struct CostModel {
+    double scan_fixed = 25e-6, hbm_bps = 6.5e12, batched_fixed = 200e-6, tile_seconds = 1.45e-6;
+    uint32_t calls = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int pending_kind = 0;      // 0 none, 1 scan, 2 batched
+    double pending_work = 0.0;
+    double scan_seconds(double bytes) const { return scan_fixed + bytes / hbm_bps; }
+    double batched_seconds(double units) const { return batched_fixed + units * tile_seconds; }
+    bool want_sample() const { return pending_kind == 0 && (calls & 15u) == 1u; }
+    bool events(cudaEvent_t *e0, cudaEvent_t *e1) {
+        for (cudaEvent_t &e : ev)
+            if (!e && cudaEventCreate(&e) != cudaSuccess) {
+                cudaGetLastError();
+                e = nullptr;
+                return false;
+            }
+        *e0 = ev[0];
+        *e1 = ev[1];
+        return true;
+    }
+    void pending(int kind, double work) {
+        pending_kind = kind;
+        pending_work = work;
+    }
+    static double blend(double old_v, double new_v, double seed) {
+        if (!(new_v > 0.25 * seed)) new_v = 0.25 * seed;   // one odd sample (a clock ramp, a page fault) must not swing the choice
+        if (new_v > 4.0 * seed) new_v = 4.0 * seed;
+        return 0.75 * old_v + 0.25 * new_v;
+    }
+    void collect() {
+        ++calls;
+        if (pending_kind == 0 || cudaEventQuery(ev[1]) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess && ms > 0.f) {
+            const double t = ms * 1e-3;
+            if (pending_kind == 1) {
+                const double stream_t = pending_work / hbm_bps;
+                if (stream_t > 4.0 * scan_fixed) hbm_bps = blend(hbm_bps, pending_work / (t > scan_fixed ? t - scan_fixed : t), 6.5e12);
+                else if (stream_t < scan_fixed) scan_fixed = blend(scan_fixed, t - stream_t, 25e-6);
+            } else {
+                const double tiles_t = pending_work * tile_seconds;
+                if (tiles_t > 4.0 * batched_fixed) tile_seconds = blend(tile_seconds, (t > batched_fixed ? t - batched_fixed : t) / pending_work, 1.45e-6);
+                else if (tiles_t < batched_fixed) batched_fixed = blend(batched_fixed, t - tiles_t, 200e-6);
+            }
+        } else {
+            cudaGetLastError();
+        }
+        pending_kind = 0;
+    }
+    void release() {
+        for (cudaEvent_t &e : ev) {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
+    }
+};
+
 struct vrod_ctx {
     int device = 0, rank = 0, world = 1, sms = 0;
     cudaStream_t stream = nullptr;
@@ -155,6 +222,13 @@ struct vrod_ctx {
     int *d_xchg_err = nullptr;
     uint32_t xchg_seq = 0;
     bool fused_exchange = false;
+    CostModel cost;
+    cudaEvent_t ev_status = nullptr;            // marks the guard flags' arrival in status_host (batched path)
+    // single-process multi-GPU context (vrod_ctx_create_multi): the parent owns one sub-context per device (sub r is
+    // "rank r of subs.size()": same shard rule, same kernels) and drives them all from the caller's one thread
+    std::vector<vrod_ctx *> subs;               // empty for single-GPU and per-rank contexts
+    vrod_ctx *parent = nullptr;
+    cudaEvent_t ev_done = nullptr;              // sub: this device's hits have been copied to device 0 (gather path)
     // optional kernel timing (vrod_ctx_profile)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
@@ -192,6 +266,7 @@ struct vrod_collection {
     // automatic path choice discounts the batched pass by it, so that data the tensor-core pass cannot resolve
     // (tight clusters under the Euclidean metric) stops paying for a pass that proves nothing
     double rescan_share = 0.0;
+    std::vector<vrod_collection *> parts;   // collection of a multi-GPU parent context: one part per device, in id order
 };
 
 static int *ctx_ticket(vrod_ctx *c) { return reinterpret_cast<int *>(c->small.p); }
@@ -282,6 +357,93 @@ static vrod_status vrod_ctx_create_sharded_impl(int device, int rank, int world,
     return VROD_OK;
 }
 
+// Single-process multi-GPU context (the reference's caller is ONE single-threaded
+// process -- Rc<RefCell<Database>>, src/command/types.rs:10; fn main, src/main.rs:42).  One sub-context per device
+// ("rank r of n": same shard rule, same kernels as the process-per-GPU mode), all driven from the caller's thread.
+// The devices' exchange windows are plain cudaMalloc memory reached through direct peer access (no IPC needed inside
+// one process); without peer access the per-device lists are gathered on device 0 with cudaMemcpyPeerAsync instead.
+static vrod_status vrod_ctx_create_multi_impl(const int *device_ids, int n_devices, vrod_ctx **out);
+extern "C" vrod_status vrod_ctx_create_multi(const int *device_ids, int n_devices, vrod_ctx **out) {
+    return guarded([&]() -> vrod_status { return vrod_ctx_create_multi_impl(device_ids, n_devices, out); });
+}
+static vrod_status vrod_ctx_create_multi_impl(const int *device_ids, int n_devices, vrod_ctx **out) {
+    if (!out) return fail(VROD_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!device_ids || n_devices < 1 || n_devices > (int)kXchgMaxWorld) return fail(VROD_EINVAL, "need 1..16 device ordinals");
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (device_ids[i] == device_ids[j]) return fail(VROD_EINVAL, "a device ordinal is listed twice");
+    if (n_devices == 1) return vrod_ctx_create_impl(device_ids[0], out);
+    vrod_ctx *parent = new (std::nothrow) vrod_ctx();
+    if (!parent) return fail(VROD_ENOMEM, "host allocation failed");
+    struct Undo {   // any early return tears down what was built (the error message is kept)
+        vrod_ctx *p;
+        ~Undo() {
+            if (!p) return;
+            const std::string msg = g_last_error;
+            vrod_ctx_destroy(p);
+            g_last_error = msg;
+        }
+    } undo{parent};
+    parent->device = device_ids[0];
+    const int W = n_devices;
+    for (int r = 0; r < W; ++r) {
+        vrod_ctx *sub = new (std::nothrow) vrod_ctx();
+        if (!sub) return fail(VROD_ENOMEM, "host allocation failed");
+        parent->subs.push_back(sub);
+        sub->parent = parent;
+        vrod_status st = ctx_init(sub, device_ids[r]);
+        if (st != VROD_OK) return st;
+        sub->rank = r;
+        sub->world = W;
+        VROD_CUDA(cudaEventCreateWithFlags(&sub->ev_done, cudaEventDisableTiming));
+    }
+    parent->sms = parent->subs[0]->sms;
+    // direct peer access between every pair of devices (NVLink through the NVSwitch on an HGX box)
+    bool peer_ok = getenv("VROD_NO_P2P_EXCHANGE") == nullptr;
+    for (int i = 0; i < W && peer_ok; ++i) {
+        VROD_CUDA(cudaSetDevice(device_ids[i]));
+        for (int j = 0; j < W && peer_ok; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, device_ids[i], device_ids[j]) != cudaSuccess || !can) {
+                peer_ok = false;
+                break;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(device_ids[j], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) peer_ok = false;
+            cudaGetLastError();
+        }
+    }
+    if (peer_ok) {
+        std::vector<unsigned char *> wins(W, nullptr);
+        for (int r = 0; r < W; ++r) {
+            vrod_ctx *sub = parent->subs[r];
+            VROD_CUDA(cudaSetDevice(sub->device));
+            VROD_CUDA(cudaMalloc(&sub->xchg, xchg_window_bytes()));
+            VROD_CUDA(cudaMemsetAsync(sub->xchg, 0, xchg_window_bytes(), sub->stream));
+            VROD_CUDA(cudaMalloc(&sub->d_xchg_err, 64));
+            VROD_CUDA(cudaMemsetAsync(sub->d_xchg_err, 0, 64, sub->stream));
+            wins[r] = sub->xchg;
+        }
+        for (int r = 0; r < W; ++r) {
+            vrod_ctx *sub = parent->subs[r];
+            VROD_CUDA(cudaSetDevice(sub->device));
+            VROD_CUDA(cudaMalloc(&sub->d_windows, sizeof(unsigned char *) * W));
+            VROD_CUDA(cudaMemcpyAsync(sub->d_windows, wins.data(), sizeof(unsigned char *) * W, cudaMemcpyHostToDevice, sub->stream));
+            VROD_CUDA(cudaStreamSynchronize(sub->stream));
+            sub->fused_exchange = true;
+        }
+    }
+    if (getenv("VROD_VERBOSE"))
+        fprintf(stderr, "[vrod] single-process context over %d devices: %s\n", W,
+                peer_ok ? "fused NVLink exchange through direct peer access" : "no peer access, lists gathered with cudaMemcpyPeerAsync");
+    VROD_CUDA(cudaSetDevice(parent->device));
+    undo.p = nullptr;
+    *out = parent;
+    return VROD_OK;
+}
+
 // Map every rank's exchange window into this process (CUDA IPC over NVLink P2P).  Collective.  On any failure
 // on any rank all ranks fall back to ncclAllGather + merge.
 static vrod_status setup_fused_exchange(vrod_ctx *c) {
@@ -349,6 +511,18 @@ static void collection_free(vrod_collection *c) {
 
 extern "C" void vrod_ctx_destroy(vrod_ctx *ctx) {
     if (!ctx) return;
+    if (!ctx->subs.empty()) {
+        // parent of a single-process multi-GPU context: its collections are thin handles over the subs' parts
+        for (auto &kv : ctx->colls) delete kv.second;
+        ctx->colls.clear();
+        for (vrod_ctx *sub : ctx->subs) vrod_ctx_destroy(sub);
+        ctx->subs.clear();
+        cudaSetDevice(ctx->device);
+        PinBuf *pin[] = {&ctx->q_host, &ctx->ids_host, &ctx->dist_host, &ctx->status_host};
+        for (PinBuf *b : pin) b->release();
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->colls) collection_free(kv.second);
@@ -364,6 +538,9 @@ extern "C" void vrod_ctx_destroy(vrod_ctx *ctx) {
     PinBuf *pin[] = {&ctx->q_host, &ctx->ids_host, &ctx->dist_host, &ctx->status_host};
     for (PinBuf *b : pin) b->release();
     cudaFree(ctx->dev_counters);
+    ctx->cost.release();
+    if (ctx->ev_status) cudaEventDestroy(ctx->ev_status);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -375,12 +552,34 @@ extern "C" vrod_status vrod_ctx_synchronize(vrod_ctx *ctx) {
 }
 static vrod_status vrod_ctx_synchronize_impl(vrod_ctx *ctx) {
     if (!ctx) return fail(VROD_EINVAL, "ctx is NULL");
+    if (!ctx->subs.empty()) {
+        for (vrod_ctx *sub : ctx->subs) {
+            vrod_status st = vrod_ctx_synchronize_impl(sub);
+            if (st != VROD_OK) return st;
+        }
+        VROD_CUDA(cudaSetDevice(ctx->device));
+        return VROD_OK;
+    }
+    VROD_CUDA(cudaSetDevice(ctx->device));
     VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->fused_exchange && !ctx->parent) {
+        // searches enqueued through the device-pointer API report a peer that never arrived only here
+        int err = 0;
+        VROD_CUDA(cudaMemcpy(&err, ctx->d_xchg_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err == 1) {
+            VROD_CUDA(cudaMemset(ctx->d_xchg_err, 0, sizeof(int)));
+            return fail(VROD_ENCCL, "peer exchange timed out: a rank did not take part in a search");
+        }
+    }
     return VROD_OK;
 }
-extern "C" void *vrod_ctx_stream(vrod_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" void *vrod_ctx_stream(vrod_ctx *ctx) {
+    if (!ctx) return nullptr;
+    return ctx->subs.empty() ? (void *)ctx->stream : (void *)ctx->subs[0]->stream;
+}
 extern "C" int vrod_ctx_rank(vrod_ctx *ctx) { return ctx ? ctx->rank : -1; }
 extern "C" int vrod_ctx_world(vrod_ctx *ctx) { return ctx ? ctx->world : -1; }
+extern "C" int vrod_ctx_devices(vrod_ctx *ctx) { return ctx ? (ctx->subs.empty() ? 1 : (int)ctx->subs.size()) : -1; }
 
 static vrod_status vrod_ctx_profile_impl(vrod_ctx *ctx, int enable);
 extern "C" vrod_status vrod_ctx_profile(vrod_ctx *ctx, int enable) {
@@ -389,6 +588,7 @@ extern "C" vrod_status vrod_ctx_profile(vrod_ctx *ctx, int enable) {
 static vrod_status vrod_ctx_profile_impl(vrod_ctx *ctx, int enable) {
     if (!ctx) return fail(VROD_EINVAL, "ctx is NULL");
     ctx->profiling = enable != 0;
+    for (vrod_ctx *sub : ctx->subs) sub->profiling = enable != 0;
     return VROD_OK;
 }
 
@@ -398,6 +598,24 @@ extern "C" vrod_status vrod_ctx_profile_read(vrod_ctx *ctx, double *kernel_ms, u
 }
 static vrod_status vrod_ctx_profile_read_impl(vrod_ctx *ctx, double *kernel_ms, uint64_t *launches) {
     if (!ctx) return fail(VROD_EINVAL, "ctx is NULL");
+    if (!ctx->subs.empty()) {   // the slowest device's kernels (the devices run side by side)
+        double worst = -1.0;
+        uint64_t n = 0;
+        for (vrod_ctx *sub : ctx->subs) {
+            double ms = 0.0;
+            uint64_t l = 0;
+            vrod_status st = vrod_ctx_profile_read_impl(sub, &ms, &l);
+            if (st != VROD_OK) return st;
+            if (ms > worst) {
+                worst = ms;
+                n = l;
+            }
+        }
+        if (kernel_ms) *kernel_ms = worst < 0.0 ? 0.0 : worst;
+        if (launches) *launches = n;
+        VROD_CUDA(cudaSetDevice(ctx->device));
+        return VROD_OK;
+    }
     VROD_CUDA(cudaSetDevice(ctx->device));
     VROD_CUDA(cudaStreamSynchronize(ctx->stream));
     double total = 0.0;
@@ -418,6 +636,21 @@ extern "C" vrod_status vrod_ctx_stats(vrod_ctx *ctx, vrod_stats *out) {
 }
 static vrod_status vrod_ctx_stats_impl(vrod_ctx *ctx, vrod_stats *out) {
     if (!ctx || !out) return fail(VROD_EINVAL, "NULL argument");
+    if (!ctx->subs.empty()) {   // searches / copies are counted by the parent, the kernels by the devices
+        vrod_stats sum = ctx->stats;
+        for (vrod_ctx *sub : ctx->subs) {
+            vrod_stats t{};
+            vrod_status st = vrod_ctx_stats_impl(sub, &t);
+            if (st != VROD_OK) return st;
+            sum.kernel_launches += t.kernel_launches;
+            if (t.fast_scans > sum.fast_scans) sum.fast_scans = t.fast_scans;   // every device scans every query: not a sum
+            sum.exact_rescans += t.exact_rescans;
+            sum.batched_tiles += t.batched_tiles;
+        }
+        *out = sum;
+        VROD_CUDA(cudaSetDevice(ctx->device));
+        return VROD_OK;
+    }
     VROD_CUDA(cudaSetDevice(ctx->device));
     unsigned long long dc[2] = {0, 0};
     VROD_CUDA(cudaMemcpyAsync(dc, ctx->dev_counters, sizeof(dc), cudaMemcpyDeviceToHost, ctx->stream));
@@ -430,6 +663,20 @@ static vrod_status vrod_ctx_stats_impl(vrod_ctx *ctx, vrod_stats *out) {
 // -------------------------------------------------------------------------------------------------
 // collections
 // -------------------------------------------------------------------------------------------------
+// Names end up as file names (Database::save: name + ".vrc") and as whitespace-delimited tokens of vr_config, so
+// the set is closed here, at the one place every collection is born.
+static bool valid_collection_name(const char *name) {
+    const size_t n = strlen(name);
+    if (n == 0 || n > 200 || strcmp(name, ".") == 0 || strcmp(name, "..") == 0) return false;
+    for (size_t i = 0; i < n; ++i) {
+        const char ch = name[i];
+        const bool ok = (ch >= 'A' && ch <= 'Z') || (ch >= 'a' && ch <= 'z') || (ch >= '0' && ch <= '9') || ch == '_' || ch == '.' || ch == '-';
+        if (!ok) return false;
+    }
+    return true;
+}
+
+static vrod_status vrod_collection_drop_impl(vrod_ctx *ctx, const char *name);
 static vrod_status vrod_collection_create_impl(vrod_ctx *ctx, const char *name, uint32_t dim, vrod_metric metric,
                                               uint64_t capacity_rows, vrod_collection **out);
 extern "C" vrod_status vrod_collection_create(vrod_ctx *ctx, const char *name, uint32_t dim, vrod_metric metric,
@@ -440,10 +687,39 @@ static vrod_status vrod_collection_create_impl(vrod_ctx *ctx, const char *name, 
                                               uint64_t capacity_rows, vrod_collection **out) {
     if (out) *out = nullptr;
     if (!ctx || !name || !*name) return fail(VROD_EINVAL, "ctx/name is NULL or empty");
+    if (!valid_collection_name(name))
+        return fail(VROD_EINVAL, "collection names are 1..200 characters of [A-Za-z0-9_.-] and neither '.' nor '..'");
     if (dim == 0 || dim > (1u << 20)) return fail(VROD_EINVAL, "dim must be in [1, 2^20]");
     if (metric != VROD_EUCLIDEAN && metric != VROD_COSINE) return fail(VROD_EINVAL, "unknown metric");
     if (capacity_rows == 0) return fail(VROD_EINVAL, "capacity_rows must be > 0");
     if (ctx->colls.count(name)) return fail(VROD_EEXISTS, std::string("collection '") + name + "' already exists");
+    if (!ctx->subs.empty()) {
+        // multi-GPU parent: a thin handle over one part per device (part r = shard r of the same capacity)
+        std::unique_ptr<vrod_collection> pc(new (std::nothrow) vrod_collection());
+        if (!pc) return fail(VROD_ENOMEM, "host allocation failed");
+        pc->ctx = ctx;
+        pc->name = name;
+        pc->dim = dim;
+        pc->ld = (dim + 3u) & ~3u;
+        pc->metric = metric;
+        pc->capacity = capacity_rows;
+        for (vrod_ctx *sub : ctx->subs) {
+            vrod_collection *part = nullptr;
+            vrod_status st = vrod_collection_create_impl(sub, name, dim, metric, capacity_rows, &part);
+            if (st != VROD_OK) {
+                const std::string msg = g_last_error;
+                for (vrod_ctx *s2 : ctx->subs)
+                    if (s2->colls.count(name)) vrod_collection_drop_impl(s2, name);
+                return fail(st, msg);
+            }
+            pc->parts.push_back(part);
+        }
+        VROD_CUDA(cudaSetDevice(ctx->device));
+        vrod_collection *raw = pc.release();
+        ctx->colls[name] = raw;
+        if (out) *out = raw;
+        return VROD_OK;
+    }
     VROD_CUDA(cudaSetDevice(ctx->device));
     std::unique_ptr<vrod_collection> c(new (std::nothrow) vrod_collection());
     if (!c) return fail(VROD_ENOMEM, "host allocation failed");
@@ -497,6 +773,15 @@ static vrod_status vrod_collection_drop_impl(vrod_ctx *ctx, const char *name) {
     if (!ctx || !name) return fail(VROD_EINVAL, "NULL argument");
     auto it = ctx->colls.find(name);
     if (it == ctx->colls.end()) return fail(VROD_ENOTFOUND, std::string("no collection '") + name + "'");
+    if (!ctx->subs.empty()) {
+        const std::string nm = name;   // `name` may point into the handle that is deleted here
+        for (vrod_ctx *sub : ctx->subs)
+            if (sub->colls.count(nm)) vrod_collection_drop_impl(sub, nm.c_str());
+        delete it->second;
+        ctx->colls.erase(it);
+        cudaSetDevice(ctx->device);
+        return VROD_OK;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     collection_free(it->second);
@@ -546,7 +831,7 @@ extern "C" vrod_status vrod_collection_shard(vrod_collection *c, uint64_t *id_ba
 }
 static vrod_status vrod_collection_shard_impl(vrod_collection *c, uint64_t *id_base, uint64_t *local_rows) {
     if (!c) return fail(VROD_EINVAL, "collection is NULL");
-    if (id_base) *id_base = c->id_base;
+    if (id_base) *id_base = c->id_base;    // a multi-GPU parent holds everything: base 0, all rows
     if (local_rows) *local_rows = c->local;
     return VROD_OK;
 }
@@ -558,6 +843,7 @@ extern "C" vrod_status vrod_collection_set_path(vrod_collection *c, int path) {
 static vrod_status vrod_collection_set_path_impl(vrod_collection *c, int path) {
     if (!c || path < 0 || path > 4) return fail(VROD_EINVAL, "bad path");
     c->path = path;
+    for (vrod_collection *part : c->parts) part->path = path;
     return VROD_OK;
 }
 
@@ -644,11 +930,18 @@ static vrod_status collection_grow(vrod_collection *c, uint64_t need) {
     return VROD_OK;
 }
 
-static vrod_status vrod_collection_insert_impl(vrod_collection *c, const float *rows, uint64_t n, uint64_t *first_id);
+// a multi-GPU parent handle mirrors the global counters of its parts (every part tracks them)
+static void sync_parent(vrod_collection *pc) {
+    pc->count = pc->parts[0]->count;
+    pc->capacity = pc->parts[0]->capacity;
+    pc->local = pc->count;
+}
+
+static vrod_status vrod_collection_insert_impl(vrod_collection *c, const float *rows, uint64_t n, uint64_t *first_id, bool validated = false);
 extern "C" vrod_status vrod_collection_insert(vrod_collection *c, const float *rows, uint64_t n, uint64_t *first_id) {
     return guarded([&]() -> vrod_status { return vrod_collection_insert_impl(c, rows, n, first_id); });
 }
-static vrod_status vrod_collection_insert_impl(vrod_collection *c, const float *rows, uint64_t n, uint64_t *first_id) {
+static vrod_status vrod_collection_insert_impl(vrod_collection *c, const float *rows, uint64_t n, uint64_t *first_id, bool validated) {
     if (!c) return fail(VROD_EINVAL, "collection is NULL");
     if (n == 0) {
         if (first_id) *first_id = c->count;
@@ -656,13 +949,25 @@ static vrod_status vrod_collection_insert_impl(vrod_collection *c, const float *
     }
     if (!rows) return fail(VROD_EINVAL, "rows is NULL");
     vrod_ctx *ctx = c->ctx;
+    if (!c->parts.empty()) {
+        // every device takes the rows of its own id range; accept or reject is decided once, here, for all of them
+        if (!host_rows_finite(rows, (size_t)n * c->dim)) return fail(VROD_EINVAL, "rows contain NaN or infinity");
+        if (c->count + n > c->capacity) return fail(VROD_ENOMEM, "collection capacity exceeded (sharded collections do not grow)");
+        for (vrod_collection *part : c->parts) {
+            vrod_status st = vrod_collection_insert_impl(part, rows, n, first_id, true);
+            if (st != VROD_OK) return st;
+        }
+        sync_parent(c);
+        VROD_CUDA(cudaSetDevice(ctx->device));
+        return VROD_OK;
+    }
     VROD_CUDA(cudaSetDevice(ctx->device));
     if (c->count + n > c->capacity) {
         if (ctx->world > 1) return fail(VROD_ENOMEM, "collection capacity exceeded (sharded collections do not grow)");
         vrod_status gs = collection_grow(c, c->count + n);
         if (gs != VROD_OK) return gs;
     }
-    if (ctx->world > 1 && !host_rows_finite(rows, (size_t)n * c->dim))
+    if (ctx->world > 1 && !validated && !host_rows_finite(rows, (size_t)n * c->dim))
         return fail(VROD_EINVAL, "rows contain NaN or infinity");   // decided identically on every rank (same rows)
     uint64_t loc0, cnt, off;
     shard_overlap(c, c->count, n, &loc0, &cnt, &off);
@@ -689,6 +994,15 @@ static vrod_status vrod_collection_fill_synthetic_impl(vrod_collection *c, uint6
     if (!c) return fail(VROD_EINVAL, "collection is NULL");
     if (c->count + n > c->capacity) return fail(VROD_ENOMEM, "collection capacity exceeded");
     vrod_ctx *ctx = c->ctx;
+    if (!c->parts.empty()) {
+        for (vrod_collection *part : c->parts) {
+            vrod_status st = vrod_collection_fill_synthetic_impl(part, n, seed);
+            if (st != VROD_OK) return st;
+        }
+        sync_parent(c);
+        VROD_CUDA(cudaSetDevice(ctx->device));
+        return VROD_OK;
+    }
     VROD_CUDA(cudaSetDevice(ctx->device));
     uint64_t loc0, cnt, off;
     shard_overlap(c, c->count, n, &loc0, &cnt, &off);
@@ -714,6 +1028,17 @@ static vrod_status vrod_collection_read_rows_impl(vrod_collection *c, uint64_t r
     if (row0 + n > c->local) return fail(VROD_EINVAL, "row range outside this rank's shard");
     if (n == 0) return VROD_OK;
     vrod_ctx *ctx = c->ctx;
+    if (!c->parts.empty()) {   // global row indices: every part returns its piece of the range
+        for (vrod_collection *part : c->parts) {
+            const uint64_t lo = part->id_base, hi = part->id_base + part->local;
+            const uint64_t a = row0 > lo ? row0 : lo, b = row0 + n < hi ? row0 + n : hi;
+            if (b <= a) continue;
+            vrod_status st = vrod_collection_read_rows_impl(part, a - lo, b - a, out + (size_t)(a - row0) * c->dim);
+            if (st != VROD_OK) return st;
+        }
+        VROD_CUDA(cudaSetDevice(ctx->device));
+        return VROD_OK;
+    }
     VROD_CUDA(cudaSetDevice(ctx->device));
     VROD_CUDA(cudaMemcpy2DAsync(out, (size_t)c->dim * sizeof(float), c->rows + (size_t)row0 * c->ld,
                                 (size_t)c->ld * sizeof(float), (size_t)c->dim * sizeof(float), (size_t)n,
@@ -829,37 +1154,46 @@ static ShardView shard_view(const vrod_collection *c) {
     return s;
 }
 
-// queries already on the device as [b x ld]; enqueue everything, no synchronisation
-// d_status: per-query guard flags (device).  host_checks: the caller reads d_status after synchronising and
-// rescans the flagged queries itself, so the conditional exact-scan launches are left out (single GPU only).
-static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t b, uint32_t k, uint64_t *d_ids,
-                                  float *d_dist, bool force_exact, int *d_status = nullptr, bool host_checks = false,
-                                  bool *used_scan = nullptr, int *d_xerr = nullptr) {
+// -------------------------------------------------------------------------------------------------
+// One search = local pass (this GPU's shard) [+ read-back of the batched pass's guard flags and rescans] [+ exchange].
+// The stages are separate functions so that the single-process multi-GPU context can run each stage over all its
+// devices before the next one (one host thread, nothing waits on a device that has not been given its work yet).
+// -------------------------------------------------------------------------------------------------
+struct LocalPass {
+    bool batched = false;     // the tensor-core pass ran: its guard flags must be read back (batched_fetch_status + batched_rescans)
+    bool used_scan = false;   // per-query f32 scans ran (host_checks: the caller rescans the flagged queries itself)
+};
+
+static ScanScratch scan_scratch(vrod_ctx *ctx, int *d_status) {
+    return ScanScratch{reinterpret_cast<unsigned long long *>(ctx->blk_cand.p), reinterpret_cast<unsigned int *>(ctx_ticket(ctx)),
+                       d_status, ctx->dev_counters};
+}
+
+// Stage 1.  Queries already on the device as [b x ld]; enqueue the local pass, no synchronisation.  On a single-GPU
+// context the kernels write d_ids / d_dist themselves; otherwise the local hits land in ctx->hits_local.
+// d_status: per-query guard flags (device).  host_checks: the caller reads d_status after synchronising and rescans the
+// flagged queries itself, so the conditional exact-scan launches are left out (single GPU only).
+static vrod_status local_enqueue(vrod_collection *c, const float *d_q, uint32_t b, uint32_t k, uint64_t *d_ids, float *d_dist,
+                                 bool force_exact, int *d_status, bool host_checks, LocalPass *lp) {
     vrod_ctx *ctx = c->ctx;
-    if (!d_status) d_status = ctx_status(ctx);
     if (ctx->world > 1) host_checks = false;
-    if (used_scan) *used_scan = false;
     const ShardView s = shard_view(c);
     const size_t nhits = (size_t)b * k;
     VROD_CUDA(ctx->hits_local.ensure(nhits * sizeof(Hit)));
     Hit *local = reinterpret_cast<Hit *>(ctx->hits_local.p);
-    ScanScratch scr{reinterpret_cast<unsigned long long *>(ctx->blk_cand.p),
-                    reinterpret_cast<unsigned int *>(ctx_ticket(ctx)), d_status, ctx->dev_counters};
+    const ScanScratch scr = scan_scratch(ctx, d_status);
     const bool exact_only = force_exact || c->path == 2 || !c->fast_ok;
     // single GPU: the scan kernels write the final arrays themselves, no merge launch
     const bool direct = ctx->world == 1;
     auto oid = [&](uint32_t qi) { return direct ? reinterpret_cast<unsigned long long *>(d_ids) + (size_t)qi * k : nullptr; };
     auto odd = [&](uint32_t qi) { return direct ? d_dist + (size_t)qi * k : nullptr; };
-    // automatic choice between b single-query scans and one batched (tensor-core) pass: a crude cost model from the
-    // round-1 measurements -- a scan costs ~25 us + its HBM bytes at 6.5 TB/s, a batched pass ~200 us of phase and
-    // launch overhead + 1.45 us per (128-row tile x 144 bf16 columns x query group of 256) spread over the SMs
-    // (configs[2]: 2111 tiles per SM in 3.2 ms)
+    // automatic choice between b single-query scans and one batched (tensor-core) pass: the context's cost model
+    // (CostModel: seeded from round-1 measurements, then corrected by the times this context measures)
     bool prefer_batched = false;
     if (b >= 2) {
-        const double bytes = (double)s.n * s.ld * 4.0;
-        const double t_scan = 25e-6 + bytes / 6.5e12;
+        const double t_scan = ctx->cost.scan_seconds((double)s.n * s.ld * 4.0);
         const double groups = (double)((b + 255) / 256);
-        const double t_batched = 200e-6 + groups * ((double)s.n / 128.0) * 1.45e-6 * ((double)mirror_ld(s.dim) / 144.0) / (double)ctx->sms;
+        const double t_batched = ctx->cost.batched_seconds(groups * ((double)s.n / 128.0) * ((double)mirror_ld(s.dim) / 144.0) / (double)ctx->sms);
         prefer_batched = (1.0 - c->rescan_share) * (double)b * t_scan > t_batched;
         if (!prefer_batched) c->rescan_share *= 0.995;   // forget slowly: the batched pass is probed again later
     }
@@ -890,34 +1224,22 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
             }
         }
         BatchedStats bs{};
-        cudaEvent_t e0 = ctx->profiling ? ctx->prof_event() : nullptr, e1 = ctx->profiling ? ctx->prof_event() : nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        bool sample = false;
+        if (ctx->profiling) {
+            e0 = ctx->prof_event();
+            e1 = ctx->prof_event();
+        } else if (ctx->cost.want_sample()) {
+            sample = ctx->cost.events(&e0, &e1);
+        }
         cudaError_t e = launch_batched_search(sb, d_q, b, k, ctx->sms, &ctx->batched.p, &ctx->batched.bytes, d_status,
                                               local, oid(0), odd(0), ctx->stream, &bs, e0, e1);
         if (e != cudaSuccess) return fail(VROD_ECUDA, std::string("batched search: ") + cudaGetErrorString(e));
+        if (sample)
+            ctx->cost.pending(2, (double)((b + 255) / 256) * ((double)s.n / 128.0) * ((double)mirror_ld(s.dim) / 144.0) / (double)ctx->sms);
         ctx->stats.kernel_launches += bs.launches;
         ctx->stats.batched_tiles += bs.tiles;
-        // queries whose guard failed are answered by the single-query scan.  The count is only known on
-        // the device, so this path synchronises once (the shard-local rescans involve no collective).
-        VROD_CUDA(ctx->status_host.ensure(sizeof(int) * b));
-        int *hs = reinterpret_cast<int *>(ctx->status_host.p);
-        VROD_CUDA(cudaMemcpyAsync(hs, d_status, sizeof(int) * b, cudaMemcpyDeviceToHost, ctx->stream));
-        VROD_CUDA(cudaStreamSynchronize(ctx->stream));
-        const ScanPlan fp = make_scan_plan(s, k, ctx->sms, false);
-        const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
-        uint32_t flagged = 0;
-        for (uint32_t qi = 0; qi < b; ++qi) flagged += hs[qi] ? 1u : 0u;
-        {   // rises at once, falls slowly
-            const double share = (double)flagged / (double)b, ema = 0.5 * c->rescan_share + 0.5 * share;
-            c->rescan_share = share > ema ? share : ema;
-        }
-        for (uint32_t qi = 0; qi < b; ++qi) {
-            if (!hs[qi]) continue;
-            const float *q = d_q + (size_t)qi * s.ld;
-            VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, d_status + qi, local + (size_t)qi * k, oid(qi), odd(qi), ctx->stream));
-            VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, d_status + qi, local + (size_t)qi * k, oid(qi), odd(qi), ctx->stream));
-            ctx->stats.kernel_launches += 2;
-            ctx->stats.fast_scans++;
-        }
+        lp->batched = true;
     } else if (exact_only) {
         const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
         for (uint32_t qi = 0; qi < b; ++qi) {
@@ -925,20 +1247,27 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
                                         ctx->stream));
             ctx->stats.kernel_launches++;
         }
-        ctx->stats.exact_rescans += 0;
     } else {
         const ScanPlan fp = make_scan_plan(s, k, ctx->sms, false);
         const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
         for (uint32_t qi = 0; qi < b; ++qi) {
             const float *q = d_q + (size_t)qi * s.ld;
-            static const bool scan_dbg = getenv("VROD_SCAN_DEBUG") != nullptr;
+            static const bool scan_dbg = kDbg && getenv("VROD_SCAN_DEBUG") != nullptr;
             unsigned long long *dbgbuf = nullptr;
             if (scan_dbg) {
                 dbgbuf = scan_debug_enable();
                 const unsigned long long init[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};
                 cudaMemcpyAsync(dbgbuf, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream);
             }
-            if (ctx->profiling) VROD_CUDA(cudaEventRecord(ctx->prof_event(), ctx->stream));
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            bool sample = false;
+            if (ctx->profiling) {
+                e0 = ctx->prof_event();
+                e1 = ctx->prof_event();
+            } else if (qi == 0 && ctx->cost.want_sample()) {
+                sample = ctx->cost.events(&e0, &e1);
+            }
+            if (e0) VROD_CUDA(cudaEventRecord(e0, ctx->stream));
             VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, d_status + qi, local + (size_t)qi * k, oid(qi), odd(qi),
                                        ctx->stream));
             if (scan_dbg) {
@@ -949,7 +1278,8 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
                         (h[1] - h[0]) / 1e3, (h[2] - h[1]) / 1e3, (h[3] - h[2]) / 1e3, (h[4] - h[3]) / 1e3, (h[5] - h[4]) / 1e3,
                         (h[5] - h[0]) / 1e3);
             }
-            if (ctx->profiling) VROD_CUDA(cudaEventRecord(ctx->prof_event(), ctx->stream));
+            if (e1) VROD_CUDA(cudaEventRecord(e1, ctx->stream));
+            if (sample) ctx->cost.pending(1, (double)s.n * s.ld * 4.0);
             if (!host_checks) {
                 VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, d_status + qi, local + (size_t)qi * k, oid(qi), odd(qi),
                                             ctx->stream));
@@ -958,29 +1288,99 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
             ctx->stats.kernel_launches++;
         }
         ctx->stats.fast_scans += b;
-        if (used_scan) *used_scan = true;
+        lp->used_scan = true;
     }
-    const Hit *lists = local;
-    uint32_t g = 1;
-    if (ctx->world > 1 && ctx->fused_exchange && b <= kXchgMaxB && nhits <= kXchgMaxHits) {
+    return VROD_OK;
+}
+
+// Stage 2a (after a batched local pass).  The number of queries whose guard failed is only known on the device:
+// copy the flags to pinned memory and mark the point in the stream.
+static vrod_status batched_fetch_status(vrod_collection *c, uint32_t b, const int *d_status) {
+    vrod_ctx *ctx = c->ctx;
+    VROD_CUDA(ctx->status_host.ensure(sizeof(int) * b));
+    if (!ctx->ev_status) VROD_CUDA(cudaEventCreateWithFlags(&ctx->ev_status, cudaEventDisableTiming));
+    VROD_CUDA(cudaMemcpyAsync(ctx->status_host.p, d_status, sizeof(int) * b, cudaMemcpyDeviceToHost, ctx->stream));
+    VROD_CUDA(cudaEventRecord(ctx->ev_status, ctx->stream));
+    return VROD_OK;
+}
+
+// Stage 2b.  Wait for the flags (the one synchronisation of the batched path; the rescans are shard-local, no
+// collective is involved) and answer the flagged queries with the single-query scan.
+static vrod_status batched_rescans(vrod_collection *c, const float *d_q, uint32_t b, uint32_t k, uint64_t *d_ids, float *d_dist,
+                                   int *d_status) {
+    vrod_ctx *ctx = c->ctx;
+    VROD_CUDA(cudaEventSynchronize(ctx->ev_status));
+    const int *hs = reinterpret_cast<const int *>(ctx->status_host.p);
+    const ShardView s = shard_view(c);
+    const bool direct = ctx->world == 1;
+    Hit *local = reinterpret_cast<Hit *>(ctx->hits_local.p);
+    const ScanScratch scr = scan_scratch(ctx, d_status);
+    uint32_t flagged = 0;
+    for (uint32_t qi = 0; qi < b; ++qi) flagged += hs[qi] ? 1u : 0u;
+    {   // rises at once, falls slowly
+        const double share = (double)flagged / (double)b, ema = 0.5 * c->rescan_share + 0.5 * share;
+        c->rescan_share = share > ema ? share : ema;
+    }
+    if (!flagged) return VROD_OK;
+    const ScanPlan fp = make_scan_plan(s, k, ctx->sms, false);
+    const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
+    for (uint32_t qi = 0; qi < b; ++qi) {
+        if (!hs[qi]) continue;
+        const float *q = d_q + (size_t)qi * s.ld;
+        unsigned long long *oi = direct ? reinterpret_cast<unsigned long long *>(d_ids) + (size_t)qi * k : nullptr;
+        float *od = direct ? d_dist + (size_t)qi * k : nullptr;
+        VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, d_status + qi, local + (size_t)qi * k, oi, od, ctx->stream));
+        VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, d_status + qi, local + (size_t)qi * k, oi, od, ctx->stream));
+        ctx->stats.kernel_launches += 2;
+        ctx->stats.fast_scans++;
+    }
+    return VROD_OK;
+}
+
+// Stage 3 (one process per GPU).  Every rank ends up with the global answer in d_ids / d_dist.
+static vrod_status exchange_enqueue(vrod_collection *c, uint32_t b, uint32_t k, uint64_t *d_ids, float *d_dist, int *d_xerr,
+                                    bool *used_fused) {
+    vrod_ctx *ctx = c->ctx;
+    const size_t nhits = (size_t)b * k;
+    Hit *local = reinterpret_cast<Hit *>(ctx->hits_local.p);
+    if (used_fused) *used_fused = false;
+    if (ctx->world == 1) return VROD_OK;   // the kernels of the local pass wrote the final arrays
+    if (ctx->fused_exchange && b <= kXchgMaxB && nhits <= kXchgMaxHits) {
         // one kernel: push the local lists into every rank's window over NVLink, wait for the peers', merge
         VROD_CUDA(launch_exchange_merge(ctx->d_windows, (uint32_t)ctx->rank, (uint32_t)ctx->world, ++ctx->xchg_seq, local, b, k,
                                         reinterpret_cast<unsigned long long *>(d_ids), d_dist, d_xerr ? d_xerr : ctx->d_xchg_err,
-                                        ctx->stream));
+                                        kXchgAllRanks, ctx->stream));
         ctx->stats.kernel_launches++;
-        ctx->stats.searches += b;
+        if (used_fused) *used_fused = true;
         return VROD_OK;
     }
-    if (ctx->world > 1) {
-        VROD_CUDA(ctx->hits_all.ensure(nhits * sizeof(Hit) * ctx->world));
-        VROD_NCCL(g_nccl.AllGather(local, ctx->hits_all.p, nhits * sizeof(Hit), ncclChar, ctx->comm, ctx->stream));
-        lists = reinterpret_cast<const Hit *>(ctx->hits_all.p);
-        g = (uint32_t)ctx->world;
+    if (!ctx->comm) return fail(VROD_ENCCL, "no communicator on this context");
+    VROD_CUDA(ctx->hits_all.ensure(nhits * sizeof(Hit) * ctx->world));
+    VROD_NCCL(g_nccl.AllGather(local, ctx->hits_all.p, nhits * sizeof(Hit), ncclChar, ctx->comm, ctx->stream));
+    VROD_CUDA(launch_merge_hits(reinterpret_cast<const Hit *>(ctx->hits_all.p), (uint32_t)ctx->world, b, k,
+                                reinterpret_cast<unsigned long long *>(d_ids), d_dist, ctx->stream));
+    ctx->stats.kernel_launches++;
+    return VROD_OK;
+}
+
+// All stages on one (single-GPU or per-rank) context.
+static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t b, uint32_t k, uint64_t *d_ids,
+                                  float *d_dist, bool force_exact, int *d_status = nullptr, bool host_checks = false,
+                                  bool *used_scan = nullptr, int *d_xerr = nullptr, bool *used_fused = nullptr) {
+    vrod_ctx *ctx = c->ctx;
+    if (!d_status) d_status = ctx_status(ctx);
+    ctx->cost.collect();
+    LocalPass lp;
+    vrod_status st = local_enqueue(c, d_q, b, k, d_ids, d_dist, force_exact, d_status, host_checks, &lp);
+    if (st != VROD_OK) return st;
+    if (lp.batched) {
+        st = batched_fetch_status(c, b, d_status);
+        if (st == VROD_OK) st = batched_rescans(c, d_q, b, k, d_ids, d_dist, d_status);
+        if (st != VROD_OK) return st;
     }
-    if (!direct) {
-        VROD_CUDA(launch_merge_hits(lists, g, b, k, reinterpret_cast<unsigned long long *>(d_ids), d_dist, ctx->stream));
-        ctx->stats.kernel_launches++;
-    }
+    if (used_scan) *used_scan = lp.used_scan;
+    st = exchange_enqueue(c, b, k, d_ids, d_dist, d_xerr, used_fused);
+    if (st != VROD_OK) return st;
     ctx->stats.searches += b;
     return VROD_OK;
 }
@@ -1006,6 +1406,8 @@ static vrod_status vrod_collection_search_device_impl(vrod_collection *c, const 
     vrod_status st = check_search_args(c, d_queries, b, k, d_out_ids, d_out_dist);
     if (st != VROD_OK || b == 0) return st;
     vrod_ctx *ctx = c->ctx;
+    if (!c->parts.empty())
+        return fail(VROD_EINVAL, "the device-pointer search needs a single-device context (a multi-GPU context answers host buffers)");
     VROD_CUDA(cudaSetDevice(ctx->device));
     const float *q = d_queries;
     if (c->ld != c->dim) {
@@ -1017,27 +1419,12 @@ static vrod_status vrod_collection_search_device_impl(vrod_collection *c, const 
     return search_enqueue(c, q, b, k, d_out_ids, d_out_dist, false);
 }
 
-static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *queries, uint32_t b, uint32_t k,
-                                              uint64_t *out_ids, float *out_dist);
-extern "C" vrod_status vrod_collection_search(vrod_collection *c, const float *queries, uint32_t b, uint32_t k,
-                                              uint64_t *out_ids, float *out_dist) {
-    return guarded([&]() -> vrod_status { return vrod_collection_search_impl(c, queries, b, k, out_ids, out_dist); });
-}
-static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *queries, uint32_t b, uint32_t k,
-                                              uint64_t *out_ids, float *out_dist) {
-    vrod_status st = check_search_args(c, queries, b, k, out_ids, out_dist);
-    if (st != VROD_OK || b == 0) return st;
-    vrod_ctx *ctx = c->ctx;
-    VROD_CUDA(cudaSetDevice(ctx->device));
-    // validate + pack (zero padded to ld) into pinned staging
-    const size_t qbytes = (size_t)b * c->ld * sizeof(float);
-    VROD_CUDA(ctx->q_host.ensure(qbytes));
-    float *qh = reinterpret_cast<float *>(ctx->q_host.p);
-    // queries outside the range the f32 / tensor-core passes' error bounds cover are answered by the exact f64 scan:
-    // each on its own on a single GPU (the rest of the batch keeps its fast path), the whole call on sharded contexts
-    // (every rank must enqueue the same collectives)
-    std::vector<unsigned char> unsafe_q(b, 0);
-    uint32_t n_unsafe = 0;
+// validate + pack (zero padded to ld) into pinned staging.  Queries outside the range the f32 / tensor-core passes'
+// error bounds cover are marked in unsafe_q: they are answered by the exact f64 scan.
+static vrod_status pack_queries(const vrod_collection *c, const float *queries, uint32_t b, float *qh,
+                                std::vector<unsigned char> &unsafe_q, uint32_t *n_unsafe) {
+    unsafe_q.assign(b, 0);
+    *n_unsafe = 0;
     for (uint32_t i = 0; i < b; ++i) {
         const float *src = queries + (size_t)i * c->dim;
         float *dst = qh + (size_t)i * c->ld;
@@ -1054,35 +1441,160 @@ static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *
         if (nq > 0.0 && (nq < 0x1p-80 || nq > 0x1p100)) u = true;
         if (c->metric == VROD_COSINE && nq == 0.0) u = true;  // all distances are 1: answered by the exact scan
         unsafe_q[i] = u ? 1 : 0;
-        n_unsafe += u ? 1 : 0;
+        *n_unsafe += u ? 1 : 0;
     }
+    return VROD_OK;
+}
+
+// layout of the packed result buffer [ids | dist | status (+1: peer-exchange error flag)]: results and guard flags
+// come back in ONE device-to-host copy
+struct PackLayout {
+    size_t nres, off_dist, off_stat, bytes;
+    PackLayout(uint32_t b, uint32_t k) {
+        nres = (size_t)b * k;
+        off_dist = nres * sizeof(uint64_t);
+        off_stat = off_dist + ((nres * sizeof(float) + 15) & ~(size_t)15);
+        bytes = off_stat + ((size_t)b + 1) * sizeof(int);
+    }
+};
+
+// SEARCH on a single-process multi-GPU context: every stage runs over all devices before the next one starts, from
+// the caller's one thread.  Device 0 receives the per-device top-k lists (fused NVLink push + merge kernel, or peer
+// copies + merge for large batches) and is the only device the host reads.
+static vrod_status multi_search(vrod_collection *pc, const float *queries, uint32_t b, uint32_t k, uint64_t *out_ids, float *out_dist) {
+    vrod_ctx *P = pc->ctx;
+    const int W = (int)P->subs.size();
+    vrod_ctx *s0 = P->subs[0];
+    const size_t qbytes = (size_t)b * pc->ld * sizeof(float);
+    VROD_CUDA(cudaSetDevice(s0->device));
+    VROD_CUDA(P->q_host.ensure(qbytes));
+    float *qh = reinterpret_cast<float *>(P->q_host.p);
+    std::vector<unsigned char> unsafe_q;
+    uint32_t n_unsafe = 0;
+    vrod_status st = pack_queries(pc, queries, b, qh, unsafe_q, &n_unsafe);
+    if (st != VROD_OK) return st;
+    const bool unsafe = n_unsafe != 0;   // the whole call goes the exact way
+    const PackLayout L(b, k);
+    VROD_CUDA(P->ids_host.ensure(L.bytes));
+    unsigned char *hpack = reinterpret_cast<unsigned char *>(P->ids_host.p);
+    const bool fused = s0->fused_exchange && b <= kXchgMaxB && L.nres <= kXchgMaxHits;
+    std::vector<LocalPass> lp(W);
+    auto ids_of = [&](vrod_ctx *sub) { return reinterpret_cast<uint64_t *>(sub->out_ids.p); };
+    auto dist_of = [&](vrod_ctx *sub) { return reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(sub->out_ids.p) + L.off_dist); };
+    auto stat_of = [&](vrod_ctx *sub) { return reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(sub->out_ids.p) + L.off_stat); };
+    // stage 1: queries in, local pass on every device
+    for (int r = 0; r < W; ++r) {
+        vrod_ctx *sub = P->subs[r];
+        VROD_CUDA(cudaSetDevice(sub->device));
+        sub->cost.collect();
+        VROD_CUDA(sub->q_dev.ensure(qbytes));
+        VROD_CUDA(sub->out_ids.ensure(L.bytes));
+        VROD_CUDA(cudaMemcpyAsync(sub->q_dev.p, qh, qbytes, cudaMemcpyHostToDevice, sub->stream));
+        st = local_enqueue(pc->parts[r], reinterpret_cast<const float *>(sub->q_dev.p), b, k, ids_of(sub), dist_of(sub), unsafe,
+                           stat_of(sub), false, &lp[r]);
+        if (st != VROD_OK) return st;
+        if (lp[r].batched) {
+            st = batched_fetch_status(pc->parts[r], b, stat_of(sub));
+            if (st != VROD_OK) return st;
+        }
+    }
+    // stage 2: the batched passes' guard flags, one device after the other (the others keep computing)
+    for (int r = 0; r < W; ++r) {
+        if (!lp[r].batched) continue;
+        vrod_ctx *sub = P->subs[r];
+        VROD_CUDA(cudaSetDevice(sub->device));
+        st = batched_rescans(pc->parts[r], reinterpret_cast<const float *>(sub->q_dev.p), b, k, ids_of(sub), dist_of(sub), stat_of(sub));
+        if (st != VROD_OK) return st;
+    }
+    // stage 3: the lists meet on device 0
+    if (fused) {
+        const uint32_t seq = ++P->xchg_seq;
+        for (int r = 0; r < W; ++r) {
+            vrod_ctx *sub = P->subs[r];
+            VROD_CUDA(cudaSetDevice(sub->device));
+            VROD_CUDA(launch_exchange_merge(sub->d_windows, (uint32_t)r, (uint32_t)W, seq, reinterpret_cast<const Hit *>(sub->hits_local.p), b, k,
+                                            reinterpret_cast<unsigned long long *>(ids_of(sub)), dist_of(sub), stat_of(sub) + b, 0u, sub->stream));
+            sub->stats.kernel_launches++;
+        }
+    } else {
+        VROD_CUDA(cudaSetDevice(s0->device));
+        VROD_CUDA(s0->hits_all.ensure(L.nres * sizeof(Hit) * W));
+        Hit *all = reinterpret_cast<Hit *>(s0->hits_all.p);
+        for (int r = 0; r < W; ++r) {
+            vrod_ctx *sub = P->subs[r];
+            VROD_CUDA(cudaSetDevice(sub->device));
+            if (r == 0) {
+                VROD_CUDA(cudaMemcpyAsync(all, sub->hits_local.p, L.nres * sizeof(Hit), cudaMemcpyDeviceToDevice, sub->stream));
+            } else {
+                VROD_CUDA(cudaMemcpyPeerAsync(all + (size_t)r * L.nres, s0->device, sub->hits_local.p, sub->device, L.nres * sizeof(Hit), sub->stream));
+                VROD_CUDA(cudaEventRecord(sub->ev_done, sub->stream));
+            }
+        }
+        VROD_CUDA(cudaSetDevice(s0->device));
+        for (int r = 1; r < W; ++r) VROD_CUDA(cudaStreamWaitEvent(s0->stream, P->subs[r]->ev_done, 0));
+        VROD_CUDA(launch_merge_hits(all, (uint32_t)W, b, k, reinterpret_cast<unsigned long long *>(ids_of(s0)), dist_of(s0), s0->stream));
+        s0->stats.kernel_launches++;
+    }
+    // stage 4: one copy back from device 0
+    VROD_CUDA(cudaSetDevice(s0->device));
+    VROD_CUDA(cudaMemcpyAsync(hpack, s0->out_ids.p, L.bytes, cudaMemcpyDeviceToHost, s0->stream));
+    VROD_CUDA(cudaStreamSynchronize(s0->stream));
+    if (fused && reinterpret_cast<const int *>(hpack + L.off_stat)[b] == 1)
+        return fail(VROD_ENCCL, "peer exchange timed out: a device did not deliver its lists");
+    memcpy(out_ids, hpack, L.nres * sizeof(uint64_t));
+    memcpy(out_dist, hpack + L.off_dist, L.nres * sizeof(float));
+    P->stats.searches += b;
+    P->stats.h2d_bytes += qbytes * W;
+    P->stats.d2h_bytes += L.bytes;
+    return VROD_OK;
+}
+
+static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *queries, uint32_t b, uint32_t k,
+                                              uint64_t *out_ids, float *out_dist);
+extern "C" vrod_status vrod_collection_search(vrod_collection *c, const float *queries, uint32_t b, uint32_t k,
+                                              uint64_t *out_ids, float *out_dist) {
+    return guarded([&]() -> vrod_status { return vrod_collection_search_impl(c, queries, b, k, out_ids, out_dist); });
+}
+static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *queries, uint32_t b, uint32_t k,
+                                              uint64_t *out_ids, float *out_dist) {
+    vrod_status st = check_search_args(c, queries, b, k, out_ids, out_dist);
+    if (st != VROD_OK || b == 0) return st;
+    vrod_ctx *ctx = c->ctx;
+    if (!c->parts.empty()) return multi_search(c, queries, b, k, out_ids, out_dist);
+    VROD_CUDA(cudaSetDevice(ctx->device));
+    const size_t qbytes = (size_t)b * c->ld * sizeof(float);
+    VROD_CUDA(ctx->q_host.ensure(qbytes));
+    float *qh = reinterpret_cast<float *>(ctx->q_host.p);
+    // out-of-range queries: each on its own on a single GPU (the rest of the batch keeps its fast path), the whole
+    // call on sharded contexts (every rank must enqueue the same collectives)
+    std::vector<unsigned char> unsafe_q;
+    uint32_t n_unsafe = 0;
+    st = pack_queries(c, queries, b, qh, unsafe_q, &n_unsafe);
+    if (st != VROD_OK) return st;
     const bool unsafe = n_unsafe != 0 && (ctx->world > 1 || n_unsafe == b);   // the whole call goes the exact way
-    // one device buffer [ids | dist | status] so that the results and the guard flags come back in ONE copy
-    const size_t nres = (size_t)b * k;
-    const size_t off_dist = nres * sizeof(uint64_t);
-    const size_t off_stat = off_dist + ((nres * sizeof(float) + 15) & ~(size_t)15);
-    const size_t pack = off_stat + ((size_t)b + 1) * sizeof(int);   // + 1: peer-exchange error flag (sharded contexts)
+    const PackLayout L(b, k);
     VROD_CUDA(ctx->q_dev.ensure(qbytes));
-    VROD_CUDA(ctx->out_ids.ensure(pack));
-    VROD_CUDA(ctx->ids_host.ensure(pack));
+    VROD_CUDA(ctx->out_ids.ensure(L.bytes));
+    VROD_CUDA(ctx->ids_host.ensure(L.bytes));
     unsigned char *dpack = reinterpret_cast<unsigned char *>(ctx->out_ids.p);
     unsigned char *hpack = reinterpret_cast<unsigned char *>(ctx->ids_host.p);
     uint64_t *d_ids = reinterpret_cast<uint64_t *>(dpack);
-    float *d_dist = reinterpret_cast<float *>(dpack + off_dist);
-    int *d_stat = reinterpret_cast<int *>(dpack + off_stat);
+    float *d_dist = reinterpret_cast<float *>(dpack + L.off_dist);
+    int *d_stat = reinterpret_cast<int *>(dpack + L.off_stat);
     VROD_CUDA(cudaMemcpyAsync(ctx->q_dev.p, qh, qbytes, cudaMemcpyHostToDevice, ctx->stream));
-    bool used_scan = false;
+    bool used_scan = false, used_fused = false;
     st = search_enqueue(c, reinterpret_cast<const float *>(ctx->q_dev.p), b, k, d_ids, d_dist, unsafe, d_stat, true, &used_scan,
-                        d_stat + b);
+                        d_stat + b, &used_fused);
     if (st != VROD_OK) return st;
-    VROD_CUDA(cudaMemcpyAsync(hpack, dpack, pack, cudaMemcpyDeviceToHost, ctx->stream));
+    VROD_CUDA(cudaMemcpyAsync(hpack, dpack, L.bytes, cudaMemcpyDeviceToHost, ctx->stream));
     VROD_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->fused_exchange && reinterpret_cast<const int *>(hpack + off_stat)[b] == 1)
+    // (the flag word is written only by the fused exchange kernel: the all-gather path leaves stale bytes there)
+    if (used_fused && reinterpret_cast<const int *>(hpack + L.off_stat)[b] == 1)
         return fail(VROD_ENCCL, "peer exchange timed out: a rank did not take part in this search");
     if (ctx->world == 1 && !unsafe && (used_scan || n_unsafe)) {
         // the scans ran without their device-side conditional rescans: answer the flagged queries exactly now,
         // and with them the queries that were out of range for the fast paths
-        int *hs = reinterpret_cast<int *>(hpack + off_stat);
+        int *hs = reinterpret_cast<int *>(hpack + L.off_stat);
         bool any = false;
         for (uint32_t qi = 0; qi < b; ++qi) {
             hs[qi] = (used_scan && hs[qi] != 0) || unsafe_q[qi] ? 1 : 0;
@@ -1091,8 +1603,7 @@ static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *
         if (any) {
             const ShardView s = shard_view(c);
             const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
-            ScanScratch scr{reinterpret_cast<unsigned long long *>(ctx->blk_cand.p),
-                            reinterpret_cast<unsigned int *>(ctx_ticket(ctx)), d_stat, ctx->dev_counters};
+            const ScanScratch scr = scan_scratch(ctx, d_stat);
             Hit *local = reinterpret_cast<Hit *>(ctx->hits_local.p);
             for (uint32_t qi = 0; qi < b; ++qi) {
                 if (!hs[qi]) continue;
@@ -1101,16 +1612,16 @@ static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *
                                             d_dist + (size_t)qi * k, ctx->stream));
                 ctx->stats.kernel_launches++;
             }
-            VROD_CUDA(cudaMemcpyAsync(hpack, dpack, off_stat, cudaMemcpyDeviceToHost, ctx->stream));
+            VROD_CUDA(cudaMemcpyAsync(hpack, dpack, L.off_stat, cudaMemcpyDeviceToHost, ctx->stream));
             VROD_CUDA(cudaStreamSynchronize(ctx->stream));
         }
     }
-    memcpy(out_ids, hpack, nres * sizeof(uint64_t));
-    memcpy(out_dist, hpack + off_dist, nres * sizeof(float));
+    memcpy(out_ids, hpack, L.nres * sizeof(uint64_t));
+    memcpy(out_dist, hpack + L.off_dist, L.nres * sizeof(float));
     ctx->stats.h2d_bytes += qbytes;
-    ctx->stats.d2h_bytes += pack;
+    ctx->stats.d2h_bytes += L.bytes;
     return VROD_OK;
 }
 
 extern "C" const char *vrod_last_error(void) { return g_last_error.c_str(); }
-extern "C" const char *vrod_version(void) { return "vrod_knn_b200 0.1.0 (sm_100a)"; }
+extern "C" const char *vrod_version(void) { return "vrod_knn_b200 0.2.0 (sm_100a)"; }

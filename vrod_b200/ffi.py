@@ -21,7 +21,8 @@ PATH_AUTO, PATH_SCAN, PATH_EXACT, PATH_BATCHED = 0, 1, 2, 3
 
 # every symbol include/vrod_knn.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
-    "vrod_ctx_create", "vrod_comm_unique_id", "vrod_ctx_create_sharded", "vrod_ctx_destroy",
+    "vrod_ctx_create", "vrod_comm_unique_id", "vrod_ctx_create_sharded", "vrod_ctx_create_multi", "vrod_ctx_devices",
+    "vrod_ctx_destroy",
     "vrod_ctx_synchronize", "vrod_ctx_stream", "vrod_ctx_stats", "vrod_ctx_profile", "vrod_ctx_profile_read",
     "vrod_ctx_rank", "vrod_ctx_world",
     "vrod_collection_create", "vrod_collection_get", "vrod_collection_drop", "vrod_collection_list",
@@ -60,6 +61,8 @@ def lib():
         L.vrod_ctx_create.argtypes = [i32, C.POINTER(vp)]
         L.vrod_comm_unique_id.argtypes = [vp]
         L.vrod_ctx_create_sharded.argtypes = [i32, i32, i32, vp, C.POINTER(vp)]
+        L.vrod_ctx_create_multi.argtypes = [C.POINTER(i32), i32, C.POINTER(vp)]
+        L.vrod_ctx_devices.argtypes = [vp]
         L.vrod_ctx_destroy.argtypes = [vp]
         L.vrod_ctx_destroy.restype = None
         L.vrod_ctx_synchronize.argtypes = [vp]
@@ -160,9 +163,14 @@ class Collection:
 
 
 class Context:
+    """device: a CUDA ordinal, or a list of ordinals for ONE process driving several GPUs (vrod_ctx_create_multi)."""
+
     def __init__(self, device=0, rank=0, world=1, comm_id=None):
         self.h = C.c_void_p()
-        if world > 1:
+        if isinstance(device, (list, tuple)):
+            arr = (C.c_int * len(device))(*device)
+            _check(lib().vrod_ctx_create_multi(arr, len(device), C.byref(self.h)))
+        elif world > 1:
             cid = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(comm_id)
             _check(lib().vrod_ctx_create_sharded(device, rank, world, cid, C.byref(self.h)))
         else:
@@ -186,6 +194,10 @@ class Context:
     @property
     def world(self):
         return lib().vrod_ctx_world(self.h)
+
+    @property
+    def devices(self):
+        return lib().vrod_ctx_devices(self.h)
 
     def stream(self):
         return lib().vrod_ctx_stream(self.h)

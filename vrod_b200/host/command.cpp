@@ -80,6 +80,12 @@ void CreateCollectionCommand::execute() const {
     if (!collection_name || collection_name->empty()) return set_error(db, "CREATE needs a collection name in the argument");
     const std::vector<std::string> f = split(*collection_name, ';');
     const std::string &name = f[0];
+    {   // the library's rule (vrod_collection_create), applied here too because a CREATE without a dimension only
+        // materialises at the first INSERT: names become file names and vr_config tokens
+        bool ok = !name.empty() && name.size() <= 200 && name != "." && name != "..";
+        for (const char ch : name) ok = ok && (std::isalnum((unsigned char)ch) || ch == '_' || ch == '.' || ch == '-');
+        if (!ok) return set_error(db, "bad collection name '" + name + "': use 1..200 characters of [A-Za-z0-9_.-]");
+    }
     CollectionSpec spec;
     if (f.size() > 1 && !f[1].empty()) {
         const long d = std::strtol(f[1].c_str(), nullptr, 10);

@@ -39,14 +39,18 @@ class Database {
     // Database::new(path, name) (mod.rs:13-17): creates path/name with empty vr_config and vr_wal,
     // io error AlreadyExists if the directory exists (src/database/setup.rs:3-26).
     static Database create(const std::filesystem::path &path, const std::string &name);
-    // An in-memory database on one GPU.
-    explicit Database(int device = 0) : device_(device) {}
+    // An in-memory database on one GPU, or row-sharded over several GPUs driven by this one process
+    // (vrod_ctx_create_multi: the reference's caller is a single-threaded process, src/main.rs:42).
+    explicit Database(int device = 0) : devices_{device} {}
+    explicit Database(std::vector<int> devices) : devices_(std::move(devices)) {}
     // Database::load(path) (mod.rs:19-21, todo!() upstream): opens a directory made by create() and loads
     // every collection listed in its vr_config into GPU memory.  Throws std::runtime_error on a directory
     // without vr_config or a damaged collection file.
-    static Database load(const std::filesystem::path &dir, int device = 0);
+    static Database load(const std::filesystem::path &dir, std::vector<int> devices = {0});
     // Writes vr_config, one <name>.vrc rows file (vrod_collection_save) and one <name>.payloads text file per
-    // collection into `path`.  vr_wal is left untouched: there is no write-ahead log in this build.
+    // collection into `path`: everything goes to <file>.tmp first, is flushed to disk, and is renamed into place
+    // only after every collection has been written, so a failure midway (full disk) leaves the previous state.
+    // vr_wal is left untouched: there is no write-ahead log in this build.
     void save();
     bool dirty = false;   // set by the commands that change collections
     ~Database();
@@ -61,7 +65,7 @@ class Database {
     std::filesystem::path path;
 
   private:
-    int device_ = 0;
+    std::vector<int> devices_{0};
     vrod_ctx *ctx_ = nullptr;
 };
 

@@ -9,6 +9,8 @@
 //   --script FILE|-   one command per line: COMMAND <collection|-> [ARG...rest of line]
 //   --describe        build the command and print its type and fields instead of executing it
 //   --device N        CUDA ordinal (default 0)
+//   --devices A,B,..  several GPUs driven by this one process: every collection is row-sharded over them
+//                     (vrod_ctx_create_multi), a SEARCH scans all shards at once
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -21,7 +23,7 @@ using namespace vrod;
 
 static int usage() {
     std::fputs("Usage: vrod [-i PATH -n NAME] [-d DIR] [-c COLLECTION_NAME] [-e COMMAND] [-a COMMAND_ARG]\n"
-               "            [--script FILE|-] [--describe] [--device N]\n", stderr);
+               "            [--script FILE|-] [--describe] [--device N | --devices A,B,...]\n", stderr);
     return 2;
 }
 
@@ -29,7 +31,7 @@ int main(int argc, char **argv) {
     if (argc == 1) return usage();   // #[command(arg_required_else_help(true))], main.rs:11
     OptStr init_db, init_name, database, collection, execute, command_arg, script;
     bool describe = false;
-    int device = 0;
+    std::vector<int> devices{0};
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto val = [&](OptStr &dst) {
@@ -44,7 +46,22 @@ int main(int argc, char **argv) {
         else if (a == "-a" || a == "--command-arg") val(command_arg);
         else if (a == "--script") val(script);
         else if (a == "--describe") describe = true;
-        else if (a == "--device") { OptStr d; val(d); device = std::atoi(d->c_str()); }
+        else if (a == "--device") { OptStr d; val(d); devices = {std::atoi(d->c_str())}; }
+        else if (a == "--devices") {
+            OptStr d;
+            val(d);
+            devices.clear();
+            std::stringstream ss(*d);
+            std::string tok;
+            while (std::getline(ss, tok, ',')) {
+                if (tok.empty() || tok.find_first_not_of("0123456789") != std::string::npos) {
+                    std::fprintf(stderr, "error: --devices takes a comma-separated list of CUDA ordinals, got '%s'\n", d->c_str());
+                    return 2;
+                }
+                devices.push_back(std::atoi(tok.c_str()));
+            }
+            if (devices.empty()) { std::fputs("error: --devices needs at least one ordinal\n", stderr); return 2; }
+        }
         else if (a == "-g" || a == "--generate-embeddings") {
             std::fputs("error: --generate-embeddings is the reference's dev-only fastembed path; not part of this build\n", stderr);
             return 2;
@@ -62,7 +79,7 @@ int main(int argc, char **argv) {
         }
         // -d DIR: main.rs:64-74 (commented out upstream) loads the database from DIR; without -d the database
         // lives in GPU memory for this process only
-        Db db = database ? std::make_shared<Database>(Database::load(*database, device)) : std::make_shared<Database>(device);
+        Db db = database ? std::make_shared<Database>(Database::load(*database, devices)) : std::make_shared<Database>(devices);
         CommandBuilder builder(db);
         int rc = 0;
         auto run = [&](OptStr coll, const std::string &cmd, OptStr arg) {
