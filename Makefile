@@ -3,17 +3,23 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 HOSTCXX   := /usr/bin/g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -std=c++17 -O3 -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC,-fvisibility=hidden -I/usr/include
-ifdef DEBUG_KERNELS
-NVFLAGS   += -DVROD_KERNEL_DEBUG    # development stamps / timing modes (VROD_BATCHED_DEBUG, VROD_SCAN_DEBUG): never in production
-endif
 CSRC      := vrod_b200/csrc
-OBJS      := $(CSRC)/knn_scan.o $(CSRC)/knn_batched.o $(CSRC)/vrod_capi.o
-LIB       := vrod_b200/libvrod_knn.so
+# `make debug` builds vrod_b200/libvrod_knn_dbg.so with the development stamps / timing modes compiled in
+# (VROD_BATCHED_DEBUG, VROD_SCAN_DEBUG); VROD_LIB=<path> makes vrod_b200/ffi.py load it.  Never the production library.
+ifdef DEBUG_KERNELS
+NVFLAGS   += -DVROD_KERNEL_DEBUG
+SUF       := _dbg
+endif
+OBJS      := $(CSRC)/knn_scan$(SUF).o $(CSRC)/knn_batched$(SUF).o $(CSRC)/vrod_capi$(SUF).o
+LIB       := vrod_b200/libvrod_knn$(SUF).so
 
 all: $(LIB) oracle host
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/vrod_knn.h
+$(CSRC)/%$(SUF).o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/vrod_knn.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+debug:
+	$(MAKE) DEBUG_KERNELS=1 vrod_b200/libvrod_knn_dbg.so
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -o $@ $(OBJS) -ldl -lcuda
@@ -25,7 +31,7 @@ host: $(LIB)
 	@if [ -f vrod_b200/host/Makefile ]; then $(MAKE) -C vrod_b200/host -s; fi
 
 clean:
-	rm -f $(OBJS) $(LIB)
+	rm -f $(CSRC)/*.o vrod_b200/libvrod_knn.so vrod_b200/libvrod_knn_dbg.so
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle host clean
+.PHONY: all oracle host clean debug

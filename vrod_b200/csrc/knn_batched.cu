@@ -55,10 +55,18 @@ constexpr int MAX_SLABS = 4;                // tf32, dim <= 128: the query group
 // a row / a query is [kd data columns | 16 aux columns] (kd = dim rounded up to 16): the aux columns fold the query's
 // threshold and the row's norm term into the contraction (see build_mirror_kernel), so the accumulator already
 // holds the candidate test value.
-constexpr int KS_H = 64;
 constexpr int UMMA_K_H = 16;
 constexpr int AUX_H = 16;
-constexpr int MAX_SLABS_H = 5;              // bf16: (dim + 16) <= 320 columns resident (160 KB)
+// The bf16 mirrors are stored TILED, one contiguous block per (tile, K step): a K step is 16 columns = 32 bytes per
+// row, and its block holds [rows/8 groups][2 chunks of 8 columns][8 rows][16 bytes] -- the tensor core's plain
+// (no-swizzle) K-major form, core matrices of 8 rows x 16 bytes stored contiguously.  A 128-row tile is T blocks of
+// 4 KB back to back in global memory, a 256-query group T blocks of 8 KB, so a pipeline stage is ONE contiguous
+// cp.async.bulk of up to 36 KB -- no tensor map, no 128-byte box rows cut out of 288-byte matrix rows (round 1: 48 KB
+// of shared-memory writes per 128 x 144 tile, 1286 cycles per tile for the TMA ring alone), no padding of the
+// 16-column tail slab.
+constexpr int KB_A = BM * 32;               // bytes of one K-step block of a row tile
+constexpr int KB_B = BN * 32;               // bytes of one K-step block of a query group
+constexpr uint32_t kPlainLBO = 128, kPlainSBO = 256;   // chunk-to-chunk and group-to-group strides inside a block
 
 struct BatchedParams {
     const float *sq_norm, *inv_norm;
@@ -72,6 +80,10 @@ struct BatchedParams {
     int kprime;
     int stream_q;               // 1: the query slabs are streamed with the row slabs (dim > 128: the group does not fit)
     uint32_t ksteps_last;       // MMA K steps in the last slab (the others hold 4)
+    // bf16 mode: tiled mirrors (see KB_A / KB_B)
+    const unsigned char *rows_t;   // [tiles][T][KB_A]
+    const unsigned char *q_t;      // [query groups of the wave][T][KB_B]
+    uint32_t T, S;                 // K steps per tile; K steps per pipeline stage
     int debug_nocand;           // VROD_BATCHED_DEBUG=nocand: thresholds start at -inf (timing experiments only)
     int debug_skip;             // timing experiments only: bit 0 = epilogue skips the TMEM reads (noepi), bit 1 = no MMAs issued (nomma)
     long long *dbg;             // VROD_BATCHED_DEBUG set: per-CTA cycle counters [grid][8]
@@ -154,12 +166,35 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+// 1-D bulk copy global -> shared (contiguous, multiple of 16 bytes), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// One lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// Plain (no-swizzle) K-major operand block: low word = start address | LBO, high word = SBO | descriptor version.
+// Advancing to another block only ever adds to the start-address field of the LOW word (shared memory is < 256 KB,
+// so the 14-bit field cannot carry into the LBO field): the issue loop needs ONE integer add per operand per MMA.
+__device__ __forceinline__ uint32_t plain_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | ((kPlainLBO >> 4) << 16); }
+constexpr uint32_t kPlainDescHi = (kPlainSBO >> 4) | (1u << 14);
+__device__ __forceinline__ void tc_mma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kPlainDescHi)
         : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -196,6 +231,18 @@ __host__ __device__ constexpr uint32_t idesc_bf16() {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// Deferred appends: an epilogue warp that finds a candidate in a 32-column block does NOT stop to append it while it
+// still holds the accumulator stage -- every such stop (shared-memory atomics, a global store, cold code) delayed the
+// stage's release and with it the MMA warp: ~90 cycles per candidate, 30 % of a configs[2] batch in round 2's first
+// measurement.  The hitting lane parks its 32 scores in a small per-warp stash instead (32 predicated STS with static
+// register indices) and the warp empties the stash after it has handed the stage back.
+constexpr int kStash = 32;                // parked blocks per warp: one per lane, so any block can be parked whole
+struct StashSlot {      // 35 words: lane e reads word j of slot e from bank (3e + j) mod 32 -- conflict-free across the warp
+    float score[32];
+    uint32_t row, colbase;
+    float hx;
+};
+static_assert(sizeof(StashSlot) == 140, "stash slot size");
 struct BatchCtl {
     uint64_t full[8], empty[8], tfull[2], tempty[2], qfull;
     uint64_t pfull[8], pqfull;   // leader's view of the PEER's slabs / query slabs (CTA pairs only)
@@ -203,28 +250,28 @@ struct BatchCtl {
     int flag;
     alignas(16) float thr[BN];
     int cnt[BN];
+    StashSlot stash[kEpiWarps][kStash];
 };
 
 // ---- epilogue: prune one (CTA, query) list with one warp ------------------------------------------
 // Keep the entries <= t where t is the smallest sampled key with at least kprime entries at or below
-// it (verified by an exact count), compact them to the front, tighten the threshold.
+// it (verified by an exact count), compact them to the front, tighten the threshold.  A safety net for adversarial
+// row orders -- it does not run at all on the benchmark workloads -- so it is written for SIZE (rolled loops over
+// the list in L2, one copy per kernel): the register-resident version it replaces was 14 KB of SASS, inlined twice,
+// in a kernel whose hot loops want the 32 KB instruction cache for themselves.
 // H (bf16 mode): ctl->thr[q] is the threshold FOLDED into the contraction (the accumulator holds D = dot + thr - hx and
-// warp_append recovers the surrogate as thr - D), so it must stay what the query mirror carries: the prune then only
+// the append recovers the surrogate as thr - D), so it must stay what the query mirror carries: the prune then only
 // compacts the list and candidates keep arriving at the phase threshold until the next phase tightens it.
 template <bool H>
-__device__ __forceinline__ void prune_list(unsigned long long *cq, int q, BatchCtl *ctl, int kprime, int lane, int *fail) {
-    const int c = ctl->cnt[q];
+__device__ __noinline__ void prune_list(unsigned long long *cq, int q, BatchCtl *ctl, int kprime, int lane) {
+    int c = ctl->cnt[q];
+    if (c > CAP) c = CAP;
     if (c <= kprime) return;
-    unsigned long long key[CAP / 32];
-#pragma unroll
-    for (int i = 0; i < CAP / 32; ++i) {
-        const int idx = lane + 32 * i;
-        key[i] = idx < c ? __ldcg(cq + idx) : kKeyMax;
-    }
-    unsigned long long s = key[0];   // 32 samples (arrival order is unrelated to value), sorted across the warp
-#pragma unroll
+    // 32 samples (arrival order is unrelated to value), sorted across the warp
+    unsigned long long s = __ldcg(cq + lane);   // c > kprime >= 64 > lane
+#pragma unroll 1
     for (int k2 = 2; k2 <= 32; k2 <<= 1)
-#pragma unroll
+#pragma unroll 1
         for (int j = k2 >> 1; j > 0; j >>= 1) {
             const unsigned long long o = __shfl_xor_sync(kFull, s, j);
             const bool up = (lane & k2) == 0, low = (lane & j) == 0;
@@ -234,30 +281,33 @@ __device__ __forceinline__ void prune_list(unsigned long long *cq, int q, BatchC
     if (j > 31) j = 31;
     unsigned long long t;
     int count;
+#pragma unroll 1
     while (true) {
         t = __shfl_sync(kFull, s, j);
         count = 0;
-#pragma unroll
-        for (int i = 0; i < CAP / 32; ++i) count += key[i] <= t ? 1 : 0;
+#pragma unroll 1
+        for (int i = lane; i < c; i += 32) count += __ldcg(cq + i) <= t ? 1 : 0;
         count = __reduce_add_sync(kFull, count);
         if (count >= kprime || j == 31) break;
         ++j;
     }
-    if (count < kprime) {   // pathological arrival order: give the query up, the scan path answers it
-        if (lane == 0) {
-            *fail = 1;
-            ctl->cnt[q] = 0;
-            if (!H) ctl->thr[q] = -__int_as_float(0x7f800000);
-        }
-        return;
-    }
+    // No sampled key has kprime entries at or below it: the list is barely longer than kprime (with c = kprime + 1 the
+    // largest of 32 samples is the wanted key only ~1 time in 5) or the samples were unlucky.  Nothing can be dropped
+    // safely, so the list stays as it is.  (Round 1 gave the query up here -- with k' = 256 and lists that hover just
+    // above 256 entries that flagged three quarters of an 8192-query batch for a rescan.)  A list that really
+    // overruns CAP later is caught at the append (qflags), so leaving it alone is safe.
+    if (count < kprime) return;
+    // in-place compaction, 32 entries at a time (a chunk is read by the whole warp before any lane writes, and it is
+    // written at or below where it was read)
     int base = 0;
-#pragma unroll
-    for (int i = 0; i < CAP / 32; ++i) {
-        const bool keep = key[i] <= t;
+#pragma unroll 1
+    for (int i0 = 0; i0 < c; i0 += 32) {
+        const unsigned long long key = i0 + lane < c ? __ldcg(cq + i0 + lane) : kKeyMax;
+        const bool keep = key <= t;
         const unsigned m = __ballot_sync(kFull, keep);
-        if (keep) __stcg(cq + base + __popc(m & ((1u << lane) - 1)), key[i]);
+        if (keep) __stcg(cq + base + __popc(m & ((1u << lane) - 1)), key);
         base += __popc(m);
+        __syncwarp();
     }
     if (lane == 0) {
         ctl->cnt[q] = base;
@@ -308,79 +358,51 @@ __device__ __forceinline__ float block_max_h(const uint32_t (&r)[32]) {
     return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// Rare path, entered by the whole warp when ANY of its rows beat some threshold among the 32 columns of the block
-// held in registers (`hit` = this thread's row did).
-//  * dense block (every row x every column passes: the start phase, where the thresholds are still above every
-//    surrogate): lane j claims 32 slots of column j's list with one shared-memory atomic for the whole warp, then
-//    the 32 columns are written as 32 coalesced 256-byte stores (static register indices);
-//  * otherwise each hitting THREAD appends its own survivors -- one shared-memory atomic per candidate, no TMEM
-//    re-read -- with deliberately COMPACT code: a dense mask pass, then a loop over the set bits that picks the score
-//    out of the 32 registers with a 5-level select tree (31 selects; a run-time register index would push the block
-//    into local memory).  Cold straight-line code is paid for in instruction-cache misses: a fully unrolled
-//    per-column form (15 KB) cost ~2500 cycles per entry, and round 1's first form (TMEM re-read + ballot
-//    transpose) ~2000 while holding the accumulator stage.
-// (H = bf16 mode: the register holds D, a candidate is D > 0 and its surrogate is v = thr_q - D.)
+// ---- rare paths of the epilogue ---------------------------------------------------------------------
+// Code size is a first-order cost here: the tile kernel is far larger than the SM's 32 KB instruction cache, so any
+// path that a warp enters only now and then is fetched cold (~2000 cycles for a few dozen straight-line
+// instructions; round 1 measured 2000-2500 cycles per entry for its first forms).  The rare paths are therefore
+// (a) as few instructions as possible, (b) NOT inlined -- one copy per kernel, shared by both halves of the
+// ping-pong loop -- and (c) kept off the accumulator's critical path (stash, above).  (Round 1's register-resident
+// append -- a 31-select tree per candidate, inlined twice, plus a separate dense-block form -- was 35 KB of the kernel.)
+
+// Empty a warp's stash: lane e appends the survivors of parked block e.  Eight scores are fetched at a time (independent
+// shared-memory loads) and turned into a bit mask; only the set bits reach the append body.
 template <bool COS, bool H>
-__device__ __forceinline__ void warp_append(const uint32_t (&r)[32], bool hit, const float *thr, float hx, int colbase, uint32_t row,
-                                            BatchCtl *ctl, unsigned long long *cand, int *qflags, uint32_t qbase, uint32_t b, int lane) {
-    uint32_t m0 = 0, m1 = 0;
-    if constexpr (H) {
+__device__ __noinline__ void stash_flush(int nst, StashSlot *slots, BatchCtl *ctl, unsigned long long *cand, int *qflags, uint32_t qbase,
+                                         uint32_t b, int lane) {
+    if (lane < nst) {
+        const StashSlot &e = slots[lane];
+        const float *thr = ctl->thr + e.colbase;
+        const float hx = e.hx;
+#pragma unroll 1
+        for (int j0 = 0; j0 < 32; j0 += 8) {
+            float d[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const bool h = __uint_as_float(r[j]) > 0.f;
-            if (j & 1) m1 |= h ? (1u << j) : 0u;
-            else m0 |= h ? (1u << j) : 0u;
-        }
-    } else {
+            for (int u = 0; u < 8; ++u) d[u] = e.score[j0 + u];
+            uint32_t mask = 0;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 th = *reinterpret_cast<const float4 *>(thr + j4 * 4);
-            const float t4[4] = {th.x, th.y, th.z, th.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const bool h = cand_hit<COS>(cand_w<COS>(__uint_as_float(r[j4 * 4 + e]), t4[e], hx), hx);
-                if (e & 1) m1 |= h ? (1u << (j4 * 4 + e)) : 0u;
-                else m0 |= h ? (1u << (j4 * 4 + e)) : 0u;
+            for (int u = 0; u < 8; ++u) {
+                bool hit;
+                if constexpr (H) hit = d[u] > 0.f;
+                else hit = cand_hit<COS>(cand_w<COS>(d[u], thr[j0 + u], hx), hx);
+                mask |= hit ? (1u << u) : 0u;
+            }
+#pragma unroll 1
+            while (mask) {
+                const int j = j0 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float dot = e.score[j];
+                const int q = (int)e.colbase + j;
+                const int pos = atomicAdd(&ctl->cnt[q], 1);
+                if (pos >= PRUNE_AT) *(volatile int *)&ctl->flag = 1;
+                const float v = H ? (thr[j] - dot) : (COS ? -(dot * hx) : (hx - dot));
+                if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, e.row));
+                else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
             }
         }
     }
-    uint32_t mask = hit ? (m0 | m1) : 0u;
-    if (__all_sync(kFull, mask == 0xffffffffu)) {
-        const int base = atomicAdd(&ctl->cnt[colbase + lane], 32);
-        if (base + 32 > PRUNE_AT) *(volatile int *)&ctl->flag = 1;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int pos = __shfl_sync(kFull, base, j) + lane;
-            const float dot = __uint_as_float(r[j]);
-            const float v = H ? (thr[j] - dot) : (COS ? -(dot * hx) : (hx - dot));
-            const int q = colbase + j;
-            if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
-            else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
-        }
-        return;
-    }
-#pragma unroll 1
-    while (mask) {
-        const int j = __ffs(mask) - 1;
-        mask &= mask - 1;
-        uint32_t s16[16], s8[8], s4[4], s2[2];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) s16[i] = (j & 16) ? r[i + 16] : r[i];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s8[i] = (j & 8) ? s16[i + 8] : s16[i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s4[i] = (j & 4) ? s8[i + 4] : s8[i];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) s2[i] = (j & 2) ? s4[i + 2] : s4[i];
-        const float dot = __uint_as_float((j & 1) ? s2[1] : s2[0]);
-        const int q = colbase + j;
-        const int pos = atomicAdd(&ctl->cnt[q], 1);
-        if (pos >= PRUNE_AT) *(volatile int *)&ctl->flag = 1;
-        const float v = H ? (thr[j] - dot) : (COS ? -(dot * hx) : (hx - dot));
-        if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, row));
-        else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
-    }
-    __syncwarp();   // the caller continues with warp-aligned TMEM instructions
+    __syncwarp();
 }
 
 // PSZ = 1 (default): one CTA per unit (tcgen05 cta_group::1, M = 128).  PSZ = 2 (experiment, VROD_BATCHED_PAIR=1):
@@ -390,18 +412,21 @@ __device__ __forceinline__ void warp_append(const uint32_t (&r)[32], bool hit, c
 // cycles per tile in the MMA (12 KB of shared-memory operands per K=8 step); the pair was meant to cut that to
 // 8 KB per CTA but measured slower in round 1.
 // H = bf16 operand mode (PSZ = 1 only): operands are the bf16 mirrors with the folded aux columns, MMA kind::f16.
-template <bool COS, int PSZ, bool H>
+// DENSE = the start phase (one tile per CTA, every threshold still above every surrogate): the epilogue writes all 128
+// rows of the tile as candidates of all 256 queries, no test, position = row inside the tile, 256-byte coalesced stores.
+template <bool COS, int PSZ, bool H, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                    const __grid_constant__ CUtensorMap tmQ,
                                                                    const BatchedParams p) {
     static_assert(!(H && PSZ == 2), "the bf16 mode has no CTA-pair variant");
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int SLAB_B = slab_b_bytes(PSZ);
-    constexpr int KSE = H ? KS_H : KS;   // elements per K slab (128 bytes either way)
-    // resident mode: [nslab query slabs][stages row slabs]; streamed mode: [stages x (row slab + query slab)]
-    const uint32_t stage_bytes = p.stream_q ? (SLAB_A_BYTES + SLAB_B) : SLAB_A_BYTES;
+    constexpr int KSE = KS;   // f32 elements per K slab (tf32 mode)
+    // resident mode: [query operand of the group][stages x row operand]; streamed mode: [stages x (row + query operand)]
+    // (tf32: 128-byte-swizzled slabs written by TMA; bf16: S K-step blocks of the tiled mirrors per stage)
+    const uint32_t stage_bytes = H ? (p.stream_q ? p.S * (KB_A + KB_B) : p.S * KB_A) : (p.stream_q ? (SLAB_A_BYTES + SLAB_B) : SLAB_A_BYTES);
     unsigned char *q_s = smem;
-    unsigned char *a_s = p.stream_q ? smem : smem + (size_t)p.nslab * SLAB_B;
+    unsigned char *a_s = p.stream_q ? smem : smem + (H ? (size_t)p.T * KB_B : (size_t)p.nslab * SLAB_B);
     BatchCtl *ctl = reinterpret_cast<BatchCtl *>(a_s + (size_t)p.stages * stage_bytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (smem_u32(smem) & 1023u) __trap();          // the 128-byte swizzle needs a 1024-byte aligned base
@@ -456,7 +481,34 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs of a pair: each loads its own row tile and its share of the queries) =====
-        if (lane == 0) {
+        if (H) {
+            // ===== bf16 mode: contiguous bulk copies of the tiled mirrors (one per stage and operand) =====
+            if (lane == 0) {
+                const unsigned char *qg = p.q_t + (size_t)g * p.T * KB_B;
+                auto copy = [&](unsigned char *dst, const unsigned char *src, uint32_t bytes, uint64_t *bar) {
+#pragma unroll 1
+                    for (uint32_t o = 0; o < bytes; o += 32768) bulk_load(dst + o, src + o, bytes - o < 32768 ? bytes - o : 32768, bar);
+                };
+                if (!p.stream_q) {
+                    mbar_expect_tx(&ctl->qfull, p.T * KB_B);
+                    copy(q_s, qg, p.T * KB_B, &ctl->qfull);
+                }
+                const uint32_t ns = (p.T + p.S - 1) / p.S;
+                uint32_t stage = 0, phase = 0;
+                for (uint32_t i = 0; i < my_tiles; ++i) {
+                    const unsigned char *ta = p.rows_t + (size_t)tile_of(i) * p.T * KB_A;
+                    for (uint32_t st = 0; st < ns; ++st) {
+                        const uint32_t nk = p.T - st * p.S < p.S ? p.T - st * p.S : p.S;
+                        mbar_wait(&ctl->empty[stage], phase ^ 1);
+                        unsigned char *dst = a_s + (size_t)stage * stage_bytes;
+                        mbar_expect_tx(&ctl->full[stage], nk * KB_A + (p.stream_q ? nk * KB_B : 0));
+                        copy(dst, ta + (size_t)st * p.S * KB_A, nk * KB_A, &ctl->full[stage]);
+                        if (p.stream_q) copy(dst + p.S * KB_A, qg + (size_t)st * p.S * KB_B, nk * KB_B, &ctl->full[stage]);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        } else if (lane == 0) {
             // every CTA completes its TMA bytes on its OWN barrier (completing the peer's bytes on the leader's
             // barrier through the cluster made the loads ~2x slower); the peer's forwarder warp tells the leader
             auto load = [&](void *dst, const CUtensorMap *m, int c0, int c1, uint64_t *bar) { tma_load_2d(dst, m, c0, c1, bar); };
@@ -480,6 +532,56 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 }
             }
             if (kDbg && p.dbg) p.dbg[blockIdx.x * 16 + 9] = w_empty;
+        }
+    } else if (warp == 1 && H) {
+        // ===== bf16 mode MMA issuer.  The whole warp runs the loop converged (waits included) and ONE elected lane
+        // issues; the operand descriptors advance by a single add on their low word.  Round 1 issued from inside an
+        // `if (lane == 0)` region and rebuilt both 64-bit descriptors from byte addresses for every MMA: ~18 dependent
+        // uniform-datapath instructions per tcgen05.mma, 214 cycles per MMA where the tensor core needs 128
+        // (tools/mma_probe.cu measures 128.0 with operands, bulk copies and tcgen05.ld all running). =====
+        if (!p.stream_q) mbar_wait(&ctl->qfull, 0);
+        const uint32_t ns = (p.T + p.S - 1) / p.S;
+        const uint32_t q_lo = plain_desc_lo(smem_u32(q_s));
+        const uint32_t a_lo0 = plain_desc_lo(smem_u32(a_s));
+        const uint32_t stage_step = stage_bytes >> 4;
+        const uint32_t idesc = idesc_bf16();
+        uint32_t stage = 0, phase = 0;
+        long long w_tempty = 0, w_full = 0;
+        const long long tstart = kDbg ? clock64() : 0;
+        for (uint32_t i = 0; i < my_tiles; ++i) {
+            const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
+            long long t0 = (kDbg && p.dbg) ? clock64() : 0;
+            mbar_wait(&ctl->tempty[acc], aphase ^ 1);
+            if (kDbg && p.dbg) w_tempty += clock64() - t0;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + acc * BN;
+            uint32_t ks = 0;
+            for (uint32_t st = 0; st < ns; ++st) {
+                const uint32_t nk = p.T - ks < p.S ? p.T - ks : p.S;
+                t0 = (kDbg && p.dbg) ? clock64() : 0;
+                mbar_wait(&ctl->full[stage], phase);
+                if (kDbg && p.dbg) w_full += clock64() - t0;
+                tc_fence_after();
+                const uint32_t a_lo = a_lo0 + stage * stage_step;
+                const uint32_t b_lo = p.stream_q ? a_lo + p.S * (KB_A >> 4) : q_lo + ks * (KB_B >> 4);
+                if (elect_one()) {
+                    if (!(kDbg && (p.debug_skip & 2))) {
+#pragma unroll 1
+                        for (uint32_t kk = 0; kk < nk; ++kk)
+                            tc_mma_bf16_lo(d_tmem, a_lo + kk * (KB_A >> 4), b_lo + kk * (KB_B >> 4), idesc, (ks + kk) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&ctl->empty[stage]);                      // frees the stage when these MMAs have read it
+                    if (st + 1 == ns) tc_commit(&ctl->tfull[acc]);      // accumulator complete
+                }
+                __syncwarp();
+                ks += nk;
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+        if (kDbg && p.dbg && lane == 0) {
+            p.dbg[blockIdx.x * 16 + 5] = w_tempty;
+            p.dbg[blockIdx.x * 16 + 6] = w_full;
+            p.dbg[blockIdx.x * 16 + 1] = clock64() - tstart;
         }
     } else if (warp == 1) {
         // ===== peer CTA of a pair: forward "my slab has landed" to the leader, one remote arrive per slab =====
@@ -530,8 +632,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                         if ((kDbg && (p.debug_skip & 2)) || kk >= nk) break;
                         const uint64_t ad = umma_desc_sw128(a_addr + kk * 32), bd = umma_desc_sw128(b_addr + kk * 32);
                         const uint32_t accum = (s | kk) != 0 ? 1u : 0u;
-                        if constexpr (H) tc_mma_bf16(d_tmem, ad, bd, idesc_bf16(), accum);
-                        else if constexpr (PSZ == 2) tc_mma_tf32_pair(d_tmem, ad, bd, idesc_tf32(2), accum);
+                        if constexpr (PSZ == 2) tc_mma_tf32_pair(d_tmem, ad, bd, idesc_tf32(2), accum);
                         else tc_mma_tf32(d_tmem, ad, bd, idesc_tf32(1), accum);
                     }
                     // frees the slab (in both CTAs) when these MMAs have read it
@@ -556,7 +657,6 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
         const int ew = warp - 2;                     // 0..7
         const int half = ew >> 2;                    // which 128 of the 256 query columns
         unsigned long long *cand = p.cand + (size_t)blockIdx.x * BN * CAP;
-        int fail = 0;
         long long w_tfull = 0, w_prune = 0, n_slow = 0;
         const long long tstart = kDbg ? clock64() : 0;
         // per-row factor of the NEXT tile is fetched one tile ahead (its global-load latency would otherwise
@@ -584,10 +684,60 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             // (placed out of line): the body must stay inside the instruction cache (a fully unrolled version
             // was 130 KB of SASS and ran at ~0.04 IPC on instruction fetch).
             uint32_t ra[32], rb[32];
+            int nst = 0;                                  // parked blocks of this warp in this tile (warp-uniform)
+            int cur_col = 0;                              // first query column of the block being filtered
+            StashSlot *slots = ctl->stash[ew];
+            // A block with candidates.  Usually one lane with one candidate: the lane parks its 32 scores and the warp moves
+            // on.  More hitting lanes than free slots (the dense early phases, where every row passes every column): park
+            // in rounds of kStash lanes and empty the stash in between -- that holds the accumulator stage, but only where
+            // a CTA has a handful of tiles anyway.
+            auto on_hit = [&](const uint32_t (&r)[32], bool hit) {
+                const unsigned hm = __ballot_sync(kFull, hit);
+                const int nh = __popc(hm), rank = __popc(hm & ((1u << lane) - 1u));
+                int done = 0;
+#pragma unroll 1
+                while (done < nh) {
+                    if (nst == kStash) {
+                        stash_flush<COS, H>(nst, slots, ctl, cand, p.qflags, g * BN, p.b, lane);
+                        nst = 0;
+                    }
+                    const int take = min(kStash - nst, nh - done);
+                    if (hit && rank >= done && rank < done + take) {
+                        StashSlot &e = slots[nst + rank - done];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) e.score[j] = __uint_as_float(r[j]);
+                        e.row = row;
+                        e.colbase = (uint32_t)cur_col;
+                        e.hx = hx;
+                    }
+                    nst += take;
+                    done += take;
+                    __syncwarp();
+                }
+            };
             const float *thr_h = ctl->thr + half * (BN / 2);
             const float ninf = -__int_as_float(0x7f800000);
             const int col_h = half * (BN / 2);
-            if (!(kDbg && (p.debug_skip & 1))) {
+            if constexpr (DENSE) {
+                const int rt = quad * 32 + lane;   // row inside the tile = its position in every list
+#pragma unroll 1
+                for (int cb = 0; cb < BN / 64; ++cb) {
+                    tc_ld32(taddr + cb * 32, ra);
+                    tc_wait_ld();
+                    unsigned long long *dst = cand + (size_t)(col_h + cb * 32) * CAP + rt;
+                    const float *thr_b = thr_h + cb * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float dot = __uint_as_float(ra[j]);
+                        const float v = H ? (thr_b[j] - dot) : (COS ? -(dot * hx) : (hx - dot));
+                        if (rowok) __stcg(dst + (size_t)j * CAP, make_key(v, row));
+                    }
+                }
+                if (quad == 0 && lane == 0 && half == 0) {
+                    const uint32_t left = p.n - tile * BM;
+                    ctl->flag = (int)(left < (uint32_t)BM ? left : (uint32_t)BM);   // rows of this tile = entries of every list
+                }
+            } else if (!(kDbg && (p.debug_skip & 1))) {
                 tc_ld32(taddr, ra);
                 tc_wait_ld();
 #pragma unroll 1
@@ -598,7 +748,8 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                     const bool hita = (H ? wa > 0.f : cand_hit<COS>(wa, hx)) && rowok;
                     if (__builtin_expect(__any_sync(kFull, hita), 0)) {
                         if (kDbg) n_slow++;
-                        warp_append<COS, H>(ra, hita, thr_h + cb * 32, hx, col_h + cb * 32, row, ctl, cand, p.qflags, g * BN, p.b, lane);
+                        cur_col = col_h + cb * 32;
+                        on_hit(ra, hita);
                     }
                     tc_wait_ld();
                     if (cb + 2 < BN / 64) tc_ld32(taddr + (cb + 2) * 32, ra);
@@ -607,7 +758,8 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                     const bool hitb = (H ? wb > 0.f : cand_hit<COS>(wb, hx)) && rowok;
                     if (__builtin_expect(__any_sync(kFull, hitb), 0)) {
                         if (kDbg) n_slow++;
-                        warp_append<COS, H>(rb, hitb, thr_h + (cb + 1) * 32, hx, col_h + (cb + 1) * 32, row, ctl, cand, p.qflags, g * BN, p.b, lane);
+                        cur_col = col_h + (cb + 1) * 32;
+                        on_hit(rb, hitb);
                     }
                     if (cb + 2 < BN / 64) tc_wait_ld();
                 }
@@ -619,18 +771,19 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 if (leader) mbar_arrive(&ctl->tempty[acc]);
                 else mbar_arrive_leader(&ctl->tempty[acc]);
             }
+            // the stage is back with the MMA warp: now the parked candidates
+            if (nst) {
+                __syncwarp();
+                stash_flush<COS, H>(nst, slots, ctl, cand, p.qflags, g * BN, p.b, lane);
+            }
             // list maintenance every kCheckEvery tiles (all epilogue warps; the lists have room for the
             // appends of the tiles in between, see PRUNE_AT)
-            if ((i + 1) % kCheckEvery != 0) continue;
+            if (DENSE || (i + 1) % kCheckEvery != 0) continue;
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (*(volatile int *)&ctl->flag) {
                 t0 = kDbg ? clock64() : 0;
                 for (int q = ew; q < BN; q += kEpiWarps) {
-                    if (ctl->cnt[q] > PRUNE_AT / 2) prune_list<H>(cand + (size_t)q * CAP, q, ctl, p.kprime, lane, &fail);
-                    if (fail) {
-                        if (lane == 0 && g * BN + q < p.b) atomicOr(p.qflags + g * BN + q, 1);
-                        fail = 0;
-                    }
+                    if (ctl->cnt[q] > PRUNE_AT / 2) prune_list<H>(cand + (size_t)q * CAP, q, ctl, p.kprime, lane);
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (ew == 0 && lane == 0) ctl->flag = 0;
@@ -650,7 +803,10 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
 
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int q = ew * 32 + lane; q < BN; q += 32 * kEpiWarps) p.cnt_out[(size_t)blockIdx.x * BN + q] = ctl->cnt[q] < CAP ? ctl->cnt[q] : CAP;
+        for (int q = ew * 32 + lane; q < BN; q += 32 * kEpiWarps) {
+            const int c = DENSE ? *(volatile int *)&ctl->flag : ctl->cnt[q];
+            p.cnt_out[(size_t)blockIdx.x * BN + q] = c < CAP ? c : CAP;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -687,35 +843,49 @@ __device__ __forceinline__ float split3(float v, unsigned short (&t)[3]) {
 __device__ __forceinline__ unsigned short bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 constexpr unsigned short kBf16One = 0x3F80;
 
-// rows [row0, row0 + n) of the shard -> mirror.  One warp per row, a lane writes 8 columns (16 bytes) at a time.
+// Byte offset of 8-column chunk `chunk` (K step chunk / 2, half chunk % 2) of row `r` inside a tile of R rows whose
+// K-step blocks are R * 32 bytes: [K step][r / 8][chunk % 2][r % 8][16 bytes].
+__host__ __device__ __forceinline__ size_t tiled_offset(uint32_t r, uint32_t chunk, uint32_t R) {
+    return (size_t)(chunk >> 1) * R * 32 + (size_t)(r >> 3) * kPlainSBO + (size_t)(chunk & 1) * kPlainLBO + (size_t)(r & 7) * 16;
+}
+
+// Tiles [tile0, tile0 + ntiles) of the shard -> tiled mirror.  A warp converts 8 rows x 4 chunks per step: lane l
+// reads 32 bytes (8 floats: one full sector) of row l % 8 and writes the 16-byte bf16 chunk, so each group of 8 lanes
+// stores one contiguous 128-byte core matrix.  Rows at and beyond n_valid (the tail of the last tile, rows not
+// inserted yet) become zero rows: D = 0 for them, never a candidate.
 template <bool COS>
 __global__ void __launch_bounds__(256) build_mirror_kernel(const float *__restrict__ rows, const float *__restrict__ sq_norm,
-                                                           const float *__restrict__ inv_norm, uint32_t row0, uint32_t n, uint32_t ld,
-                                                           uint32_t kd, uint32_t ld_h, unsigned short *__restrict__ out) {
-    const int lane = threadIdx.x & 31;
+                                                           const float *__restrict__ inv_norm, uint32_t tile0, uint32_t ntiles, uint32_t n_valid,
+                                                           uint32_t ld, uint32_t kd, uint32_t T, unsigned char *__restrict__ out) {
+    const int lane = threadIdx.x & 31, rr = lane & 7, cc = lane >> 3;
     const uint32_t wpg = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += wpg) {
-        const uint32_t r = row0 + i;
+    const uint32_t groups = ntiles * (BM / 8);          // 8-row groups to convert
+    const uint32_t nchunk = T * 2, aux = kd / 8;
+    for (uint32_t gi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); gi < groups; gi += wpg) {
+        const uint32_t tile = tile0 + gi / (BM / 8), rt = (gi % (BM / 8)) * 8 + rr;   // row inside the tile
+        const uint32_t r = tile * BM + rt;
+        const bool live = r < n_valid;
         const float *x = rows + (size_t)r * ld;
-        const float scale = COS ? __ldg(inv_norm + r) : 1.f;
+        const float scale = (COS && live) ? __ldg(inv_norm + r) : 1.f;
         unsigned short h[3] = {0, 0, 0};
-        if (!COS) split3(0.5f * __ldg(sq_norm + r), h);
-        for (uint32_t c0 = lane * 8; c0 < ld_h; c0 += 256) {
-            unsigned short v[8];
+        if (!COS && live) split3(0.5f * __ldg(sq_norm + r), h);
+        unsigned char *tbase = out + (size_t)tile * T * KB_A;
+        for (uint32_t ch = cc; ch < nchunk; ch += 4) {
+            unsigned short v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const uint32_t c0 = ch * 8;
+            if (live) {
+                if (ch < aux) {
 #pragma unroll
-            for (int g4 = 0; g4 < 2; ++g4) {
-                const uint32_t c = c0 + g4 * 4;
-                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c < ld && c < kd) f = *reinterpret_cast<const float4 *>(x + c);   // ld % 4 == 0; columns >= dim hold zeros
-                v[g4 * 4 + 0] = bf16_bits(f.x * scale);
-                v[g4 * 4 + 1] = bf16_bits(f.y * scale);
-                v[g4 * 4 + 2] = bf16_bits(f.z * scale);
-                v[g4 * 4 + 3] = bf16_bits(f.w * scale);
-            }
-            if (c0 >= kd) {   // aux columns (kd % 16 == 0: an 8-column chunk is all data or all aux)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = 0;
-                if (c0 == kd) {
+                    for (int g4 = 0; g4 < 2; ++g4) {
+                        const uint32_t c = c0 + g4 * 4;
+                        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c < ld) f = __ldg(reinterpret_cast<const float4 *>(x + c));   // ld % 4 == 0; columns >= dim hold zeros
+                        v[g4 * 4 + 0] = bf16_bits(f.x * scale);
+                        v[g4 * 4 + 1] = bf16_bits(f.y * scale);
+                        v[g4 * 4 + 2] = bf16_bits(f.z * scale);
+                        v[g4 * 4 + 3] = bf16_bits(f.w * scale);
+                    }
+                } else if (ch == aux) {   // aux columns (kd % 16 == 0: an 8-column chunk is all data or all aux)
                     v[0] = v[1] = v[2] = kBf16One;
                     if (!COS) {
                         v[3] = h[0] ^ 0x8000;
@@ -729,26 +899,29 @@ __global__ void __launch_bounds__(256) build_mirror_kernel(const float *__restri
             w.y = v[2] | ((uint32_t)v[3] << 16);
             w.z = v[4] | ((uint32_t)v[5] << 16);
             w.w = v[6] | ((uint32_t)v[7] << 16);
-            *reinterpret_cast<uint4 *>(out + (size_t)r * ld_h + c0) = w;
+            *reinterpret_cast<uint4 *>(tbase + tiled_offset(rt, ch, BM)) = w;
         }
     }
 }
 
-// Queries of one wave -> mirror, with the START threshold: no finite k'-th key exists yet, so the threshold is a
-// finite cap above every possible surrogate (every row passes) -- an infinite one would poison D = dot + thr - hx.
+// Queries of one wave -> tiled mirror (groups of BN queries), with the START threshold: no finite k'-th key exists
+// yet, so the threshold is a finite cap above every possible surrogate (every row passes) -- an infinite one would
+// poison D = dot + thr - hx.
 //   Euclidean  v = ||x||^2/2 - dot  <=  M/2 + sqrt(M) ||q||   (M = max ||x||^2 of the shard)
 //   cosine     v = -dot/||x||       <=  ||q||
-// One warp per query.
+// One warp per query slot of the wave's groups; slots beyond b become zero rows.
 template <bool COS>
-__global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restrict__ q, uint32_t b, uint32_t ld, uint32_t kd, uint32_t ld_h,
-                                                           const unsigned int *__restrict__ maxnorm_bits, unsigned short *__restrict__ qh,
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restrict__ q, uint32_t b, uint32_t slots, uint32_t ld, uint32_t kd, uint32_t T,
+                                                           const unsigned int *__restrict__ maxnorm_bits, unsigned char *__restrict__ qt,
                                                            float *__restrict__ gthr, float *__restrict__ qcap, float cap_sign) {
     const int lane = threadIdx.x & 31;
     const uint32_t qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (qi >= b) return;
+    if (qi >= slots) return;
+    const bool live = qi < b;
     const float *x = q + (size_t)qi * ld;
     float nq = 0.f;
-    for (uint32_t c = lane; c < ld; c += 32) nq = fmaf(x[c], x[c], nq);
+    if (live)
+        for (uint32_t c = lane; c < ld; c += 32) nq = fmaf(x[c], x[c], nq);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nq += __shfl_xor_sync(kFull, nq, o);
     const float nqs = sqrtf(nq) * 1.0001f;
@@ -757,14 +930,32 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restri
     const float cap = cap_sign * ((COS ? nqs : fmaf(sqrtf(M), nqs, 0.5f * M)) * 1.02f + 1e-30f);
     unsigned short t[3];
     const float thr = split3(cap, t);
-    for (uint32_t c = lane; c < ld_h; c += 32) {
-        unsigned short v = 0;
-        if (c < kd) v = c < ld ? bf16_bits(x[c]) : 0;
-        else if (c < kd + 3) v = t[c - kd];
-        else if (!COS && c < kd + 6) v = kBf16One;
-        qh[(size_t)qi * ld_h + c] = v;
+    unsigned char *gbase = qt + (size_t)(qi / BN) * T * KB_B;
+    const uint32_t rq = qi % BN, aux = kd / 8;
+    for (uint32_t ch = lane; ch < T * 2; ch += 32) {
+        unsigned short v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (live) {
+            if (ch < aux) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const uint32_t c = ch * 8 + e;
+                    v[e] = c < ld ? bf16_bits(x[c]) : 0;
+                }
+            } else if (ch == aux) {
+                v[0] = t[0];
+                v[1] = t[1];
+                v[2] = t[2];
+                if (!COS) v[3] = v[4] = v[5] = kBf16One;
+            }
+        }
+        uint4 w;
+        w.x = v[0] | ((uint32_t)v[1] << 16);
+        w.y = v[2] | ((uint32_t)v[3] << 16);
+        w.z = v[4] | ((uint32_t)v[5] << 16);
+        w.w = v[6] | ((uint32_t)v[7] << 16);
+        *reinterpret_cast<uint4 *>(gbase + tiled_offset(rq, ch, BN)) = w;
     }
-    if (lane == 0) {
+    if (lane == 0 && live) {
         gthr[qi] = thr;
         qcap[qi] = thr;
     }
@@ -795,8 +986,8 @@ struct FinishParams {
     float *out_dist;
     double eps_dot;         // relative error of the tf32 / bf16 dot product w.r.t. ||x|| ||q||
     // bf16 operand mode (qh != nullptr): the next phase's threshold goes into the query mirror's aux columns
-    unsigned short *qh;     // [b][ld_h]
-    uint32_t ld_h, kd;
+    unsigned char *qt;      // tiled query mirror of the wave (prep_queries_kernel)
+    uint32_t ld_h, kd, T;
     const float *qcap;      // [b] the finite start threshold (above every surrogate)
     double acc_eps;         // f32 accumulation noise of the folded contraction, relative to |dot| + |thr| + |hx|
 };
@@ -928,12 +1119,13 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
             p.gcnt[qi] = ncand;
             // (the kept keys are unsorted: the kprime-th one is the select's threshold key)
             float thr = ncand == p.kprime ? ord2f((uint32_t)(ctl->thrkey >> 32)) : __int_as_float(0x7f800000);
-            if (p.qh) {   // bf16 mode: finite thresholds only, folded into the query mirror as three exact parts
+            if (p.qt) {   // bf16 mode: finite thresholds only, folded into the query mirror as three exact parts
                 const float cap = p.qcap[qi];
                 if (!(thr < cap)) thr = cap;
                 unsigned short t[3];
                 thr = split3(thr, t);
-                unsigned short *aux = p.qh + (size_t)qi * p.ld_h + p.kd;
+                // the first three columns of the aux chunk of this query's row in its group's tile
+                unsigned short *aux = reinterpret_cast<unsigned short *>(p.qt + (size_t)(qi / BN) * p.T * KB_B + tiled_offset(qi % BN, p.kd / 8, BN));
                 aux[0] = t[0];
                 aux[1] = t[1];
                 aux[2] = t[2];
@@ -971,7 +1163,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
         }
     }
     if (tid == 0) {
-        int bad = ctl->overflow | (p.qflags[qi] & 1);
+        int bad = (ctl->overflow | (p.qflags[qi] & 1)) ? 1 : 0;
         if (p.n > (uint32_t)ncand) {
             const int kk = (int)p.k < ncand ? (int)p.k : ncand;
             // (no candidate at all -- e.g. a query the tensor-core pass could not represent: flagged below, kk < k)
@@ -985,19 +1177,22 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
             } else if constexpr (COS) {
                 // v = -dot~ * inv~ ;  |v - (-dot/||x||)| <= (eps_dot + 3*2^-24) * ||q||
                 double E = (p.eps_dot + 3.0e-7) * nqs + 1.2e-7 * fabs(u);
-                if (p.qh) E += p.acc_eps * (1.01 * nqs + (double)p.qcap[qi] + fabs(u));
+                if (p.qt) E += p.acc_eps * (1.01 * nqs + (double)p.qcap[qi] + fabs(u));
                 lb = nqs > 0.0 ? __double2float_rd(1.0 + (u - E) / nqs - 1.0e-12) : -1.f;
             } else {
                 // v = hx~ - dot~ ;  |v - (||x||^2/2 - dot)| <= eps_dot*||x||max*||q|| + 2^-23*(||x||max^2/2 + |u|)
                 double E = (p.eps_dot + 2.4e-7) * __dsqrt_rn(xn_max) * nqs + 2.4e-7 * (0.5 * xn_max + fabs(u));
-                if (p.qh) E += p.acc_eps * (__dsqrt_rn(xn_max) * nqs + 0.5 * xn_max + (double)p.qcap[qi] + fabs(u));
+                if (p.qt) E += p.acc_eps * (__dsqrt_rn(xn_max) * nqs + 0.5 * xn_max + (double)p.qcap[qi] + fabs(u));
                 double s = 2.0 * (u - E) + nq;
                 s -= 1.0e-12 * (fabs(s) + nq);
                 lb = s > 0.0 ? __double2float_rd(__dsqrt_rd(s)) : 0.f;
                 if (!(s > 0.0)) lb = -1.f;
             }
-            if (!(lb > T)) bad = 1;
-            if (kk < (int)p.k) bad = 1;
+            if (!(lb > T)) bad |= 4;
+            if (kk < (int)p.k) bad |= 8;
+            if (kDbg && bad && qi < 4)
+                printf("[finish dbg] q %u: bad %d (1 overflow/flag, 4 bound, 8 short) ncand %d u %.6g lb %.6g T %.6g nq %.6g xn_max %.6g\n", qi, bad,
+                       ncand, u, (double)lb, (double)T, nq, xn_max);
         }
         p.status[qi] = bad ? 1 : 0;
     }
@@ -1022,17 +1217,16 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2D tensor [rows][ld] of f32 (bf16 = false) or bf16, box = {one 128-byte swizzle row, box_rows}, zero fill out of bounds
-bool make_map(CUtensorMap *m, const void *base, bool bf16, uint64_t rows, uint32_t ld, uint32_t box_rows) {
+// 2D tensor [rows][ld] of f32, box = {one 128-byte swizzle row, box_rows}, zero fill out of bounds (tf32 mode)
+bool make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t ld, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn || rows == 0) return false;
     cuuint64_t dims[2] = {ld, rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
-    cuuint32_t box[2] = {(cuuint32_t)(bf16 ? KS_H : KS), box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)KS, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 long long *g_dbg_buf = nullptr;
@@ -1048,11 +1242,17 @@ int next_pow2i(int v) {
 uint32_t mirror_kd(uint32_t dim) { return (dim + 15u) & ~15u; }
 uint32_t mirror_ld(uint32_t dim) { return mirror_kd(dim) + AUX_H; }
 
+size_t mirror_bytes(uint64_t rows, uint32_t dim) { return (size_t)((rows + BM - 1) / BM) * (mirror_ld(dim) / UMMA_K_H) * KB_A; }
+
 cudaError_t launch_build_mirror(const ShardView &s, unsigned short *rows_h, uint32_t row0, uint32_t n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    const uint32_t blocks = (n + 7) / 8 < 148u * 16u ? (n + 7) / 8 : 148u * 16u;
+    // whole tiles: the tile that holds row0 is rebuilt from its start; the rows of the last tile beyond s.n become zero rows
+    const uint32_t tile0 = row0 / BM, tile1 = (row0 + n + BM - 1) / BM, ntiles = tile1 - tile0;
+    const uint32_t want = (ntiles * (BM / 8) + 7) / 8;
+    const uint32_t blocks = want < 148u * 16u ? want : 148u * 16u;
     auto fn = s.metric ? build_mirror_kernel<true> : build_mirror_kernel<false>;
-    fn<<<blocks, 256, 0, st>>>(s.rows, s.sq_norm, s.inv_norm, row0, n, s.ld, mirror_kd(s.dim), mirror_ld(s.dim), rows_h);
+    fn<<<blocks, 256, 0, st>>>(s.rows, s.sq_norm, s.inv_norm, tile0, ntiles, s.n, s.ld, mirror_kd(s.dim), mirror_ld(s.dim) / UMMA_K_H,
+                               reinterpret_cast<unsigned char *>(rows_h));
     return cudaGetLastError();
 }
 
@@ -1069,8 +1269,9 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
     // operand mode: bf16 mirrors with folded thresholds when the collection has a mirror, else the stored f32 rows as tf32
     const bool H = s.rows_h != nullptr;
     const uint32_t kd = mirror_kd(s.dim), ld_h = mirror_ld(s.dim);
-    const uint32_t nslab = H ? (ld_h + KS_H - 1) / KS_H : (s.ld + KS - 1) / KS;
-    const uint32_t ksteps_last = H ? (ld_h - (nslab - 1) * KS_H) / UMMA_K_H : (s.ld - (nslab - 1) * KS + UMMA_K - 1) / UMMA_K;
+    const uint32_t nslab = (s.ld + KS - 1) / KS;                                               // tf32 mode: 128-byte K slabs
+    const uint32_t ksteps_last = (s.ld - (nslab - 1) * KS + UMMA_K - 1) / UMMA_K;
+    const uint32_t T = ld_h / UMMA_K_H;                                                        // bf16 mode: K steps per tile
     const uint32_t ntiles = (s.n + BM - 1) / BM;
     uint32_t qgroups = (b + BN - 1) / BN;
     // one CTA per SM; query groups beyond the SM count are handled in waves
@@ -1083,12 +1284,11 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
     // on the CPU, including operands built to sit just under the rounding boundary in every component.
     const double eps_dot = H ? ldexp(1.0, -7) * 1.01 + (double)ld_h * ldexp(1.0, -22) : ldexp(1.0, -9) * 1.01 + (double)s.ld * ldexp(1.0, -22);
 
-    // One CTA per unit (cta_group::1) by default.  VROD_BATCHED_PAIR=1 selects the CTA-pair kernel (cta_group::2,
-    // M = 256): it passes the same parity tests but measured SLOWER on B200 in round 1 (8.1 vs 5.6 ms per batch at
-    // configs[2]: the MMA issue time per tile did not drop and the leader waits for operand slabs ~50 % of the
-    // time), so it stays an experiment until that is understood.
-    static const bool want_pair = getenv("VROD_BATCHED_PAIR") != nullptr;
-    const uint32_t psz = (want_pair && !H && !(sm_count & 1)) ? 2u : 1u;
+    // One CTA per unit (cta_group::1).  The CTA-pair form of the tf32 kernel (cta_group::2, M = 256; the template's
+    // PSZ = 2 paths) passed parity but measured slower in round 1 and is no longer instantiated: tools/mma_probe.cu
+    // shows a single CTA already issues its M = 128 x N = 256 MMAs at the tensor core's full rate (128.0 cycles each)
+    // with the operand copies and the accumulator reads running, so pairing has nothing to give here.
+    const uint32_t psz = 1u;
     const uint32_t max_units = (uint32_t)sm_count / psz;
     const uint32_t super_tiles = (ntiles + psz - 1) / psz;
 
@@ -1108,8 +1308,8 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         const size_t cnt_bytes = (size_t)grid * BN * sizeof(int);
         const size_t flag_bytes = (((size_t)bq * sizeof(int)) + 255) & ~(size_t)255;
         const size_t glist_bytes = (size_t)bq * kprime * sizeof(unsigned long long);
-        const size_t qh_bytes = H ? ((((size_t)bq * ld_h * sizeof(unsigned short)) + 255) & ~(size_t)255) : 0;
-        const size_t need = cand_bytes + cnt_bytes + 4 * flag_bytes + glist_bytes + qh_bytes + 256;
+        const size_t qh_bytes = H ? (size_t)groups * T * KB_B : 0;                    // tiled query mirror of the wave
+        const size_t need = cand_bytes + cnt_bytes + 4 * flag_bytes + glist_bytes + qh_bytes + 2048;
         if (*scratch_bytes < need) {
             if (*scratch) cudaFree(*scratch);
             *scratch = nullptr;
@@ -1126,19 +1326,22 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         float *gthr = reinterpret_cast<float *>(base + cand_bytes + cnt_bytes + 2 * flag_bytes);
         float *qcap = reinterpret_cast<float *>(base + cand_bytes + cnt_bytes + 3 * flag_bytes);
         unsigned long long *glist = reinterpret_cast<unsigned long long *>(base + cand_bytes + cnt_bytes + 4 * flag_bytes);
-        unsigned short *qh = reinterpret_cast<unsigned short *>(base + cand_bytes + cnt_bytes + 4 * flag_bytes + glist_bytes);
+        // (kept 1 KB aligned: bulk copies need 16-byte aligned sources)
+        unsigned char *qt = base + ((cand_bytes + cnt_bytes + 4 * flag_bytes + glist_bytes + 1023) & ~(size_t)1023);
         e = cudaMemsetAsync(qflags, 0, flag_bytes, st);
         if (e != cudaSuccess) return e;
 
         CUtensorMap tmX, tmQ;
         if (H) {
-            if (!make_map(&tmX, s.rows_h, true, s.n, ld_h, BM) || !make_map(&tmQ, qh, true, bq, ld_h, BN)) return cudaErrorInvalidValue;
+            memset(&tmX, 0, sizeof(tmX));   // the bf16 mode moves its operands with plain bulk copies: no tensor maps
+            memset(&tmQ, 0, sizeof(tmQ));
             auto prep = s.metric ? prep_queries_kernel<true> : prep_queries_kernel<false>;
             const char *dbg = kDbg ? getenv("VROD_BATCHED_DEBUG") : nullptr;
             const bool nocand = dbg && (strstr(dbg, "nocand") || strstr(dbg, "noepi") || strstr(dbg, "nomma") || strstr(dbg, "ldonly"));
-            prep<<<(bq + 7) / 8, 256, 0, st>>>(qw, bq, s.ld, kd, ld_h, s.maxnorm_bits, qh, gthr, qcap, nocand ? -1.f : 1.f);
+            const uint32_t slots = groups * BN;
+            prep<<<(slots + 7) / 8, 256, 0, st>>>(qw, bq, slots, s.ld, kd, T, s.maxnorm_bits, qt, gthr, qcap, nocand ? -1.f : 1.f);
             if (stats) stats->launches += 1;
-        } else if (!make_map(&tmX, s.rows, false, s.n, s.ld, BM) || !make_map(&tmQ, qw, false, bq, s.ld, BN / psz)) {
+        } else if (!make_map(&tmX, s.rows, s.n, s.ld, BM) || !make_map(&tmQ, qw, bq, s.ld, BN / psz)) {
             return cudaErrorInvalidValue;
         }
 
@@ -1164,15 +1367,44 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             p.dbg = dbg ? dbg_buf : nullptr;
             if (dbg) g_dbg_buf = dbg_buf;
         }
-        // dim <= 128: the query group is resident (nslab x 32 KB) and only row slabs stream; larger dims stream the
-        // query slab next to every row slab (48 KB stages, L2-bandwidth bound: DESIGN.md)
-        p.stream_q = nslab > (uint32_t)(H ? MAX_SLABS_H : MAX_SLABS) ? 1 : 0;
-        const size_t slab_b = (size_t)slab_b_bytes((int)psz);
-        const size_t resident = p.stream_q ? 0 : (size_t)nslab * slab_b;
-        const size_t stage_bytes = p.stream_q ? (SLAB_A_BYTES + slab_b) : SLAB_A_BYTES;
+        const size_t smem_budget = 227 * 1024 - sizeof(BatchCtl);
+        size_t resident, stage_bytes;
+        if (H) {
+            // bf16 mode.  The query group stays resident (T x 8 KB) whenever at least 3 stages of >= 2 K steps fit next
+            // to it (dim + 16 <= ~400); a stage then holds S K-step blocks of the row tile -- the whole tile when it
+            // fits 4 times (dim = 128: 4 stages x 36 KB next to 72 KB of queries).  Larger dims stream S = 4 K steps
+            // of both operands per stage (48 KB).
+            p.rows_t = reinterpret_cast<const unsigned char *>(s.rows_h);
+            p.q_t = qt;
+            p.T = T;
+            uint32_t S = 0;
+            const size_t qres = (size_t)T * KB_B;
+            if (qres + 3 * 2 * KB_A <= smem_budget) {
+                for (S = T; S >= 2; --S)
+                    if ((smem_budget - qres) / ((size_t)S * KB_A) >= (S == 2 ? 3u : 4u)) break;
+            }
+            if (S >= 2) {
+                p.stream_q = 0;
+                resident = qres;
+                stage_bytes = (size_t)S * KB_A;
+            } else {
+                S = T < 4 ? T : 4;
+                p.stream_q = 1;
+                resident = 0;
+                stage_bytes = (size_t)S * (KB_A + KB_B);
+            }
+            p.S = S;
+        } else {
+            // tf32 mode, dim <= 128: the query group is resident (nslab x 32 KB) and only row slabs stream; larger dims
+            // stream the query slab next to every row slab (48 KB stages, L2-bandwidth bound: DESIGN.md)
+            p.stream_q = nslab > (uint32_t)MAX_SLABS ? 1 : 0;
+            const size_t slab_b = (size_t)slab_b_bytes((int)psz);
+            resident = p.stream_q ? 0 : (size_t)nslab * slab_b;
+            stage_bytes = p.stream_q ? (SLAB_A_BYTES + slab_b) : SLAB_A_BYTES;
+        }
         // (dynamic shared memory starts 1024-byte aligned -- the kernel has no static shared memory and traps
-        // otherwise -- so no alignment slack is reserved: at dim 128 that is what makes the 6th stage fit)
-        size_t stages = (227 * 1024 - resident - sizeof(BatchCtl)) / stage_bytes;
+        // otherwise -- so no alignment slack is reserved: at dim 128 in tf32 mode that is what makes the 6th stage fit)
+        size_t stages = (smem_budget - resident) / stage_bytes;
         {
             static const int st_env = getenv("VROD_BATCHED_STAGES") ? atoi(getenv("VROD_BATCHED_STAGES")) : 0;
             if (st_env >= 2 && (size_t)st_env < stages) stages = (size_t)st_env;
@@ -1181,11 +1413,14 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         if (stages < 2) return cudaErrorInvalidConfiguration;
         p.stages = (uint32_t)stages;
         const size_t smem = resident + stages * stage_bytes + sizeof(BatchCtl);
-        void (*tile_fn)(const CUtensorMap, const CUtensorMap, const BatchedParams) =
-            H          ? (s.metric ? batched_tile_kernel<true, 1, true> : batched_tile_kernel<false, 1, true>)
-            : psz == 2 ? (s.metric ? batched_tile_kernel<true, 2, false> : batched_tile_kernel<false, 2, false>)
-                       : (s.metric ? batched_tile_kernel<true, 1, false> : batched_tile_kernel<false, 1, false>);
+        typedef void (*TileFn)(const CUtensorMap, const CUtensorMap, const BatchedParams);
+        const TileFn tile_fn = H ? (s.metric ? batched_tile_kernel<true, 1, true, false> : batched_tile_kernel<false, 1, true, false>)
+                                 : (s.metric ? batched_tile_kernel<true, 1, false, false> : batched_tile_kernel<false, 1, false, false>);
+        // the start phase (one tile per CTA, everything passes) has its own epilogue
+        const TileFn tile_fn_first = H ? (s.metric ? batched_tile_kernel<true, 1, true, true> : batched_tile_kernel<false, 1, true, true>)
+                                       : (s.metric ? batched_tile_kernel<true, 1, false, true> : batched_tile_kernel<false, 1, false, true>);
         e = cudaFuncSetAttribute(tile_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_fn_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         cudaLaunchConfig_t cfg{};
         cudaLaunchAttribute cattr[1];
@@ -1226,9 +1461,10 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         f.out_ids = out_ids ? out_ids + (size_t)g0 * BN * k : nullptr;
         f.out_dist = out_dist ? out_dist + (size_t)g0 * BN * k : nullptr;
         f.eps_dot = eps_dot;
-        f.qh = H ? qh : nullptr;
+        f.qt = H ? qt : nullptr;
         f.ld_h = ld_h;
         f.kd = kd;
+        f.T = T;
         f.qcap = qcap;
         f.acc_eps = H ? (double)(ld_h / UMMA_K_H + 2) * ldexp(1.0, -23) : 0.0;
         const size_t fsmem = kFinCtl + (size_t)f.cap * sizeof(unsigned long long) + ((size_t)kFinHist + (size_t)cpg_max * psz + 2) * sizeof(int);
@@ -1246,7 +1482,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             p.tile_begin = t_begin;
             p.tile_end = t_end;
             p.thr_init = (first && !H) ? nullptr : gthr;   // bf16 mode starts from the finite caps of prep_queries_kernel
-            e = cudaLaunchKernelEx(&cfg, tile_fn, tmX, tmQ, p);
+            e = cudaLaunchKernelEx(&cfg, first ? tile_fn_first : tile_fn, tmX, tmQ, p);
             if (e != cudaSuccess) return e;
             f.first_phase = first ? 1 : 0;
             f.final_phase = last ? 1 : 0;

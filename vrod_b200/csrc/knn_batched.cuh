@@ -16,7 +16,10 @@ struct BatchedStats {
 // bf16 operand mirror of the rows (see knn_batched.cu): kd = dim rounded up to 16 data columns + 16 aux columns
 uint32_t mirror_kd(uint32_t dim);
 uint32_t mirror_ld(uint32_t dim);
-// rows [row0, row0 + n) of the shard -> rows_h ([.. x mirror_ld] bf16); needs the rows' norms (launch_row_norms)
+// bytes of the TILED mirror of `rows` rows (128-row tiles x mirror_ld/16 K-step blocks of 4 KB, see knn_batched.cu)
+size_t mirror_bytes(uint64_t rows, uint32_t dim);
+// rows [row0, row0 + n) of the shard -> the tiles of rows_h that hold them (whole tiles are rewritten; rows beyond s.n
+// become zero rows); needs the rows' norms (launch_row_norms)
 cudaError_t launch_build_mirror(const ShardView &s, unsigned short *rows_h, uint32_t row0, uint32_t n, cudaStream_t st);
 
 // Can the tensor-core path answer this (shape, k) at all?

@@ -1206,7 +1206,7 @@ static vrod_status local_enqueue(vrod_collection *c, const float *d_q, uint32_t 
                 // VROD_NO_MIRROR=1 behaves like a failed allocation (tests of the fallback; memory-tight deployments)
                 static const bool no_mirror = getenv("VROD_NO_MIRROR") != nullptr;
                 const cudaError_t me = no_mirror ? cudaErrorMemoryAllocation
-                                                 : cudaMalloc(&c->rows_h, (size_t)c->shard_rows * mirror_ld(c->dim) * sizeof(unsigned short));
+                                                 : cudaMalloc(&c->rows_h, mirror_bytes(c->shard_rows, c->dim));
                 if (me != cudaSuccess) {
                     cudaGetLastError();
                     c->rows_h = nullptr;

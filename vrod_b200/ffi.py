@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvrod_knn.so")
+# VROD_LIB: development override (e.g. the `make debug` build with the kernels' timing stamps compiled in)
+LIB_PATH = os.environ.get("VROD_LIB") or os.path.join(_HERE, "libvrod_knn.so")
 
 OK, EINVAL, ENOTFOUND, EEXISTS, ENOMEM, ECUDA, ENCCL, ENOGPU = range(8)
 EUCLIDEAN, COSINE = 0, 1
