@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, call G (1 GPU): batched parity + phase counters + cfg2 bench (32-slot stash, dense start-phase kernel)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_batched.py -q -m gpu -x 2>&1 | tail -5
+timeout 300 python -m pytest tests/test_gpu_batched.py -q -m gpu -x --timeout 120 2>&1 | tail -5
 export VROD_LIB=$PWD/vrod_b200/libvrod_knn_dbg.so
 for M in 1 nocand; do
   echo "=== VROD_BATCHED_DEBUG=$M"

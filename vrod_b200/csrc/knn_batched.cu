@@ -45,8 +45,10 @@ constexpr int UMMA_K = 8;        // tf32
 constexpr int CAP = 1024;        // candidate keys per (CTA, query)
 constexpr int kCheckEvery = 4;     // tiles between two list-maintenance points of the epilogue warps
 constexpr int PRUNE_AT = CAP - (kCheckEvery + 2) * BM;   // lists longer than this ask for a prune at the next point
-constexpr int kEpiWarps = 8;     // two per TMEM lane quadrant (each takes half of the 256 columns)
-constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..9 epilogue
+constexpr int kEpiWarps = 16;    // four per TMEM lane quadrant, each takes 64 of the 256 columns (two 32-column blocks per tile)
+// warp 0 TMA / bulk copies, warp 1 MMA + TMEM alloc, warps 2..17 epilogue, warp 18 second MMA issuer (bf16 mode)
+constexpr int kThreads = 64 + 32 * kEpiWarps + 32;
+constexpr int kIssuer2 = kThreads / 32 - 1;
 constexpr int SLAB_A_BYTES = BM * KS * 4;   // 16 KB: 128 rows x 128 B
 // query slab of one CTA: all BN queries (32 KB) alone, its half (16 KB) in a CTA pair
 __host__ __device__ constexpr int slab_b_bytes(int psz) { return BN / psz * KS * 4; }
@@ -231,21 +233,28 @@ __host__ __device__ constexpr uint32_t idesc_bf16() {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-// Deferred appends: an epilogue warp that finds a candidate in a 32-column block does NOT stop to append it while it
-// still holds the accumulator stage -- every such stop (shared-memory atomics, a global store, cold code) delayed the
-// stage's release and with it the MMA warp: ~90 cycles per candidate, 30 % of a configs[2] batch in round 2's first
-// measurement.  The hitting lane parks its 32 scores in a small per-warp stash instead (32 predicated STS with static
-// register indices) and the warp empties the stash after it has handed the stage back.
-constexpr int kStash = 32;                // parked blocks per warp: one per lane, so any block can be parked whole
-struct StashSlot {      // 35 words: lane e reads word j of slot e from bank (3e + j) mod 32 -- conflict-free across the warp
-    float score[32];
+// Deferred appends.  A candidate costs the warp that finds it 1000-2000 cycles (shared-memory atomics, a global store,
+// above all COLD code: instruction fetch), and the accumulator stage it reads goes back to the MMA warp only when all
+// epilogue warps are done with it: with 8 warps of 128 columns each (~850 busy cycles per tile) every candidate stalled
+// the tensor core ~90 cycles -- 20-30 % of a configs[2] batch.  Two changes keep the rare path off the MMA's critical
+// path: (1) sixteen epilogue warps of 64 columns each (~400 busy cycles per ~1400-cycle tile), so a late warp has slack;
+// (2) the hitting lane only PARKS its 32 scores in a small per-warp stash (32 predicated STS with static register
+// indices) and the warp empties the stash after it has handed the stage back.  A warp may then be late by two tile
+// times minus twice its own work before the MMA warp notices.
+constexpr int kStash = 4;                 // parked blocks per warp; fuller blocks (the dense early phases) go in rounds
+struct StashSlot {      // 140 bytes: 16 warps x 4 slots make the control block 11264 bytes, which leaves EXACTLY four 36 KB
+    float score[32];    // stages next to the 72 KB query operand at dim = 128 (227 KB of shared memory)
     uint32_t row, colbase;
     float hx;
 };
 static_assert(sizeof(StashSlot) == 140, "stash slot size");
 struct BatchCtl {
     uint64_t full[8], empty[8], tfull[2], tempty[2], qfull;
-    uint64_t pfull[8], pqfull;   // leader's view of the PEER's slabs / query slabs (CTA pairs only)
+    union {
+        uint64_t pfull[8];       // leader's view of the PEER's slabs (CTA pairs only; not instantiated any more)
+        int pflag[4];            // per 64-column part: one of its lists is long, prune at the next maintenance point
+    };
+    uint64_t pqfull;
     uint32_t tmem_base;
     int flag;
     alignas(16) float thr[BN];
@@ -366,40 +375,27 @@ __device__ __forceinline__ float block_max_h(const uint32_t (&r)[32]) {
 // ping-pong loop -- and (c) kept off the accumulator's critical path (stash, above).  (Round 1's register-resident
 // append -- a 31-select tree per candidate, inlined twice, plus a separate dense-block form -- was 35 KB of the kernel.)
 
-// Empty a warp's stash: lane e appends the survivors of parked block e.  Eight scores are fetched at a time (independent
-// shared-memory loads) and turned into a bit mask; only the set bits reach the append body.
+// Empty a warp's stash, one parked block (= one row x 32 query columns) at a time with the lanes across the COLUMNS: lane j
+// tests column j and appends it if it passed.  No inner loops, no per-lane scans: the whole function is ~40
+// instructions, the same for one parked block or for a dense one.
 template <bool COS, bool H>
-__device__ __noinline__ void stash_flush(int nst, StashSlot *slots, BatchCtl *ctl, unsigned long long *cand, int *qflags, uint32_t qbase,
-                                         uint32_t b, int lane) {
-    if (lane < nst) {
-        const StashSlot &e = slots[lane];
-        const float *thr = ctl->thr + e.colbase;
-        const float hx = e.hx;
+__device__ __noinline__ void stash_flush(int first, int nst, const StashSlot *slots, BatchCtl *ctl, unsigned long long *cand, int *qflags,
+                                         uint32_t qbase, uint32_t b, int lane) {
 #pragma unroll 1
-        for (int j0 = 0; j0 < 32; j0 += 8) {
-            float d[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) d[u] = e.score[j0 + u];
-            uint32_t mask = 0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                bool hit;
-                if constexpr (H) hit = d[u] > 0.f;
-                else hit = cand_hit<COS>(cand_w<COS>(d[u], thr[j0 + u], hx), hx);
-                mask |= hit ? (1u << u) : 0u;
-            }
-#pragma unroll 1
-            while (mask) {
-                const int j = j0 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                const float dot = e.score[j];
-                const int q = (int)e.colbase + j;
-                const int pos = atomicAdd(&ctl->cnt[q], 1);
-                if (pos >= PRUNE_AT) *(volatile int *)&ctl->flag = 1;
-                const float v = H ? (thr[j] - dot) : (COS ? -(dot * hx) : (hx - dot));
-                if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, e.row));
-                else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
-            }
+    for (int e = first; e < first + nst; ++e) {
+        const StashSlot &sl = slots[e & (kStash - 1)];
+        const float dot = sl.score[lane];
+        const int q = (int)sl.colbase + lane;
+        const float thr = ctl->thr[q], hx = sl.hx;
+        bool hit;
+        if constexpr (H) hit = dot > 0.f;
+        else hit = cand_hit<COS>(cand_w<COS>(dot, thr, hx), hx);
+        if (hit) {
+            const int pos = atomicAdd(&ctl->cnt[q], 1);
+            if (pos >= PRUNE_AT) *(volatile int *)&ctl->pflag[q >> 6] = 1;
+            const float v = H ? (thr - dot) : (COS ? -(dot * hx) : (hx - dot));
+            if (pos < CAP) __stcg(cand + (size_t)q * CAP + pos, make_key(v, sl.row));
+            else if (qbase + q < b) atomicOr(qflags + qbase + q, 1);   // cannot happen; checked
         }
     }
     __syncwarp();
@@ -443,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
     if (tid == 0) {
         for (uint32_t s = 0; s < p.stages; ++s) {
             mbar_init(&ctl->full[s], 1);             // this CTA's own TMA (local transaction bytes)
-            mbar_init(&ctl->pfull[s], 1);            // pair leader only: the peer's forwarder arrives here
+            if (PSZ == 2) mbar_init(&ctl->pfull[s], 1);   // pair leader only: the peer's forwarder arrives here
             mbar_init(&ctl->empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -453,6 +449,8 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
         mbar_init(&ctl->qfull, 1);
         mbar_init(&ctl->pqfull, 1);
         ctl->flag = 0;
+        if (PSZ == 1)
+            for (int w = 0; w < 4; ++w) ctl->pflag[w] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < BN; i += kThreads) {
@@ -533,30 +531,39 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             }
             if (kDbg && p.dbg) p.dbg[blockIdx.x * 16 + 9] = w_empty;
         }
-    } else if (warp == 1 && H) {
+    } else if ((warp == 1 || warp == kIssuer2) && H) {
         // ===== bf16 mode MMA issuer.  The whole warp runs the loop converged (waits included) and ONE elected lane
         // issues; the operand descriptors advance by a single add on their low word.  Round 1 issued from inside an
         // `if (lane == 0)` region and rebuilt both 64-bit descriptors from byte addresses for every MMA: ~18 dependent
         // uniform-datapath instructions per tcgen05.mma, 214 cycles per MMA where the tensor core needs 128
         // (tools/mma_probe.cu measures 128.0 with operands, bulk copies and tcgen05.ld all running). =====
+        // TWO issuing warps, alternating tiles (warp 1: even tiles, accumulator stage 0; the last warp: odd tiles, stage 1).
+        // Between the last MMA of a tile and the first of the next a single issuer has two barrier waits (~90 cycles each
+        // even when long complete), a fence and an election to get through, and the tensor core's queue is too shallow to
+        // cover them: ~250 idle cycles per 9-MMA tile (moving the waits between the MMAs of the previous tile only moved
+        // the bubble).  With two issuers one of them is always past its waits, its first MMA pending at the issue port
+        // while the other's tile executes.  Tiles use different accumulator stages and every tcgen05.commit covers the
+        // MMAs of its own thread, so the two streams need no ordering between them.
         if (!p.stream_q) mbar_wait(&ctl->qfull, 0);
         const uint32_t ns = (p.T + p.S - 1) / p.S;
         const uint32_t q_lo = plain_desc_lo(smem_u32(q_s));
         const uint32_t a_lo0 = plain_desc_lo(smem_u32(a_s));
         const uint32_t stage_step = stage_bytes >> 4;
         const uint32_t idesc = idesc_bf16();
-        uint32_t stage = 0, phase = 0;
+        const uint32_t acc = warp == 1 ? 0u : 1u;          // this issuer's tiles: acc, acc + 2, ...
+        const uint32_t d_tmem = tmem + acc * BN;
         long long w_tempty = 0, w_full = 0;
         const long long tstart = kDbg ? clock64() : 0;
-        for (uint32_t i = 0; i < my_tiles; ++i) {
-            const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
+        uint32_t aphase = 0;
+        for (uint32_t i = acc; i < my_tiles; i += 2, aphase ^= 1) {
             long long t0 = (kDbg && p.dbg) ? clock64() : 0;
             mbar_wait(&ctl->tempty[acc], aphase ^ 1);
             if (kDbg && p.dbg) w_tempty += clock64() - t0;
             tc_fence_after();
-            const uint32_t d_tmem = tmem + acc * BN;
             uint32_t ks = 0;
             for (uint32_t st = 0; st < ns; ++st) {
+                const uint32_t u = i * ns + st;                        // position in the CTA's stream of stage fills
+                const uint32_t stage = u % p.stages, phase = (u / p.stages) & 1u;
                 const uint32_t nk = p.T - ks < p.S ? p.T - ks : p.S;
                 t0 = (kDbg && p.dbg) ? clock64() : 0;
                 mbar_wait(&ctl->full[stage], phase);
@@ -575,14 +582,15 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 }
                 __syncwarp();
                 ks += nk;
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
-        if (kDbg && p.dbg && lane == 0) {
+        if (kDbg && p.dbg && lane == 0 && warp == 1) {
             p.dbg[blockIdx.x * 16 + 5] = w_tempty;
             p.dbg[blockIdx.x * 16 + 6] = w_full;
             p.dbg[blockIdx.x * 16 + 1] = clock64() - tstart;
         }
+    } else if (warp == kIssuer2) {
+        // (tf32 mode: the second issuer warp of the bf16 mode has nothing to do)
     } else if (warp == 1) {
         // ===== peer CTA of a pair: forward "my slab has landed" to the leader, one remote arrive per slab =====
         if (lane == 0 && !leader) {
@@ -654,8 +662,8 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
     } else {
         // ===== epilogue warps: TMEM -> registers -> threshold filter -> candidate lists =====
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
-        const int ew = warp - 2;                     // 0..7
-        const int half = ew >> 2;                    // which 128 of the 256 query columns
+        const int ew = warp - 2;                     // 0..15
+        const int part = ew >> 2;                    // which 64 of the 256 query columns
         unsigned long long *cand = p.cand + (size_t)blockIdx.x * BN * CAP;
         long long w_tfull = 0, w_prune = 0, n_slow = 0;
         const long long tstart = kDbg ? clock64() : 0;
@@ -667,6 +675,10 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             return COS ? __ldg(p.inv_norm + r) : __ldg(p.sq_norm + r);
         };
         float hx_next = my_tiles ? row_factor(tile_of(0) * BM + quad * 32 + lane) : 0.f;
+        StashSlot *slots = ctl->stash[ew];
+        const int col0 = part * (BN / 4);
+        const float *thr_p = ctl->thr + col0;
+        const float ninf = -__int_as_float(0x7f800000);
         for (uint32_t i = 0; i < my_tiles; ++i) {
             const uint32_t tile = tile_of(i);
             const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
@@ -678,27 +690,20 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             mbar_wait(&ctl->tfull[acc], aphase);
             if (kDbg && p.dbg) w_tfull += clock64() - t0;
             tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * BN + half * (BN / 2);
-            // Hot loop: branch-free filter of this warp's 32 rows x 128 columns, 32 columns at a time, the next
-            // TMEM load in flight while the current block is compared.  Not unrolled, rare path marked unlikely
-            // (placed out of line): the body must stay inside the instruction cache (a fully unrolled version
-            // was 130 KB of SASS and ran at ~0.04 IPC on instruction fetch).
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * BN + col0;
             uint32_t ra[32], rb[32];
             int nst = 0;                                  // parked blocks of this warp in this tile (warp-uniform)
-            int cur_col = 0;                              // first query column of the block being filtered
-            StashSlot *slots = ctl->stash[ew];
             // A block with candidates.  Usually one lane with one candidate: the lane parks its 32 scores and the warp moves
-            // on.  More hitting lanes than free slots (the dense early phases, where every row passes every column): park
-            // in rounds of kStash lanes and empty the stash in between -- that holds the accumulator stage, but only where
-            // a CTA has a handful of tiles anyway.
-            auto on_hit = [&](const uint32_t (&r)[32], bool hit) {
+            // on.  More hitting lanes than free slots (the dense early phases): park in rounds of kStash lanes and empty the
+            // stash in between -- that holds the accumulator stage, but only where a CTA has a handful of tiles anyway.
+            auto on_hit = [&](const uint32_t (&r)[32], bool hit, int colbase) {
                 const unsigned hm = __ballot_sync(kFull, hit);
                 const int nh = __popc(hm), rank = __popc(hm & ((1u << lane) - 1u));
                 int done = 0;
 #pragma unroll 1
                 while (done < nh) {
                     if (nst == kStash) {
-                        stash_flush<COS, H>(nst, slots, ctl, cand, p.qflags, g * BN, p.b, lane);
+                        stash_flush<COS, H>(0, nst, slots, ctl, cand, p.qflags, g * BN, p.b, lane);
                         nst = 0;
                     }
                     const int take = min(kStash - nst, nh - done);
@@ -707,7 +712,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
 #pragma unroll
                         for (int j = 0; j < 32; ++j) e.score[j] = __uint_as_float(r[j]);
                         e.row = row;
-                        e.colbase = (uint32_t)cur_col;
+                        e.colbase = (uint32_t)colbase;
                         e.hx = hx;
                     }
                     nst += take;
@@ -715,17 +720,14 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                     __syncwarp();
                 }
             };
-            const float *thr_h = ctl->thr + half * (BN / 2);
-            const float ninf = -__int_as_float(0x7f800000);
-            const int col_h = half * (BN / 2);
             if constexpr (DENSE) {
                 const int rt = quad * 32 + lane;   // row inside the tile = its position in every list
 #pragma unroll 1
-                for (int cb = 0; cb < BN / 64; ++cb) {
+                for (int cb = 0; cb < 2; ++cb) {
                     tc_ld32(taddr + cb * 32, ra);
                     tc_wait_ld();
-                    unsigned long long *dst = cand + (size_t)(col_h + cb * 32) * CAP + rt;
-                    const float *thr_b = thr_h + cb * 32;
+                    unsigned long long *dst = cand + (size_t)(col0 + cb * 32) * CAP + rt;
+                    const float *thr_b = thr_p + cb * 32;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float dot = __uint_as_float(ra[j]);
@@ -733,35 +735,28 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                         if (rowok) __stcg(dst + (size_t)j * CAP, make_key(v, row));
                     }
                 }
-                if (quad == 0 && lane == 0 && half == 0) {
+                if (ew == 0 && lane == 0) {
                     const uint32_t left = p.n - tile * BM;
                     ctl->flag = (int)(left < (uint32_t)BM ? left : (uint32_t)BM);   // rows of this tile = entries of every list
                 }
             } else if (!(kDbg && (p.debug_skip & 1))) {
+                // Hot path: both 32-column blocks of this warp are fetched at once, then a branch-free max filter per block;
+                // a block with a candidate (rare) is parked.  Straight-line, a few dozen instructions.
                 tc_ld32(taddr, ra);
+                tc_ld32(taddr + 32, rb);
                 tc_wait_ld();
-#pragma unroll 1
-                for (int cb = 0; cb < BN / 64; cb += 2) {
-                    tc_ld32(taddr + (cb + 1) * 32, rb);
-                    float wa = H ? block_max_h(ra) : block_max<COS>(ra, thr_h + cb * 32, hx, ninf);
-                    if (kDbg && (p.debug_skip & 4)) wa = __uint_as_float(ra[0] & ra[31] & 0x80000000u) - 1.f;   // ldonly: no scan of the block
-                    const bool hita = (H ? wa > 0.f : cand_hit<COS>(wa, hx)) && rowok;
-                    if (__builtin_expect(__any_sync(kFull, hita), 0)) {
-                        if (kDbg) n_slow++;
-                        cur_col = col_h + cb * 32;
-                        on_hit(ra, hita);
-                    }
-                    tc_wait_ld();
-                    if (cb + 2 < BN / 64) tc_ld32(taddr + (cb + 2) * 32, ra);
-                    float wb = H ? block_max_h(rb) : block_max<COS>(rb, thr_h + (cb + 1) * 32, hx, ninf);
-                    if (kDbg && (p.debug_skip & 4)) wb = __uint_as_float(rb[0] & rb[31] & 0x80000000u) - 1.f;
-                    const bool hitb = (H ? wb > 0.f : cand_hit<COS>(wb, hx)) && rowok;
-                    if (__builtin_expect(__any_sync(kFull, hitb), 0)) {
-                        if (kDbg) n_slow++;
-                        cur_col = col_h + (cb + 1) * 32;
-                        on_hit(rb, hitb);
-                    }
-                    if (cb + 2 < BN / 64) tc_wait_ld();
+                float wa = H ? block_max_h(ra) : block_max<COS>(ra, thr_p, hx, ninf);
+                float wb = H ? block_max_h(rb) : block_max<COS>(rb, thr_p + 32, hx, ninf);
+                if (kDbg && (p.debug_skip & 4)) {   // ldonly: no scan of the blocks
+                    wa = __uint_as_float(ra[0] & ra[31] & 0x80000000u) - 1.f;
+                    wb = __uint_as_float(rb[0] & rb[31] & 0x80000000u) - 1.f;
+                }
+                const bool hita = (H ? wa > 0.f : cand_hit<COS>(wa, hx)) && rowok;
+                const bool hitb = (H ? wb > 0.f : cand_hit<COS>(wb, hx)) && rowok;
+                if (__builtin_expect(__any_sync(kFull, hita || hitb), 0)) {
+                    if (kDbg) n_slow++;
+                    if (__any_sync(kFull, hita)) on_hit(ra, hita, col0);
+                    if (__any_sync(kFull, hitb)) on_hit(rb, hitb, col0 + 32);
                 }
             }
             // accumulator stage drained: hand it back to the MMA warp (of the leader CTA)
@@ -771,23 +766,26 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 if (leader) mbar_arrive(&ctl->tempty[acc]);
                 else mbar_arrive_leader(&ctl->tempty[acc]);
             }
+
             // the stage is back with the MMA warp: now the parked candidates
             if (nst) {
                 __syncwarp();
-                stash_flush<COS, H>(nst, slots, ctl, cand, p.qflags, g * BN, p.b, lane);
+                stash_flush<COS, H>(0, nst, slots, ctl, cand, p.qflags, g * BN, p.b, lane);
             }
-            // list maintenance every kCheckEvery tiles (all epilogue warps; the lists have room for the
-            // appends of the tiles in between, see PRUNE_AT)
+            // list maintenance every kCheckEvery tiles, per 64-column part: the four warps that append to the lists of a
+            // part (one per lane quadrant) meet at the part's own named barrier -- not all sixteen, so a warp that is late
+            // after a flush holds up three others, not the whole epilogue.  The lists have room for the appends of the
+            // tiles in between (PRUNE_AT).
             if (DENSE || (i + 1) % kCheckEvery != 0) continue;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (*(volatile int *)&ctl->flag) {
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
+            if (*(volatile int *)&ctl->pflag[part]) {
                 t0 = kDbg ? clock64() : 0;
-                for (int q = ew; q < BN; q += kEpiWarps) {
+                for (int q = col0 + quad; q < col0 + BN / 4; q += 4) {
                     if (ctl->cnt[q] > PRUNE_AT / 2) prune_list<H>(cand + (size_t)q * CAP, q, ctl, p.kprime, lane);
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (ew == 0 && lane == 0) ctl->flag = 0;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
+                if (quad == 0 && lane == 0) ctl->pflag[part] = 0;
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
                 if (kDbg) w_prune += clock64() - t0;
             }
         }
@@ -802,7 +800,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             p.dbg[blockIdx.x * 16 + 4] = w_prune;
 
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 5, 512;" ::: "memory");   // all epilogue warps (ids 1..4 are the parts' own barriers)
         for (int q = ew * 32 + lane; q < BN; q += 32 * kEpiWarps) {
             const int c = DENSE ? *(volatile int *)&ctl->flag : ctl->cnt[q];
             p.cnt_out[(size_t)blockIdx.x * BN + q] = c < CAP ? c : CAP;
