@@ -550,12 +550,19 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
         const uint32_t a_lo0 = plain_desc_lo(smem_u32(a_s));
         const uint32_t stage_step = stage_bytes >> 4;
         const uint32_t idesc = idesc_bf16();
-        const uint32_t acc = warp == 1 ? 0u : 1u;          // this issuer's tiles: acc, acc + 2, ...
-        const uint32_t d_tmem = tmem + acc * BN;
+        // (Only when a stage is a whole tile, ns == 1: an issuer then never asks for a stage fill more than `stages` fills
+        // ahead of the ring, which is what keeps a PARITY wait unambiguous.  With several fills per tile the second issuer
+        // would start on fill ns while the ring is at fill 0 -- a fresh barrier answers "parity 1 complete" at once -- so
+        // there warp 1 issues every tile, as before.)
+        const bool dual = ns == 1;
+        if (!dual && warp != 1) goto issuer_done;
+        {
+        const uint32_t first = (dual && warp != 1) ? 1u : 0u, step = dual ? 2u : 1u;
         long long w_tempty = 0, w_full = 0;
         const long long tstart = kDbg ? clock64() : 0;
-        uint32_t aphase = 0;
-        for (uint32_t i = acc; i < my_tiles; i += 2, aphase ^= 1) {
+        for (uint32_t i = first; i < my_tiles; i += step) {
+            const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
+            const uint32_t d_tmem = tmem + acc * BN;
             long long t0 = (kDbg && p.dbg) ? clock64() : 0;
             mbar_wait(&ctl->tempty[acc], aphase ^ 1);
             if (kDbg && p.dbg) w_tempty += clock64() - t0;
@@ -589,6 +596,8 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             p.dbg[blockIdx.x * 16 + 6] = w_full;
             p.dbg[blockIdx.x * 16 + 1] = clock64() - tstart;
         }
+        }
+    issuer_done:;
     } else if (warp == kIssuer2) {
         // (tf32 mode: the second issuer warp of the bf16 mode has nothing to do)
     } else if (warp == 1) {

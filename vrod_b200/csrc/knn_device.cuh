@@ -110,6 +110,7 @@ struct CandCtl {
     double nq;                  // canonical sum q_j^2 (cosine rerank)
     float u_val;                // value part of the kprime-th approximate key (guard)
     int ncand;
+    unsigned long long thrkey2; // last-CTA merge: the warps' offers for the bound T0
 };
 
 __device__ __forceinline__ void cand_reset(CandCtl *ctl) {
@@ -135,7 +136,41 @@ __device__ __forceinline__ void cand_append(CandCtl *ctl, unsigned long long *bu
 // Pair i of a stage touches elements inside one 64-key block whenever the partner distance j <= 32, and
 // pairs [32w, 32w+32) (+ multiples of kScanThreads) belong to warp w, so those stages only need a warp
 // barrier; a block barrier is needed only around the stages with j >= 64.
+// P <= 64: one warp sorts in registers (two keys per lane, partners by shuffle; the j = 32 exchange is lane-local).  The
+// shared-memory network below pays a load-compare-store-barrier round trip of ~250 cycles per stage however few keys it
+// holds -- 2.8 us for the ~40 survivors of a merge, again for the k' reranked keys: most of a single query's serial tail.
+__device__ __forceinline__ void warp_sort64_regs(unsigned long long &x0, unsigned long long &x1, int P, int lane) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j == 32) {   // k == 64: lanes hold the pair (lane, lane + 32), ascending
+                if (x0 > x1) {
+                    const unsigned long long t = x0;
+                    x0 = x1;
+                    x1 = t;
+                }
+            } else {
+                const unsigned long long o0 = __shfl_xor_sync(kFull, x0, j), o1 = __shfl_xor_sync(kFull, x1, j);
+                const bool low = (lane & j) == 0;
+                const bool asc0 = (lane & k) == 0, asc1 = ((lane + 32) & k) == 0;
+                x0 = (low == asc0) ? (x0 < o0 ? x0 : o0) : (x0 < o0 ? o0 : x0);
+                x1 = (low == asc1) ? (x1 < o1 ? x1 : o1) : (x1 < o1 ? o1 : x1);
+            }
+        }
+    }
+}
+__device__ __forceinline__ void warp_sort64(unsigned long long *a, int P, int lane) {
+    unsigned long long x0 = a[lane], x1 = P > 32 ? a[lane + 32] : kKeyMax;
+    warp_sort64_regs(x0, x1, P, lane);
+    a[lane] = x0;
+    if (P > 32) a[lane + 32] = x1;
+}
+
 __device__ __forceinline__ void block_bitonic(unsigned long long *a, int P, int tid) {
+    if (P <= 64) {
+        if (tid < 32) warp_sort64(a, P, tid);
+        __syncthreads();
+        return;
+    }
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tid; i < (P >> 1); i += kScanThreads) {
@@ -152,16 +187,42 @@ __device__ __forceinline__ void block_bitonic(unsigned long long *a, int P, int 
     }
 }
 
+// n <= kScanThreads keys: every thread ranks its own key against all of them (pairs of keys per 128-bit
+// broadcast load) and writes it to its rank -- a sort in two barriers.  The networks above cost a dependent
+// load-compare-store (or shuffle-compare) chain per stage, ~2.5 us even for 40 keys; this is ~0.3 us for them.  Caller has
+// synced; buf must be 16-byte aligned with one readable slot behind an odd n.
+__device__ __forceinline__ void block_ranksort(unsigned long long *buf, int n, int tid) {
+    const unsigned long long mine = tid < n ? buf[tid] : kKeyMax;
+    int r0 = 0, r1 = 0;
+    if (tid < n) {
+        const ulonglong2 *b2 = reinterpret_cast<const ulonglong2 *>(buf);
+        const int n2 = n >> 1;
+        for (int j = 0; j < n2; ++j) {   // (equal keys -- there should be none -- are ordered by position, so every rank is taken once)
+            const ulonglong2 a = b2[j];
+            r0 += (a.x < mine || (a.x == mine && 2 * j < tid)) ? 1 : 0;
+            r1 += (a.y < mine || (a.y == mine && 2 * j + 1 < tid)) ? 1 : 0;
+        }
+        if (n & 1) r0 += (buf[n - 1] < mine || (buf[n - 1] == mine && n - 1 < tid)) ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid < n) buf[r0 + r1] = mine;
+    __syncthreads();
+}
+
 // Keep the best kprime keys (sorted ascending in buf[0..cnt)), refresh the threshold.  All threads of
 // the CTA call it right after a __syncthreads().
 __device__ __forceinline__ void block_prune(CandCtl *ctl, unsigned long long *buf, int kprime, int cap, int tid) {
     int cnt = ctl->cnt;
     if (cnt > cap) cnt = cap;
-    int P = 64;
-    while (P < cnt) P <<= 1;
-    for (int i = cnt + tid; i < P; i += kScanThreads) buf[i] = kKeyMax;
-    __syncthreads();
-    block_bitonic(buf, P, tid);
+    if (cnt <= kScanThreads) {   // (uniform) the usual case everywhere but in the middle of a scan
+        block_ranksort(buf, cnt, tid);
+    } else {
+        int P = 64;
+        while (P < cnt) P <<= 1;
+        for (int i = cnt + tid; i < P; i += kScanThreads) buf[i] = kKeyMax;
+        __syncthreads();
+        block_bitonic(buf, P, tid);
+    }
     if (tid == 0) {
         const int nc = cnt < kprime ? cnt : kprime;
         ctl->cnt = nc;

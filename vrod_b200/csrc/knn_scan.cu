@@ -44,11 +44,13 @@ struct ScanParams {
                                // [2] last-CTA merge start, [3] merge end, [4] rerank end, [5] kernel end
     Hit *out;
     unsigned long long *out_ids;  // optional: final [k] ids / distances of this query (single-GPU contexts
-    float *out_dist;              // skip the merge kernel)
+    float *out_dist;              // skip the merge kernel; sharded contexts with the fused exchange: the GLOBAL answer)
     double eps;
+    XchgArgs x;                   // x.windows != nullptr: the last CTA also exchanges and merges the ranks' lists (fused)
 };
 
 constexpr int kCtlBytes = 128;
+constexpr int kMaxListsPerThread = 5;   // gridDim.x <= 8 CTAs x 148 SMs = 1184 lists over 256 threads
 static_assert(sizeof(CandCtl) <= kCtlBytes, "CandCtl must fit its slot");
 
 // Finish protocol of a scanning CTA + cross-CTA merge by the last CTA to finish.
@@ -76,23 +78,165 @@ __device__ __forceinline__ bool finish_and_merge(CandCtl *ctl, unsigned long lon
     __threadfence();
     if (kDbg && p.dbg && tid == 0) p.dbg[2] = gtimer();
 
-    // ---- last CTA: merge gridDim.x sorted lists, walking them by depth ----
+    // ---- last CTA: merge gridDim.x sorted lists with (almost always) ONE round of loads ----
+    // Every thread fetches the first kPre keys of its lists, all loads in flight together.  The kprime-th smallest HEAD
+    // T0 bounds the global kprime-th key from above (the kprime smallest heads are kprime distinct keys <= T0), so the
+    // answer is made of the keys <= T0 -- and a list almost never holds more than kPre of those (the global top kprime
+    // spread over hundreds of lists): the prefetched keys are filtered straight from registers, a list whose kPre-th key
+    // is still below T0 is read on in a second round.  T0 is found by counting (each head ranked against all heads in
+    // shared memory), not by sorting.  Every step here is a dependent round trip of a single CTA while the rest of the
+    // GPU waits: round 1 of the build walked the lists by depth -- one key per active list, a barrier and often a sort
+    // per level, 3-6 levels, 10-15 us on a scan that streams 1M x 128 in 80 us.
     if (tid == 0) {
         const int ov = ctl->overflow;
         cand_reset(ctl);
         ctl->overflow = ov;
+        ctl->thrkey2 = 0;
+        ctl->ncand = 0;
         *p.ticket = 0;  // self-reset for the next launch
     }
-    __syncthreads();
     const int nlists = gridDim.x;
-    const int water = p.cap - nlists;
-    unsigned int active = 0xffffffffu;  // bit li <-> list tid + li*kScanThreads (nlists <= 32*kScanThreads)
-    for (int depth = 0; depth < p.kprime; ++depth) {
-        int any = 0;
-        int li = 0;
-        for (int b = tid; b < nlists; b += kScanThreads, ++li) {
-            if (active & (1u << li)) {
-                const unsigned long long key = __ldcg(p.blk_cand + (size_t)b * p.kprime + depth);
+    constexpr int kPre = 12;
+    unsigned long long pre[2][kPre];                 // lists tid and tid + kScanThreads (the usual grid has 296)
+    unsigned long long head[kMaxListsPerThread];
+#pragma unroll
+    for (int li = 0; li < 2; ++li) {
+        const int b = tid + li * kScanThreads;
+        const unsigned long long *lst = p.blk_cand + (size_t)b * p.kprime;
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) pre[li][u] = (b < nlists && u < p.kprime) ? __ldcg(lst + u) : kKeyMax;
+    }
+#pragma unroll
+    for (int li = 2; li < kMaxListsPerThread; ++li) {
+        const int b = tid + li * kScanThreads;
+        head[li] = b < nlists ? __ldcg(p.blk_cand + (size_t)b * p.kprime) : kKeyMax;
+    }
+    head[0] = pre[0][0];
+    head[1] = pre[1][0];
+    // the heads, staged in the (still empty) key buffer behind the slots the survivors will need first
+    unsigned long long *hs = buf + ((p.cap - nlists - 1) & ~1);   // 16-byte aligned, one pad slot; cap >= kprime + max_grid + 64
+#pragma unroll
+    for (int li = 0; li < kMaxListsPerThread; ++li) {
+        const int b = tid + li * kScanThreads;
+        if (b <= nlists) hs[b] = head[li];   // (b == nlists: the pad, kKeyMax)
+    }
+    __syncthreads();
+    // T0.  Any key with at least kprime heads at or below it will do; the tighter, the fewer survivors.  Up to 512 lists:
+    // warp w sorts the heads w, w + 8, w + 16, ... (at most 64, in registers) and offers its r-th smallest, r =
+    // ceil(kprime / 8); the largest offer has 8 r >= kprime heads at or below it.  It sits a little above the exact
+    // kprime-th smallest head (~60 survivors instead of ~36 for kprime = 32, all sorted by rank-and-scatter anyway) and
+    // costs a 64-key register sort -- ranking every head against all 296 of them in shared memory cost 4 us of bank
+    // wavefronts.
+    const int rr = (p.kprime + kScanWarps - 1) / kScanWarps;
+    const int share = nlists / kScanWarps;               // heads every warp has at least
+    if (nlists <= 64 * kScanWarps && share >= rr && rr <= 32) {
+        const int lane = tid & 31, warp = tid >> 5;
+        const int i0 = warp + kScanWarps * lane, i1 = warp + kScanWarps * (lane + 32);
+        unsigned long long x0 = i0 < nlists ? hs[i0] : kKeyMax, x1 = i1 < nlists ? hs[i1] : kKeyMax;
+        warp_sort64_regs(x0, x1, 64, lane);
+        const unsigned long long offer = __shfl_sync(kFull, x0, rr - 1);
+        if (lane == 0) {
+            if (offer == kKeyMax) ctl->ncand = 1;        // a warp with fewer than r real heads: no bound this way
+            else atomicMax(&ctl->thrkey2, offer);
+        }
+        __syncthreads();
+        if (tid == 0) ctl->thrkey = ctl->ncand ? kKeyMax : ctl->thrkey2;
+    } else if (nlists >= p.kprime) {
+        const ulonglong2 *h2 = reinterpret_cast<const ulonglong2 *>(hs);
+        const int n2 = (nlists + 1) >> 1;
+        // list tid: the thread ranks its own head against all heads (two keys per 128-bit broadcast load, eight in flight)
+        {
+            const unsigned long long mine = head[0];
+            int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+            int j = 0;
+            for (; j + 4 <= n2; j += 4) {
+                const ulonglong2 a = h2[j], c = h2[j + 1], d = h2[j + 2], e = h2[j + 3];
+                r0 += (a.x < mine ? 1 : 0) + (d.x < mine ? 1 : 0);
+                r1 += (a.y < mine ? 1 : 0) + (d.y < mine ? 1 : 0);
+                r2 += (c.x < mine ? 1 : 0) + (e.x < mine ? 1 : 0);
+                r3 += (c.y < mine ? 1 : 0) + (e.y < mine ? 1 : 0);
+            }
+            for (; j < n2; ++j) {
+                const ulonglong2 a = h2[j];
+                r0 += a.x < mine ? 1 : 0;
+                r1 += a.y < mine ? 1 : 0;
+            }
+            if (mine != kKeyMax && r0 + r1 + r2 + r3 == p.kprime - 1) ctl->thrkey = mine;
+        }
+        // lists beyond the first kScanThreads (40 of the usual 296): warp w ranks heads kScanThreads + w, + w + 8, ... with
+        // its lanes across the heads array, so that no warp walks the array a second time on its own
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int b = kScanThreads + warp; b < nlists; b += kScanWarps) {
+            const unsigned long long mine = hs[b];
+            int r = 0;
+            for (int j = lane; j < n2; j += 32) {
+                const ulonglong2 a = h2[j];
+                r += (a.x < mine ? 1 : 0) + (a.y < mine ? 1 : 0);
+            }
+            r = __reduce_add_sync(kFull, r);
+            if (lane == 0 && mine != kKeyMax && r == p.kprime - 1) ctl->thrkey = mine;
+        }
+    }
+    __syncthreads();
+    const unsigned long long t0key = ctl->thrkey;    // kKeyMax: fewer than kprime non-empty lists
+    if (kDbg && p.dbg && tid == 0) p.dbg[6] = gtimer();
+    const int room = p.cap - nlists - 2;
+    auto keep = [&](unsigned long long key) {
+        const int pos = atomicAdd(&ctl->cnt, 1);
+        if (pos < room) buf[pos] = key;
+        else ctl->overflow = 1;
+    };
+    // every key <= T0: the qualifying heads and what follows them in their lists
+#pragma unroll
+    for (int li = 0; li < kMaxListsPerThread; ++li) {
+        if (head[li] == kKeyMax || head[li] > t0key) continue;
+        keep(head[li]);
+        if (t0key == kKeyMax) continue;              // (no bound: the depth walk below reads the lists)
+        int from = 1;                                // first key of the list not looked at yet
+        if (li < 2) {
+            bool more = true;
+#pragma unroll
+            for (int u = 1; u < kPre; ++u) {
+                if (more && pre[li][u] < t0key) keep(pre[li][u]);
+                else more = false;
+            }
+            if (!more) continue;
+            from = kPre;
+        }
+        const unsigned long long *lst = p.blk_cand + (size_t)(tid + li * kScanThreads) * p.kprime;
+        for (int j0 = from; j0 < p.kprime; j0 += 16) {   // lists are sorted: stop at the first key >= T0
+            unsigned long long key[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) key[u] = j0 + u < p.kprime ? __ldcg(lst + j0 + u) : kKeyMax;
+            bool more = true;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                if (more && key[u] < t0key) keep(key[u]);
+                else more = false;
+            }
+            if (!more) break;
+        }
+    }
+    __syncthreads();
+    if (kDbg && p.dbg && tid == 0) p.dbg[7] = gtimer();
+    if (ctl->cnt > room) {   // (uniform) more survivors than the buffer holds next to the staged heads: give the query up
+        if (tid == 0) ctl->cnt = room;
+        __syncthreads();
+    }
+    // Fewer non-empty lists than kprime (large k on a small grid, tiny collections): no finite T0.  Walk the lists by
+    // depth instead, pruning on the way, so that the buffer never has to hold all of them.
+    if (t0key == kKeyMax) {
+        const int water = p.cap - nlists;
+        unsigned int active = 0;
+#pragma unroll
+        for (int li = 0; li < kMaxListsPerThread; ++li)
+            if (head[li] != kKeyMax) active |= 1u << li;
+        for (int depth = 1; depth < p.kprime; ++depth) {
+            int any = 0;
+#pragma unroll
+            for (int li = 0; li < kMaxListsPerThread; ++li) {
+                if (!(active & (1u << li))) continue;
+                const unsigned long long key = __ldcg(p.blk_cand + (size_t)(tid + li * kScanThreads) * p.kprime + depth);
                 if (key < *(volatile unsigned long long *)&ctl->thrkey) {
                     const int pos = atomicAdd(&ctl->cnt, 1);
                     if (pos < p.cap) buf[pos] = key;
@@ -102,10 +246,8 @@ __device__ __forceinline__ bool finish_and_merge(CandCtl *ctl, unsigned long lon
                     active &= ~(1u << li);
                 }
             }
-        }
-        if (!__syncthreads_or(any)) break;
-        if (ctl->cnt > water || ctl->cnt > p.kprime * 2) {  // uniform: cnt is stable after the barrier
-            block_prune(ctl, buf, p.kprime, p.cap, tid);
+            if (!__syncthreads_or(any)) break;
+            if (ctl->cnt > water || ctl->cnt > p.kprime * 2) block_prune(ctl, buf, p.kprime, p.cap, tid);   // uniform: cnt is stable after the barrier
         }
     }
     __syncthreads();
@@ -114,7 +256,12 @@ __device__ __forceinline__ bool finish_and_merge(CandCtl *ctl, unsigned long lon
 }
 
 // Write the final k hits from sorted exact keys in buf[0..ncand).
-__device__ __forceinline__ void write_hits(const unsigned long long *buf, int ncand, const ScanParams &p, int tid) {
+__device__ __forceinline__ int exchange_device(const XchgArgs &x, const Hit *local, uint32_t k, unsigned long long *buf,
+                                               unsigned long long *out_ids, float *out_dist, int tid);
+
+// `flag` = this rank's guard flag for the query; it travels to the peers in hit[0].pad.  With the fused exchange the final
+// arrays are written by exchange_device (the global answer), not here.
+__device__ __forceinline__ void write_hits(const unsigned long long *buf, int ncand, const ScanParams &p, int tid, int flag) {
     for (int i = tid; i < (int)p.k; i += kScanThreads) {
         Hit h;
         if (i < ncand) {
@@ -124,13 +271,30 @@ __device__ __forceinline__ void write_hits(const unsigned long long *buf, int nc
             h.id = kKeyMax;
             h.dist = __int_as_float(0x7f800000);
         }
-        h.pad = 0;
+        h.pad = i == 0 ? (uint32_t)flag : 0u;
         p.out[i] = h;
-        if (p.out_ids) {
+        if (p.out_ids && !p.x.windows) {
             p.out_ids[i] = h.id;
             p.out_dist[i] = h.dist;
         }
     }
+}
+
+// Tail of a scan's last CTA: publish the k hits and the guard flag; in a sharded context with the fused exchange, meet the
+// peers and leave the GLOBAL answer and the global flag instead.
+__device__ __forceinline__ void publish(const unsigned long long *keys, int ncand, const ScanParams &p, CandCtl *ctl, unsigned long long *buf,
+                                        int bad, int tid) {
+    write_hits(keys, ncand, p, tid, bad);
+    if (p.x.windows) {
+        __threadfence();
+        __syncthreads();
+        bad = exchange_device(p.x, p.out, p.k, buf, p.out_ids, p.out_dist, tid);
+    }
+    if (tid == 0 && p.status) {
+        *p.status = bad ? 1 : 0;
+        if (bad && p.counters) atomicAdd(p.counters, 1ull);
+    }
+    (void)ctl;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -272,16 +436,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) fast_scan_kernel(const ScanPa
     rerank_candidates<COS>(buf, ncand, p.rows4, p.q4, (int)p.ld4, ctl->nq, warp, lane);
     __syncthreads();
     if (kDbg && p.dbg && tid == 0) p.dbg[4] = gtimer();
-    {
+    if (ncand <= kScanThreads) {
+        block_ranksort(buf, ncand, tid);
+    } else {
         int P = 32;
         while (P < ncand) P <<= 1;
         for (int i = ncand + tid; i < P; i += kScanThreads) buf[i] = kKeyMax;
         __syncthreads();
         block_bitonic(buf, P, tid);
     }
-    write_hits(buf, ncand, p, tid);
     if (tid == 0) {
-        if (kDbg && p.dbg) p.dbg[5] = gtimer();
         int bad = ctl->overflow;
         if (p.n > (uint32_t)ncand) {
             // rows were dropped: every dropped row has surrogate >= u_val.  Bound its exact distance
@@ -308,9 +472,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) fast_scan_kernel(const ScanPa
             if (!(lb > T)) bad = 1;
             if (kk < (int)p.k) bad = 1;
         }
-        *p.status = bad ? 1 : 0;
-        if (bad && p.counters) atomicAdd(p.counters, 1ull);
+        ctl->is_last = bad;   // (the slot is free again: this IS the last CTA)
     }
+    __syncthreads();
+    publish(buf, ncand, p, ctl, buf, ctl->is_last, tid);
+    if (kDbg && p.dbg && tid == 0) p.dbg[5] = gtimer();
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -396,7 +562,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) exact_scan_kernel(const ScanP
     }
 
     if (!finish_and_merge(ctl, buf, p, tid)) return;
-    write_hits(buf, ctl->cnt, p, tid);
+    publish(buf, ctl->cnt, p, ctl, buf, 0, tid);   // exact keys: nothing to prove, the flag is clear
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -509,74 +675,80 @@ __global__ void __launch_bounds__(kScanThreads) merge_hits_kernel(const Hit *lis
 // Fused exchange + merge over NVLink peer memory (row-sharded contexts, one process per GPU).
 //
 // Every rank owns an exchange window (cudaMalloc + CUDA IPC, mapped by all peers at context creation):
-//   flags[2][world][kXchgMaxB]  u32 sequence numbers,   data[2][world][kXchgMaxHits] Hit
+//   flags[3][world][kXchgMaxB]  u32 sequence numbers,   data[3][world][kXchgMaxHits] Hit
 // One CTA per query: (1) PUSH this rank's k hits of the query into slot [seq&1][rank] of EVERY rank's window with
 // plain stores through the peer mappings (NVLink P2P), fence at system scope, then publish flag = seq in every
 // window; (2) WAIT until all `world` flags of the query in the LOCAL window carry seq (the peers' pushes);
 // (3) MERGE the world lists from the local window by (dist, shard, slot) and write the final ids / distances.
-// This replaces ncclAllGather + merge_hits_kernel (two launches, ~20-30 us of latency at 8 GPUs) with one launch
-// whose transfers overlap per query.  Searches are collective and sequence numbers advance in lockstep; two slots
-// suffice because a rank cannot start pushing search s+2 before every peer has merged search s.
+// This replaces ncclAllGather + merge_hits_kernel (two launches, ~20-30 us of latency at 8 GPUs).  For single-query
+// scans it is not even a launch: the last CTA of fast_scan_kernel / exact_scan_kernel runs it right after it has written
+// the rank's k hits (exchange_device below), so a sharded search is ONE kernel per rank.
+// Searches are collective and sequence numbers advance in lockstep.  The slot of an exchange is seq % 3: a conditional
+// exact re-scan (run by all ranks or by none -- the decision is the OR of all ranks' guard flags, which travels in
+// hit[0].pad) takes a sequence number whether it runs or not, so a slot is re-used after three numbers, of which at
+// least one (a first-pass scan) was really exchanged: a rank pushes into a slot only after it has merged that
+// exchange, which needed every peer's push, which every peer issued after merging everything before it -- including
+// the exchange that used the slot last.
 // root == kXchgAllRanks: all-to-all as above (one process per GPU: every rank returns the global answer).
 // root == r (single-process multi-GPU contexts, where the host reads the answer from device r only): the ranks push
 // into rank r's window alone and only rank r waits and merges; the host does not issue search s+1 before it has
 // read the answer of search s, which is what keeps the two slots sufficient there.
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kScanThreads) exchange_merge_kernel(unsigned char *const *windows, uint32_t rank, uint32_t world,
-                                                                      uint32_t seq, const Hit *local, uint32_t b, uint32_t k,
-                                                                      unsigned long long *out_ids, float *out_dist, int *err,
-                                                                      uint32_t root) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem);
-    const int tid = threadIdx.x;
-    const uint32_t qi = blockIdx.x;
-    const uint32_t slot = seq & 1u;
-    const size_t flags_bytes = (size_t)2 * kXchgMaxWorld * kXchgMaxB * sizeof(unsigned int);
+// One CTA, one query: push / wait / merge as described above.  `local` = this rank's k hits of the query (hit[0].pad carries
+// the rank's guard flag), out_* = the query's k output slots.  buf: >= next_pow2(world * k) keys of shared memory.
+// Returns (to every thread) the OR of the ranks' guard flags: the GLOBAL "this query needs the exact scan" decision, the
+// same on every rank that merges.  Ranks that only push (root mode, rank != root) return 0.
+__device__ __forceinline__ int exchange_device(const XchgArgs &x, const Hit *local, uint32_t k, unsigned long long *buf,
+                                               unsigned long long *out_ids, float *out_dist, int tid) {
+    const uint32_t rank = x.rank, world = x.world, seq = x.seq, qi = x.qi;
+    const uint32_t slot = seq % kXchgSlots;
+    const size_t flags_bytes = (size_t)kXchgSlots * kXchgMaxWorld * kXchgMaxB * sizeof(unsigned int);
     auto flag_of = [&](unsigned char *w, uint32_t r) {
         return reinterpret_cast<unsigned int *>(w) + ((size_t)slot * kXchgMaxWorld + r) * kXchgMaxB + qi;
     };
     auto data_of = [&](unsigned char *w, uint32_t r) {
         return reinterpret_cast<Hit *>(w + flags_bytes) + ((size_t)slot * kXchgMaxWorld + r) * kXchgMaxHits + (size_t)qi * k;
     };
-    const bool all = root == kXchgAllRanks;
-    if (qi == 0 && tid == 0) *err = 0;   // a time-out (>= 2.5 s later) sets it to 1
+    const bool all = x.root == kXchgAllRanks;
+    if (qi == 0 && tid == 0) *x.err = 0;   // a time-out (>= 2.5 s later) sets it to 1
     // (1) push
     if (all) {
         for (uint32_t i = tid; i < world * k; i += kScanThreads) {
             const uint32_t r = i / k, j = i % k;
-            data_of(windows[r], rank)[j] = local[(size_t)qi * k + j];
+            data_of(x.windows[r], rank)[j] = local[j];
         }
     } else {
-        Hit *dst = data_of(windows[root], rank);
-        for (uint32_t j = tid; j < k; j += kScanThreads) dst[j] = local[(size_t)qi * k + j];
+        Hit *dst = data_of(x.windows[x.root], rank);
+        for (uint32_t j = tid; j < k; j += kScanThreads) dst[j] = local[j];
     }
     __threadfence_system();
     __syncthreads();
     if (all) {
-        if (tid < (int)world) *(volatile unsigned int *)flag_of(windows[tid], rank) = seq;
+        if (tid < (int)world) *(volatile unsigned int *)flag_of(x.windows[tid], rank) = seq;
     } else {
-        if (tid == 0) *(volatile unsigned int *)flag_of(windows[root], rank) = seq;
-        if (rank != root) return;
+        if (tid == 0) *(volatile unsigned int *)flag_of(x.windows[x.root], rank) = seq;
+        if (rank != x.root) return 0;
     }
     // (2) wait for every peer's push of this query into MY window
-    unsigned char *mine = windows[rank];
+    unsigned char *mine = x.windows[rank];
     if (tid < (int)world) {
         volatile unsigned int *f = flag_of(mine, tid);
         unsigned long long spins = 0;
         while ((int)(*f - seq) < 0) {
             __nanosleep(64);
             if (++spins > 40000000ull) {   // ~2.5 s: a peer never arrived; report instead of hanging the GPU
-                atomicExch(err, 1);
+                atomicExch(x.err, 1);
                 break;
             }
         }
     }
     __syncthreads();
     __threadfence_system();
-    // (3) merge (same order as merge_hits_kernel)
+    // (3) merge: (dist, shard, slot) order IS (dist, id) order (shards own ascending id ranges, lists are sorted)
     const int total = (int)(world * k);
     int P = 32;
     while (P < total) P <<= 1;
+    int flagged = 0;
     for (int i = tid; i < P; i += kScanThreads) {
         unsigned long long key = kKeyMax;
         if (i < total) {
@@ -584,11 +756,12 @@ __global__ void __launch_bounds__(kScanThreads) exchange_merge_kernel(unsigned c
             const Hit *h = data_of(mine, s) + j;
             const unsigned long long id = *(volatile const unsigned long long *)&h->id;
             const float dist = *(volatile const float *)&h->dist;
+            if (j == 0) flagged |= (int)*(volatile const uint32_t *)&h->pad;
             if (id != kKeyMax) key = ((unsigned long long)f2ord(dist) << 32) | (s << 16) | j;
         }
         buf[i] = key;
     }
-    __syncthreads();
+    flagged = __syncthreads_or(flagged);
     block_bitonic(buf, P, tid);
     for (int i = tid; i < (int)k; i += kScanThreads) {
         const unsigned long long key = buf[i];
@@ -600,9 +773,20 @@ __global__ void __launch_bounds__(kScanThreads) exchange_merge_kernel(unsigned c
             id = *(volatile const unsigned long long *)&h->id;
             dist = *(volatile const float *)&h->dist;
         }
-        out_ids[(size_t)qi * k + i] = id;
-        out_dist[(size_t)qi * k + i] = dist;
+        out_ids[i] = id;
+        out_dist[i] = dist;
     }
+    return flagged;
+}
+
+// The exchange as a kernel of its own, one CTA per query: after the batched (tensor-core) pass, whose b x k local hits come
+// out of batched_finish_kernel, and for calls too large for the scan kernels' fused form.
+__global__ void __launch_bounds__(kScanThreads) exchange_merge_kernel(XchgArgs x, const Hit *local, uint32_t b, uint32_t k,
+                                                                      unsigned long long *out_ids, float *out_dist) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    x.qi = blockIdx.x;
+    exchange_device(x, local + (size_t)x.qi * k, k, reinterpret_cast<unsigned long long *>(smem), out_ids + (size_t)x.qi * k,
+                    out_dist + (size_t)x.qi * k, threadIdx.x);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -734,25 +918,29 @@ static ScanParams make_params(const ShardView &s, const float *q, uint32_t k, co
 }
 
 cudaError_t launch_fast_scan(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan, const ScanScratch &scr,
-                             int *status, Hit *out, unsigned long long *out_ids, float *out_dist, cudaStream_t st) {
+                             int *status, Hit *out, unsigned long long *out_ids, float *out_dist, cudaStream_t st, const XchgArgs *x) {
     const Variant &v = pick_variant(s.ld / 4);
     ScanParams p = make_params(s, q, k, plan, scr, v.rows);
     p.status = status;
     p.out = out;
     p.out_ids = out_ids;
     p.out_dist = out_dist;
+    if (x) p.x = *x;
     (s.metric ? v.cs : v.l2)<<<plan.grid, kScanThreads, plan.smem, st>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_exact_scan(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan, const ScanScratch &scr,
                               const int *only_if_flag, Hit *out, unsigned long long *out_ids, float *out_dist,
-                              cudaStream_t st) {
+                              cudaStream_t st, const XchgArgs *x, int *gstatus) {
     ScanParams p = make_params(s, q, k, plan, scr, s.metric ? kExactRBCos : kExactRBL2);
     p.only_if = only_if_flag;
+    p.status = x ? gstatus : nullptr;   // exact keys need no proof: alone, the query's flag stays what the f32 pass left
+    p.counters = nullptr;
     p.out = out;
     p.out_ids = out_ids;
     p.out_dist = out_dist;
+    if (x) p.x = *x;
     if (s.metric) exact_scan_kernel<kExactRBCos, true><<<plan.grid, kScanThreads, plan.smem, st>>>(p);
     else exact_scan_kernel<kExactRBL2, false><<<plan.grid, kScanThreads, plan.smem, st>>>(p);
     return cudaGetLastError();
@@ -795,19 +983,18 @@ cudaError_t launch_merge_hits(const Hit *lists, uint32_t g, uint32_t b, uint32_t
 }
 
 size_t xchg_window_bytes() {
-    return (size_t)2 * kXchgMaxWorld * kXchgMaxB * sizeof(unsigned int) + (size_t)2 * kXchgMaxWorld * kXchgMaxHits * sizeof(Hit);
+    return (size_t)kXchgSlots * kXchgMaxWorld * kXchgMaxB * sizeof(unsigned int) + (size_t)kXchgSlots * kXchgMaxWorld * kXchgMaxHits * sizeof(Hit);
 }
 
-cudaError_t launch_exchange_merge(unsigned char *const *d_windows, uint32_t rank, uint32_t world, uint32_t seq, const Hit *local,
-                                  uint32_t b, uint32_t k, unsigned long long *out_ids, float *out_dist, int *d_err, uint32_t root,
-                                  cudaStream_t st) {
+cudaError_t launch_exchange_merge(const XchgArgs &x, const Hit *local, uint32_t b, uint32_t k, unsigned long long *out_ids,
+                                  float *out_dist, cudaStream_t st) {
     if (b == 0) return cudaSuccess;
-    const size_t smem = (size_t)next_pow2((int)(world * k) < 32 ? 32 : (int)(world * k)) * sizeof(unsigned long long);
+    const size_t smem = (size_t)next_pow2((int)(x.world * k) < 32 ? 32 : (int)(x.world * k)) * sizeof(unsigned long long);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    exchange_merge_kernel<<<b, kScanThreads, smem, st>>>(d_windows, rank, world, seq, local, b, k, out_ids, out_dist, d_err, root);
+    exchange_merge_kernel<<<b, kScanThreads, smem, st>>>(x, local, b, k, out_ids, out_dist);
     return cudaGetLastError();
 }
 

@@ -40,6 +40,20 @@ struct Hit {
     uint32_t pad;
 };
 
+// Fused exchange + merge over NVLink peer memory (knn_scan.cu: exchange_device).  It serves searches with
+// b <= kXchgMaxB queries and b*k <= kXchgMaxHits hits on at most kXchgMaxWorld ranks.
+constexpr uint32_t kXchgMaxWorld = 16, kXchgMaxB = 256, kXchgMaxHits = 4096, kXchgSlots = 3;
+size_t xchg_window_bytes();
+constexpr uint32_t kXchgAllRanks = 0xffffffffu;   // root: every rank merges; else only rank `root` receives and merges
+struct XchgArgs {
+    unsigned char *const *windows;   // device table of every rank's window (peer mappings); nullptr = no exchange
+    uint32_t rank, world, seq, root;
+    uint32_t qi;                     // query index inside the search call (its flag / data slot in the windows)
+    int *err;                        // set to 1 when a peer never arrived
+};
+// exchange + merge as a kernel of its own (one CTA per query): after the batched pass
+cudaError_t launch_exchange_merge(const XchgArgs &x, const Hit *local, uint32_t b, uint32_t k, unsigned long long *out_ids,
+                                  float *out_dist, cudaStream_t st);
 int scan_sm_count(int device);
 unsigned long long *scan_debug_enable();   // development aid: device buffer of 8 globaltimer stamps (VROD_SCAN_DEBUG)
 ScanPlan make_scan_plan(const ShardView &s, uint32_t k, int sm_count, bool exact);
@@ -47,13 +61,16 @@ size_t scan_cand_bytes(int sm_count);
 
 // f32 scan + exact rerank + guard of ONE query (q: ld floats, device).  Writes k hits to `out` and, when
 // out_ids/out_dist are not null, the final ids / distances as well (single-GPU: no merge kernel needed).
+// x (optional): the last CTA also pushes the k hits to the peers, waits for theirs and writes the GLOBAL answer to
+// out_ids / out_dist; *status then is the OR of all ranks' guard flags.  Needs world * k <= plan.cap.
 cudaError_t launch_fast_scan(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan,
                              const ScanScratch &scr, int *status, Hit *out, unsigned long long *out_ids, float *out_dist,
-                             cudaStream_t st);
+                             cudaStream_t st, const XchgArgs *x = nullptr);
 // exact f64 scan of ONE query; if only_if_flag != nullptr the grid returns at once unless *only_if_flag != 0.
+// With x, *gstatus (optional) receives the OR of the ranks' guard flags that travelled with the lists.
 cudaError_t launch_exact_scan(const ShardView &s, const float *q, uint32_t k, const ScanPlan &plan,
                               const ScanScratch &scr, const int *only_if_flag, Hit *out, unsigned long long *out_ids,
-                              float *out_dist, cudaStream_t st);
+                              float *out_dist, cudaStream_t st, const XchgArgs *x = nullptr, int *gstatus = nullptr);
 
 // rows [row0, row0+n) of the shard: inv_norm / sq_norm, and flags[0] |= 1 if a value is not finite,
 // |= 2 if a value or norm is outside the range the f32 scan's error bound covers.
@@ -64,14 +81,6 @@ cudaError_t launch_fill_synthetic(float *rows, uint32_t row0, uint32_t n, uint32
                                   uint64_t seed, cudaStream_t st);
 // [b x dim] -> [b x ld] zero padded
 cudaError_t launch_pad_queries(const float *src, float *dst, uint32_t b, uint32_t dim, uint32_t ld, cudaStream_t st);
-// Fused exchange + merge over NVLink peer memory (knn_scan.cu: exchange_merge_kernel).  The fused path serves
-// searches with b <= kXchgMaxB queries and b*k <= kXchgMaxHits hits on at most kXchgMaxWorld ranks.
-constexpr uint32_t kXchgMaxWorld = 16, kXchgMaxB = 256, kXchgMaxHits = 4096;
-size_t xchg_window_bytes();
-constexpr uint32_t kXchgAllRanks = 0xffffffffu;   // root: every rank merges; else only rank `root` receives and merges
-cudaError_t launch_exchange_merge(unsigned char *const *d_windows, uint32_t rank, uint32_t world, uint32_t seq, const Hit *local,
-                                  uint32_t b, uint32_t k, unsigned long long *out_ids, float *out_dist, int *d_err, uint32_t root,
-                                  cudaStream_t st);
 // merge g lists of [b][k] hits (layout [g][b][k]) into ids/dist [b][k] by (dist, id)
 cudaError_t launch_merge_hits(const Hit *lists, uint32_t g, uint32_t b, uint32_t k, unsigned long long *out_ids,
                               float *out_dist, cudaStream_t st);

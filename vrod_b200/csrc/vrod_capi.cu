@@ -1162,7 +1162,25 @@ static ShardView shard_view(const vrod_collection *c) {
 struct LocalPass {
     bool batched = false;     // the tensor-core pass ran: its guard flags must be read back (batched_fetch_status + batched_rescans)
     bool used_scan = false;   // per-query f32 scans ran (host_checks: the caller rescans the flagged queries itself)
+    bool exchanged = false;   // the scan kernels exchanged and merged the ranks' lists themselves (fused): d_ids / d_dist hold
+                              // the GLOBAL answer and d_status the global guard flags
 };
+
+// Fused exchange inside the scan kernels' last CTA: which windows, which sequence numbers.  x.windows == nullptr: none.
+struct FusePlan {
+    XchgArgs x{};             // rank / world / root / err filled in; seq and qi are set per launch
+    uint32_t seq_fast = 0, seq_exact = 0;
+    bool on = false;
+};
+
+// May the scan kernels of this call exchange the lists themselves?  (single-query scans, small enough for the windows and
+// for the scan kernels' shared-memory merge buffer)
+static bool can_fuse_scan(const vrod_ctx *ctx, const ScanPlan &fp, const ScanPlan &xp, uint32_t b, uint32_t k) {
+    if (ctx->world <= 1 || !ctx->fused_exchange) return false;
+    if (b > kXchgMaxB || (size_t)b * k > kXchgMaxHits) return false;
+    const uint32_t need = (uint32_t)ctx->world * k;
+    return need <= (uint32_t)fp.cap && need <= (uint32_t)xp.cap;
+}
 
 static ScanScratch scan_scratch(vrod_ctx *ctx, int *d_status) {
     return ScanScratch{reinterpret_cast<unsigned long long *>(ctx->blk_cand.p), reinterpret_cast<unsigned int *>(ctx_ticket(ctx)),
@@ -1174,30 +1192,46 @@ static ScanScratch scan_scratch(vrod_ctx *ctx, int *d_status) {
 // d_status: per-query guard flags (device).  host_checks: the caller reads d_status after synchronising and rescans the
 // flagged queries itself, so the conditional exact-scan launches are left out (single GPU only).
 static vrod_status local_enqueue(vrod_collection *c, const float *d_q, uint32_t b, uint32_t k, uint64_t *d_ids, float *d_dist,
-                                 bool force_exact, int *d_status, bool host_checks, LocalPass *lp) {
+                                 bool force_exact, int *d_status, bool host_checks, LocalPass *lp, FusePlan *fuse = nullptr) {
     vrod_ctx *ctx = c->ctx;
-    if (ctx->world > 1) host_checks = false;
     const ShardView s = shard_view(c);
     const size_t nhits = (size_t)b * k;
     VROD_CUDA(ctx->hits_local.ensure(nhits * sizeof(Hit)));
     Hit *local = reinterpret_cast<Hit *>(ctx->hits_local.p);
     const ScanScratch scr = scan_scratch(ctx, d_status);
     const bool exact_only = force_exact || c->path == 2 || !c->fast_ok;
-    // single GPU: the scan kernels write the final arrays themselves, no merge launch
-    const bool direct = ctx->world == 1;
-    auto oid = [&](uint32_t qi) { return direct ? reinterpret_cast<unsigned long long *>(d_ids) + (size_t)qi * k : nullptr; };
-    auto odd = [&](uint32_t qi) { return direct ? d_dist + (size_t)qi * k : nullptr; };
+    // which kind of pass?  (the choice comes first: the fused exchange is for the scan kernels only)
     // automatic choice between b single-query scans and one batched (tensor-core) pass: the context's cost model
     // (CostModel: seeded from round-1 measurements, then corrected by the times this context measures)
+    // Sharded contexts: every rank (device) must reach the SAME decision -- the scan path exchanges inside the scan kernels,
+    // conditional re-scans included, and a rank on the other path would not answer -- so only rank-invariant inputs
+    // count there: the shard size by the partition rule, the model's seeds, no learned rescan share.
     bool prefer_batched = false;
     if (b >= 2) {
-        const double t_scan = ctx->cost.scan_seconds((double)s.n * s.ld * 4.0);
+        const bool sharded = ctx->world > 1;
+        const CostModel seeds;
+        const CostModel &cm = sharded ? seeds : ctx->cost;
+        const double rows = sharded ? (double)c->shard_rows : (double)s.n;
+        const double share = sharded ? 0.0 : c->rescan_share;
+        const double t_scan = cm.scan_seconds(rows * s.ld * 4.0);
         const double groups = (double)((b + 255) / 256);
-        const double t_batched = ctx->cost.batched_seconds(groups * ((double)s.n / 128.0) * ((double)mirror_ld(s.dim) / 144.0) / (double)ctx->sms);
-        prefer_batched = (1.0 - c->rescan_share) * (double)b * t_scan > t_batched;
+        const double t_batched = cm.batched_seconds(groups * (rows / 128.0) * ((double)mirror_ld(s.dim) / 144.0) / (double)ctx->sms);
+        prefer_batched = (1.0 - share) * (double)b * t_scan > t_batched;
         if (!prefer_batched) c->rescan_share *= 0.995;   // forget slowly: the batched pass is probed again later
     }
     const bool batched = !exact_only && batched_supported(s, b, k) && (c->path == 3 || c->path == 4 || (c->path == 0 && prefer_batched));
+    const bool fused = fuse && fuse->on && !batched;
+    if (fuse && !fused) fuse->on = false;
+    if (ctx->world > 1 && !fused) host_checks = false;   // without the exchange the flags are rank-local: every rank rescans on its own
+    // single GPU, or fused exchange: the scan kernels write the final arrays themselves, no merge launch
+    const bool direct = ctx->world == 1 || fused;
+    auto xf = [&](uint32_t qi, uint32_t seq) {
+        fuse->x.qi = qi;
+        fuse->x.seq = seq;
+        return &fuse->x;
+    };
+    auto oid = [&](uint32_t qi) { return direct ? reinterpret_cast<unsigned long long *>(d_ids) + (size_t)qi * k : nullptr; };
+    auto odd = [&](uint32_t qi) { return direct ? d_dist + (size_t)qi * k : nullptr; };
     if (batched) {
         ShardView sb = s;
         if (c->path != 4 && !c->mirror_failed) {
@@ -1243,10 +1277,19 @@ static vrod_status local_enqueue(vrod_collection *c, const float *d_q, uint32_t 
     } else if (exact_only) {
         const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
         for (uint32_t qi = 0; qi < b; ++qi) {
-            VROD_CUDA(launch_exact_scan(s, d_q + (size_t)qi * s.ld, k, xp, scr, nullptr, local + (size_t)qi * k, oid(qi), odd(qi),
-                                        ctx->stream));
+            const float *q = d_q + (size_t)qi * s.ld;
+            VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, nullptr, local + (size_t)qi * k, oid(qi), odd(qi), ctx->stream,
+                                        fused ? xf(qi, fuse->seq_fast) : nullptr, d_status + qi));
             ctx->stats.kernel_launches++;
+            if (fused && !host_checks) {
+                // a peer whose rows allow the f32 pass may have flagged the query: its re-scan round needs this rank's list too
+                VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, d_status + qi, local + (size_t)qi * k, oid(qi), odd(qi), ctx->stream,
+                                            xf(qi, fuse->seq_exact), d_status + qi));
+                ctx->stats.kernel_launches++;
+            }
         }
+        lp->used_scan = fused;    // (host_checks callers: the flags are meaningful, a peer may have raised one)
+        lp->exchanged = fused;
     } else {
         const ScanPlan fp = make_scan_plan(s, k, ctx->sms, false);
         const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
@@ -1269,26 +1312,29 @@ static vrod_status local_enqueue(vrod_collection *c, const float *d_q, uint32_t 
             }
             if (e0) VROD_CUDA(cudaEventRecord(e0, ctx->stream));
             VROD_CUDA(launch_fast_scan(s, q, k, fp, scr, d_status + qi, local + (size_t)qi * k, oid(qi), odd(qi),
-                                       ctx->stream));
+                                       ctx->stream, fused ? xf(qi, fuse->seq_fast) : nullptr));
             if (scan_dbg) {
                 unsigned long long h[8];
                 cudaStreamSynchronize(ctx->stream);
                 cudaMemcpy(h, dbgbuf, sizeof(h), cudaMemcpyDeviceToHost);
-                fprintf(stderr, "[scan dbg] scan loops %.1f us | wait+ticket %.1f | merge %.1f | rerank %.1f | sort+write %.1f | total %.1f us\n",
-                        (h[1] - h[0]) / 1e3, (h[2] - h[1]) / 1e3, (h[3] - h[2]) / 1e3, (h[4] - h[3]) / 1e3, (h[5] - h[4]) / 1e3,
-                        (h[5] - h[0]) / 1e3);
+                fprintf(stderr, "[scan dbg] scan loops %.1f us | wait+ticket %.1f | merge %.1f (heads+T0 %.1f, lists %.1f, sort %.1f) | rerank %.1f | sort+write %.1f | total %.1f us\n",
+                        (h[1] - h[0]) / 1e3, (h[2] - h[1]) / 1e3, (h[3] - h[2]) / 1e3, (h[6] - h[2]) / 1e3, (h[7] - h[6]) / 1e3, (h[3] - h[7]) / 1e3,
+                        (h[4] - h[3]) / 1e3, (h[5] - h[4]) / 1e3, (h[5] - h[0]) / 1e3);
             }
             if (e1) VROD_CUDA(cudaEventRecord(e1, ctx->stream));
             if (sample) ctx->cost.pending(1, (double)s.n * s.ld * 4.0);
             if (!host_checks) {
+                // (fused: the flag is the OR over all ranks, so every rank runs this re-scan or none does, and the re-scan
+                // exchanges again under the call's second sequence number)
                 VROD_CUDA(launch_exact_scan(s, q, k, xp, scr, d_status + qi, local + (size_t)qi * k, oid(qi), odd(qi),
-                                            ctx->stream));
+                                            ctx->stream, fused ? xf(qi, fuse->seq_exact) : nullptr, d_status + qi));
                 ctx->stats.kernel_launches++;
             }
             ctx->stats.kernel_launches++;
         }
         ctx->stats.fast_scans += b;
         lp->used_scan = true;
+        lp->exchanged = fused;
     }
     return VROD_OK;
 }
@@ -1347,9 +1393,9 @@ static vrod_status exchange_enqueue(vrod_collection *c, uint32_t b, uint32_t k, 
     if (ctx->world == 1) return VROD_OK;   // the kernels of the local pass wrote the final arrays
     if (ctx->fused_exchange && b <= kXchgMaxB && nhits <= kXchgMaxHits) {
         // one kernel: push the local lists into every rank's window over NVLink, wait for the peers', merge
-        VROD_CUDA(launch_exchange_merge(ctx->d_windows, (uint32_t)ctx->rank, (uint32_t)ctx->world, ++ctx->xchg_seq, local, b, k,
-                                        reinterpret_cast<unsigned long long *>(d_ids), d_dist, d_xerr ? d_xerr : ctx->d_xchg_err,
-                                        kXchgAllRanks, ctx->stream));
+        XchgArgs x{ctx->d_windows, (uint32_t)ctx->rank, (uint32_t)ctx->world, ++ctx->xchg_seq, kXchgAllRanks, 0u,
+                   d_xerr ? d_xerr : ctx->d_xchg_err};
+        VROD_CUDA(launch_exchange_merge(x, local, b, k, reinterpret_cast<unsigned long long *>(d_ids), d_dist, ctx->stream));
         ctx->stats.kernel_launches++;
         if (used_fused) *used_fused = true;
         return VROD_OK;
@@ -1366,12 +1412,22 @@ static vrod_status exchange_enqueue(vrod_collection *c, uint32_t b, uint32_t k, 
 // All stages on one (single-GPU or per-rank) context.
 static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t b, uint32_t k, uint64_t *d_ids,
                                   float *d_dist, bool force_exact, int *d_status = nullptr, bool host_checks = false,
-                                  bool *used_scan = nullptr, int *d_xerr = nullptr, bool *used_fused = nullptr) {
+                                  bool *used_scan = nullptr, int *d_xerr = nullptr, bool *used_fused = nullptr,
+                                  bool *scan_fused = nullptr) {
     vrod_ctx *ctx = c->ctx;
     if (!d_status) d_status = ctx_status(ctx);
     ctx->cost.collect();
     LocalPass lp;
-    vrod_status st = local_enqueue(c, d_q, b, k, d_ids, d_dist, force_exact, d_status, host_checks, &lp);
+    FusePlan fuse;
+    if (ctx->world > 1) {
+        const ShardView s = shard_view(c);
+        fuse.on = can_fuse_scan(ctx, make_scan_plan(s, k, ctx->sms, false), make_scan_plan(s, k, ctx->sms, true), b, k);
+        fuse.x = XchgArgs{ctx->d_windows, (uint32_t)ctx->rank, (uint32_t)ctx->world, 0u, kXchgAllRanks, 0u, d_xerr ? d_xerr : ctx->d_xchg_err};
+        // two sequence numbers per call, used or not (all ranks count alike): the first pass, the conditional exact re-scans
+        fuse.seq_fast = ctx->xchg_seq + 1;
+        fuse.seq_exact = ctx->xchg_seq + 2;
+    }
+    vrod_status st = local_enqueue(c, d_q, b, k, d_ids, d_dist, force_exact, d_status, host_checks, &lp, &fuse);
     if (st != VROD_OK) return st;
     if (lp.batched) {
         st = batched_fetch_status(c, b, d_status);
@@ -1379,8 +1435,14 @@ static vrod_status search_enqueue(vrod_collection *c, const float *d_q, uint32_t
         if (st != VROD_OK) return st;
     }
     if (used_scan) *used_scan = lp.used_scan;
-    st = exchange_enqueue(c, b, k, d_ids, d_dist, d_xerr, used_fused);
-    if (st != VROD_OK) return st;
+    if (scan_fused) *scan_fused = lp.exchanged;
+    if (lp.exchanged) {
+        ctx->xchg_seq += 2;
+        if (used_fused) *used_fused = true;
+    } else {
+        st = exchange_enqueue(c, b, k, d_ids, d_dist, d_xerr, used_fused);
+        if (st != VROD_OK) return st;
+    }
     ctx->stats.searches += b;
     return VROD_OK;
 }
@@ -1479,9 +1541,13 @@ static vrod_status multi_search(vrod_collection *pc, const float *queries, uint3
     unsigned char *hpack = reinterpret_cast<unsigned char *>(P->ids_host.p);
     const bool fused = s0->fused_exchange && b <= kXchgMaxB && L.nres <= kXchgMaxHits;
     std::vector<LocalPass> lp(W);
+    std::vector<FusePlan> fuse(W);
     auto ids_of = [&](vrod_ctx *sub) { return reinterpret_cast<uint64_t *>(sub->out_ids.p); };
     auto dist_of = [&](vrod_ctx *sub) { return reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(sub->out_ids.p) + L.off_dist); };
     auto stat_of = [&](vrod_ctx *sub) { return reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(sub->out_ids.p) + L.off_stat); };
+    // single-query scans: the scan kernels push their lists to device 0 themselves (one kernel per device and query); two
+    // sequence numbers per call as in the per-rank mode (first pass, exact re-scans)
+    const uint32_t seq_fast = P->xchg_seq + 1, seq_exact = P->xchg_seq + 2;
     // stage 1: queries in, local pass on every device
     for (int r = 0; r < W; ++r) {
         vrod_ctx *sub = P->subs[r];
@@ -1490,9 +1556,18 @@ static vrod_status multi_search(vrod_collection *pc, const float *queries, uint3
         VROD_CUDA(sub->q_dev.ensure(qbytes));
         VROD_CUDA(sub->out_ids.ensure(L.bytes));
         VROD_CUDA(cudaMemcpyAsync(sub->q_dev.p, qh, qbytes, cudaMemcpyHostToDevice, sub->stream));
+        const ShardView sv = shard_view(pc->parts[r]);
+        fuse[r].on = can_fuse_scan(sub, make_scan_plan(sv, k, sub->sms, false), make_scan_plan(sv, k, sub->sms, true), b, k);
+        fuse[r].x = XchgArgs{sub->d_windows, (uint32_t)r, (uint32_t)W, 0u, 0u, 0u, stat_of(sub) + b};
+        fuse[r].seq_fast = seq_fast;
+        fuse[r].seq_exact = seq_exact;
+        // host_checks: with the fused exchange device 0 ends up with the OR of all devices' guard flags, and the host (which
+        // reads only device 0) starts the exact re-scans on every device
         st = local_enqueue(pc->parts[r], reinterpret_cast<const float *>(sub->q_dev.p), b, k, ids_of(sub), dist_of(sub), unsafe,
-                           stat_of(sub), false, &lp[r]);
+                           stat_of(sub), true, &lp[r], &fuse[r]);
         if (st != VROD_OK) return st;
+        if (lp[r].exchanged != lp[0].exchanged || lp[r].batched != lp[0].batched)
+            return fail(VROD_EINVAL, "internal error: the devices of a multi-GPU context chose different search paths");
         if (lp[r].batched) {
             st = batched_fetch_status(pc->parts[r], b, stat_of(sub));
             if (st != VROD_OK) return st;
@@ -1506,14 +1581,18 @@ static vrod_status multi_search(vrod_collection *pc, const float *queries, uint3
         st = batched_rescans(pc->parts[r], reinterpret_cast<const float *>(sub->q_dev.p), b, k, ids_of(sub), dist_of(sub), stat_of(sub));
         if (st != VROD_OK) return st;
     }
-    // stage 3: the lists meet on device 0
-    if (fused) {
+    // stage 3: the lists meet on device 0 (unless the scan kernels have seen to that)
+    const bool scan_fused = lp[0].exchanged;
+    if (scan_fused) {
+        P->xchg_seq += 2;
+    } else if (fused) {
         const uint32_t seq = ++P->xchg_seq;
         for (int r = 0; r < W; ++r) {
             vrod_ctx *sub = P->subs[r];
             VROD_CUDA(cudaSetDevice(sub->device));
-            VROD_CUDA(launch_exchange_merge(sub->d_windows, (uint32_t)r, (uint32_t)W, seq, reinterpret_cast<const Hit *>(sub->hits_local.p), b, k,
-                                            reinterpret_cast<unsigned long long *>(ids_of(sub)), dist_of(sub), stat_of(sub) + b, 0u, sub->stream));
+            XchgArgs x{sub->d_windows, (uint32_t)r, (uint32_t)W, seq, 0u, 0u, stat_of(sub) + b};
+            VROD_CUDA(launch_exchange_merge(x, reinterpret_cast<const Hit *>(sub->hits_local.p), b, k,
+                                            reinterpret_cast<unsigned long long *>(ids_of(sub)), dist_of(sub), sub->stream));
             sub->stats.kernel_launches++;
         }
     } else {
@@ -1539,8 +1618,39 @@ static vrod_status multi_search(vrod_collection *pc, const float *queries, uint3
     VROD_CUDA(cudaSetDevice(s0->device));
     VROD_CUDA(cudaMemcpyAsync(hpack, s0->out_ids.p, L.bytes, cudaMemcpyDeviceToHost, s0->stream));
     VROD_CUDA(cudaStreamSynchronize(s0->stream));
-    if (fused && reinterpret_cast<const int *>(hpack + L.off_stat)[b] == 1)
+    if ((fused || scan_fused) && reinterpret_cast<const int *>(hpack + L.off_stat)[b] == 1)
         return fail(VROD_ENCCL, "peer exchange timed out: a device did not deliver its lists");
+    if (scan_fused && !unsafe) {
+        // device 0 holds the OR of all devices' guard flags: the flagged queries are re-scanned exactly on every device, the
+        // lists meet on device 0 again
+        const int *hs = reinterpret_cast<const int *>(hpack + L.off_stat);
+        std::vector<uint32_t> flagged;
+        for (uint32_t qi = 0; qi < b; ++qi)
+            if (hs[qi]) flagged.push_back(qi);
+        if (!flagged.empty()) {
+            for (int r = 0; r < W; ++r) {
+                vrod_ctx *sub = P->subs[r];
+                VROD_CUDA(cudaSetDevice(sub->device));
+                const ShardView sv = shard_view(pc->parts[r]);
+                const ScanPlan xp = make_scan_plan(sv, k, sub->sms, true);
+                const ScanScratch scr = scan_scratch(sub, stat_of(sub));
+                XchgArgs x{sub->d_windows, (uint32_t)r, (uint32_t)W, seq_exact, 0u, 0u, stat_of(sub) + b};
+                Hit *local = reinterpret_cast<Hit *>(sub->hits_local.p);
+                for (uint32_t qi : flagged) {
+                    x.qi = qi;
+                    VROD_CUDA(launch_exact_scan(sv, reinterpret_cast<const float *>(sub->q_dev.p) + (size_t)qi * sv.ld, k, xp, scr, nullptr,
+                                                local + (size_t)qi * k, reinterpret_cast<unsigned long long *>(ids_of(sub)) + (size_t)qi * k,
+                                                dist_of(sub) + (size_t)qi * k, sub->stream, &x));
+                    sub->stats.kernel_launches++;
+                }
+            }
+            VROD_CUDA(cudaSetDevice(s0->device));
+            VROD_CUDA(cudaMemcpyAsync(hpack, s0->out_ids.p, L.bytes, cudaMemcpyDeviceToHost, s0->stream));
+            VROD_CUDA(cudaStreamSynchronize(s0->stream));
+            if (reinterpret_cast<const int *>(hpack + L.off_stat)[b] == 1)
+                return fail(VROD_ENCCL, "peer exchange timed out: a device did not deliver its lists");
+        }
+    }
     memcpy(out_ids, hpack, L.nres * sizeof(uint64_t));
     memcpy(out_dist, hpack + L.off_dist, L.nres * sizeof(float));
     P->stats.searches += b;
@@ -1582,18 +1692,20 @@ static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *
     float *d_dist = reinterpret_cast<float *>(dpack + L.off_dist);
     int *d_stat = reinterpret_cast<int *>(dpack + L.off_stat);
     VROD_CUDA(cudaMemcpyAsync(ctx->q_dev.p, qh, qbytes, cudaMemcpyHostToDevice, ctx->stream));
-    bool used_scan = false, used_fused = false;
+    bool used_scan = false, used_fused = false, scan_fused = false;
     st = search_enqueue(c, reinterpret_cast<const float *>(ctx->q_dev.p), b, k, d_ids, d_dist, unsafe, d_stat, true, &used_scan,
-                        d_stat + b, &used_fused);
+                        d_stat + b, &used_fused, &scan_fused);
     if (st != VROD_OK) return st;
     VROD_CUDA(cudaMemcpyAsync(hpack, dpack, L.bytes, cudaMemcpyDeviceToHost, ctx->stream));
     VROD_CUDA(cudaStreamSynchronize(ctx->stream));
     // (the flag word is written only by the fused exchange kernel: the all-gather path leaves stale bytes there)
     if (used_fused && reinterpret_cast<const int *>(hpack + L.off_stat)[b] == 1)
         return fail(VROD_ENCCL, "peer exchange timed out: a rank did not take part in this search");
-    if (ctx->world == 1 && !unsafe && (used_scan || n_unsafe)) {
+    if ((ctx->world == 1 || scan_fused) && !unsafe && (used_scan || n_unsafe)) {
         // the scans ran without their device-side conditional rescans: answer the flagged queries exactly now,
-        // and with them the queries that were out of range for the fast paths
+        // and with them the queries that were out of range for the fast paths.  (Sharded context with the exchange
+        // fused into the scans: the flags are the OR over all ranks, so every rank re-scans the same queries, and the
+        // re-scans exchange again under the call's second sequence number.)
         int *hs = reinterpret_cast<int *>(hpack + L.off_stat);
         bool any = false;
         for (uint32_t qi = 0; qi < b; ++qi) {
@@ -1605,15 +1717,19 @@ static vrod_status vrod_collection_search_impl(vrod_collection *c, const float *
             const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
             const ScanScratch scr = scan_scratch(ctx, d_stat);
             Hit *local = reinterpret_cast<Hit *>(ctx->hits_local.p);
+            XchgArgs x{ctx->d_windows, (uint32_t)ctx->rank, (uint32_t)ctx->world, ctx->xchg_seq, kXchgAllRanks, 0u, d_stat + b};
             for (uint32_t qi = 0; qi < b; ++qi) {
                 if (!hs[qi]) continue;
+                x.qi = qi;
                 VROD_CUDA(launch_exact_scan(s, reinterpret_cast<const float *>(ctx->q_dev.p) + (size_t)qi * s.ld, k, xp, scr, nullptr,
                                             local + (size_t)qi * k, reinterpret_cast<unsigned long long *>(d_ids) + (size_t)qi * k,
-                                            d_dist + (size_t)qi * k, ctx->stream));
+                                            d_dist + (size_t)qi * k, ctx->stream, scan_fused ? &x : nullptr));
                 ctx->stats.kernel_launches++;
             }
-            VROD_CUDA(cudaMemcpyAsync(hpack, dpack, L.off_stat, cudaMemcpyDeviceToHost, ctx->stream));
+            VROD_CUDA(cudaMemcpyAsync(hpack, dpack, L.bytes, cudaMemcpyDeviceToHost, ctx->stream));
             VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (scan_fused && reinterpret_cast<const int *>(hpack + L.off_stat)[b] == 1)
+                return fail(VROD_ENCCL, "peer exchange timed out: a rank did not take part in this search");
         }
     }
     memcpy(out_ids, hpack, L.nres * sizeof(uint64_t));
