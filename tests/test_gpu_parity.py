@@ -276,3 +276,23 @@ def test_collection_grows_and_round_trips_through_a_file(ctx, oracle, tmp_path):
         ctx.load("junk", tmp_path / "junk.vrc")
     ctx.drop("grow")
     ctx.drop("grow2")
+
+
+@pytest.mark.parametrize("path", [1, 2, 3], ids=["scan", "exact", "batched"])
+def test_thousands_of_rows_at_exactly_the_same_distance(ctx, oracle, path):
+    """Sparse rows under the cosine metric: 44 % of the rows are all-zero (distance exactly 1 by the zero-norm rule) and
+    most of the others are orthogonal to the query (distance exactly 1 as well), so the top k is a handful of real
+    neighbours followed by rows ordered by id alone.  Every head of every per-CTA list then carries the same distance,
+    and no bound made from the heads is tight: the last-CTA merge must fall back to its depth walk instead of
+    overflowing its buffer, the guards must flag what they cannot prove, and the answer is still the oracle's."""
+    rng = np.random.default_rng(21)
+    n, d, b, k = 14457, 16, 40, 120
+    X = (rng.standard_normal((n, d)) * (rng.random((n, d)) < 0.05)).astype(np.float32)
+    Q = (rng.standard_normal((b, d)) * (rng.random((b, d)) < 0.05)).astype(np.float32)
+    Q[0] = 0                                  # a zero query: every distance is 1
+    c = ctx.create(f"ties{path}", d, 1, n)
+    c.insert(X)
+    c.set_path(path)
+    assert_same(*c.search(Q, k), *oracle.search(X, Q, k, 1), f"ties, path {path}")
+    assert_same(*c.search(Q[:3], 1000), *oracle.search(X, Q[:3], 1000, 1), f"ties, k = 1000, path {path}")
+    ctx.drop(c.name)

@@ -55,6 +55,16 @@ def main():
         print(f"case {i:2d} {kind:10s} n={n:6d} d={d:3d} b={b:3d} k={k:3d} metric={metric} path={path}: "
               f"{'OK' if ok else 'MISMATCH in %d queries' % wrong} batched={s1['batched_tiles'] > s0['batched_tiles']} "
               f"rescanned={s1['fast_scans'] - s0['fast_scans']}", flush=True)
+        if not ok:
+            wq = np.where((ids != rid).any(axis=1) | (dist.view(np.uint32) != rdist.view(np.uint32)).any(axis=1))[0]
+            q0 = int(wq[0])
+            j0 = int(np.where((ids[q0] != rid[q0]) | (dist[q0].view(np.uint32) != rdist[q0].view(np.uint32)))[0][0])
+            print(f"   wrong queries {wq[:12].tolist()}; query {q0} first differs at rank {j0}: got id {ids[q0, j0]} dist {dist[q0, j0]!r}, "
+                  f"want id {rid[q0, j0]} dist {rdist[q0, j0]!r}; |q|^2 = {float((Q[q0].astype(np.float64) ** 2).sum())!r}; "
+                  f"got-id in wanted list: {int(ids[q0, j0]) in set(rid[q0].tolist())}, wanted-id in got list: {int(rid[q0, j0]) in set(ids[q0].tolist())}", flush=True)
+            lo, hi = max(0, j0 - 2), min(k, j0 + 4)
+            print("   got ", ids[q0, lo:hi].tolist(), dist[q0, lo:hi].tolist())
+            print("   want", rid[q0, lo:hi].tolist(), rdist[q0, lo:hi].tolist(), flush=True)
         bad += 0 if ok else 1
         ctx.drop(c.name)
     print(f"soak done: {ncase} cases, {bad} mismatching, {time.time() - t0:.0f} s")

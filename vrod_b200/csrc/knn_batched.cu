@@ -920,7 +920,8 @@ __global__ void __launch_bounds__(256) build_mirror_kernel(const float *__restri
 template <bool COS>
 __global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restrict__ q, uint32_t b, uint32_t slots, uint32_t ld, uint32_t kd, uint32_t T,
                                                            const unsigned int *__restrict__ maxnorm_bits, unsigned char *__restrict__ qt,
-                                                           float *__restrict__ gthr, float *__restrict__ qcap, float cap_sign) {
+                                                           float *__restrict__ gthr, float *__restrict__ qcap, float cap_sign,
+                                                           float *__restrict__ qband, float eps_dot, float acc_eps) {
     const int lane = threadIdx.x & 31;
     const uint32_t qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= slots) return;
@@ -965,6 +966,14 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restri
     if (lane == 0 && live) {
         gthr[qi] = thr;
         qcap[qi] = thr;
+        if (qband) {
+            // twice the error bound of the approximate surrogate (the guard's E in batched_finish_kernel, with |u| <= cap),
+            // rounded up generously: it is a width, not a proof -- the proof stays with the guard
+            const float Ms = sqrtf(M * 1.0000002f);
+            const float E = COS ? (eps_dot + 4.2e-7f) * nqs + acc_eps * (2.01f * nqs + thr)
+                                : (eps_dot + 2.4e-7f) * Ms * nqs + 2.4e-7f * (0.5f * M + thr) + acc_eps * (Ms * nqs + 0.5f * M + 2.f * thr);
+            qband[qi] = 2.1f * E + 1e-30f;
+        }
     }
 }
 
@@ -980,7 +989,7 @@ struct FinishParams {
     uint32_t qgroups, units, psz;   // list layout of the tile kernel: unit u = g + m*qgroups, CTA = u*psz + r
     const unsigned long long *cand;
     const int *cnt_in;
-    const int *qflags;
+    int *qflags;                        // [b] |= 1: the query cannot be proven from its lists (in: tile kernels; out: a merge that overran)
     const unsigned int *maxnorm_bits;   // max ||x||^2 of the shard, f32 bits
     unsigned long long *glist;          // [b][kprime] best keys over the phases so far (in/out)
     int *gcnt;                          // [b]
@@ -997,6 +1006,11 @@ struct FinishParams {
     uint32_t ld_h, kd, T;
     const float *qcap;      // [b] the finite start threshold (above every surrogate)
     double acc_eps;         // f32 accumulation noise of the folded contraction, relative to |dot| + |thr| + |hx|
+    // BAND mode (keep > kprime): instead of the kprime best approximate keys a query keeps EVERY key within `band` of its
+    // k-th best one -- twice the error bound of the approximate surrogate, so the exact top k is among them by
+    // construction (tight clusters: whatever the contraction cannot tell apart becomes a candidate, up to `keep` of them)
+    int need, keep;         // rank of the key the threshold hangs on (kprime, band mode: k); stride and capacity of glist
+    const float *qband;     // [b] band width per query (nullptr: classic mode)
 };
 
 constexpr int kFinCtl = 128;
@@ -1026,6 +1040,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
     // offsets of this query's lists (previous global list first, then one list per CTA of the group):
     // warp 0 loads the counts and scans them 32 at a time
     int *hist = reinterpret_cast<int *>(buf + p.cap);   // [kFinHist] block_select scratch
+    const float band = p.qband ? p.qband[qi] : 0.f;
     int *offs = hist + kFinHist;                        // [nlists + 2]
     if (warp == 0) {
         int carry = p.first_phase ? 0 : p.gcnt[qi];
@@ -1053,7 +1068,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
         const int prev = offs[1];
         for (int i = tid; i < total; i += kScanThreads) {
             if (i < prev) {
-                buf[i] = p.glist[(size_t)qi * p.kprime + i];
+                buf[i] = p.glist[(size_t)qi * p.keep + i];
             } else {
                 uint32_t lo = 0, hi = nlists - 1;   // largest m with offs[m + 1] <= i
                 while (lo < hi) {
@@ -1070,11 +1085,11 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
         // more entries than the sort buffer holds (phase 0, or a candidate-heavy phase): stream them through the
         // threshold filter in rounds of as many entries as fit next to the kprime survivors
         const int prev = offs[1];
-        for (int i = tid; i < prev; i += kScanThreads) buf[i] = p.glist[(size_t)qi * p.kprime + i];
+        for (int i = tid; i < prev; i += kScanThreads) buf[i] = p.glist[(size_t)qi * p.keep + i];
         __syncthreads();
         if (tid == 0) ctl->cnt = prev;
         __syncthreads();
-        block_select<kFinPer>(ctl, buf, p.kprime, p.cap, tid, hist);
+        block_select<kFinPer>(ctl, buf, p.need, p.cap, tid, hist, band, p.qband ? p.keep : 0);
         // rounds of as many whole LISTS as the buffer has room for (a list holds at most CAP = cap/2 keys and a
         // select runs whenever the buffer is more than half full, so at least one list always fits).  A warp takes
         // a list at a time, its lanes read consecutive keys (4 independent loads each) -- no per-key search of the
@@ -1112,20 +1127,23 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
             }
             __syncthreads();
             m0 = m1;
-            const bool no_threshold_yet = ctl->thrkey == kKeyMax && ctl->cnt >= p.kprime;
-            if (m0 < nlists && (ctl->cnt > p.cap / 2 || no_threshold_yet)) block_select<kFinPer>(ctl, buf, p.kprime, p.cap, tid, hist);   // uniform
+            const bool no_threshold_yet = ctl->thrkey == kKeyMax && ctl->cnt >= p.need;
+            if (m0 < nlists && (ctl->cnt > p.cap / 2 || no_threshold_yet)) block_select<kFinPer>(ctl, buf, p.need, p.cap, tid, hist, band, p.qband ? p.keep : 0);   // uniform
         }
     }
     __syncthreads();
-    block_select<kFinPer>(ctl, buf, p.kprime, p.cap, tid, hist);
+    block_select<kFinPer>(ctl, buf, p.need, p.cap, tid, hist, band, p.qband ? p.keep : 0);
 
     const int ncand = ctl->cnt;
     if (!p.final_phase) {
-        for (int i = tid; i < ncand; i += kScanThreads) p.glist[(size_t)qi * p.kprime + i] = buf[i];
+        for (int i = tid; i < ncand; i += kScanThreads) p.glist[(size_t)qi * p.keep + i] = buf[i];
         if (tid == 0) {
             p.gcnt[qi] = ncand;
+            // a merge that could not hold everything it had to keep (band mode: more rows inside the error band than the list
+            // has room for) has dropped keys: the flag must outlive this launch, the last phase cannot know
+            if (ctl->overflow) atomicOr(p.qflags + qi, 1);
             // (the kept keys are unsorted: the kprime-th one is the select's threshold key)
-            float thr = ncand == p.kprime ? ord2f((uint32_t)(ctl->thrkey >> 32)) : __int_as_float(0x7f800000);
+            float thr = ctl->thrkey != kKeyMax ? ord2f((uint32_t)(ctl->thrkey >> 32)) : __int_as_float(0x7f800000);
             if (p.qt) {   // bf16 mode: finite thresholds only, folded into the query mirror as three exact parts
                 const float cap = p.qcap[qi];
                 if (!(thr < cap)) thr = cap;
@@ -1142,7 +1160,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
         return;
     }
     // u = the largest kept approximate key: the select's threshold key, or the tail of the (sorted) short list
-    if (tid == 0) ctl->u_val = ncand == p.kprime ? ord2f((uint32_t)(ctl->thrkey >> 32)) : (ncand > 0 ? ord2f((uint32_t)(buf[ncand - 1] >> 32)) : 0.f);
+    if (tid == 0) ctl->u_val = ctl->thrkey != kKeyMax ? ord2f((uint32_t)(ctl->thrkey >> 32)) : (ncand > 0 ? ord2f((uint32_t)(buf[ncand - 1] >> 32)) : 0.f);
     __syncthreads();
     rerank_candidates<COS>(buf, ncand, p.rows4, q4, (int)p.ld4, ctl->nq, warp, lane);
     __syncthreads();
@@ -1272,7 +1290,7 @@ bool batched_supported(const ShardView &s, uint32_t b, uint32_t k) {
 
 cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t b, uint32_t k, int sm_count, void **scratch,
                                   size_t *scratch_bytes, int *status, Hit *out, unsigned long long *out_ids, float *out_dist,
-                                  cudaStream_t st, BatchedStats *stats, cudaEvent_t ev_start, cudaEvent_t ev_stop) {
+                                  cudaStream_t st, BatchedStats *stats, cudaEvent_t ev_start, cudaEvent_t ev_stop, bool band_mode) {
     // operand mode: bf16 mirrors with folded thresholds when the collection has a mirror, else the stored f32 rows as tf32
     const bool H = s.rows_h != nullptr;
     const uint32_t kd = mirror_kd(s.dim), ld_h = mirror_ld(s.dim);
@@ -1296,6 +1314,11 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
     // shows a single CTA already issues its M = 128 x N = 256 MMAs at the tensor core's full rate (128.0 cycles each)
     // with the operand copies and the accumulator reads running, so pairing has nothing to give here.
     const uint32_t psz = 1u;
+    // band mode (bf16 operand mode only): every key within the error band above the k-th best approximate key is kept, up to
+    // kBandKeep per query
+    constexpr int kBandKeep = 1024;
+    const bool band = band_mode && H && (int)k <= kBandKeep / 2;
+    const int keep = band ? kBandKeep : kprime;
     const uint32_t max_units = (uint32_t)sm_count / psz;
     const uint32_t super_tiles = (ntiles + psz - 1) / psz;
 
@@ -1314,9 +1337,9 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         const size_t cand_bytes = (size_t)grid * BN * CAP * sizeof(unsigned long long);
         const size_t cnt_bytes = (size_t)grid * BN * sizeof(int);
         const size_t flag_bytes = (((size_t)bq * sizeof(int)) + 255) & ~(size_t)255;
-        const size_t glist_bytes = (size_t)bq * kprime * sizeof(unsigned long long);
+        const size_t glist_bytes = (size_t)bq * keep * sizeof(unsigned long long);
         const size_t qh_bytes = H ? (size_t)groups * T * KB_B : 0;                    // tiled query mirror of the wave
-        const size_t need = cand_bytes + cnt_bytes + 4 * flag_bytes + glist_bytes + qh_bytes + 2048;
+        const size_t need = cand_bytes + cnt_bytes + 5 * flag_bytes + glist_bytes + qh_bytes + 2048;
         if (*scratch_bytes < need) {
             if (*scratch) cudaFree(*scratch);
             *scratch = nullptr;
@@ -1332,9 +1355,10 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         int *gcnt = reinterpret_cast<int *>(base + cand_bytes + cnt_bytes + flag_bytes);
         float *gthr = reinterpret_cast<float *>(base + cand_bytes + cnt_bytes + 2 * flag_bytes);
         float *qcap = reinterpret_cast<float *>(base + cand_bytes + cnt_bytes + 3 * flag_bytes);
-        unsigned long long *glist = reinterpret_cast<unsigned long long *>(base + cand_bytes + cnt_bytes + 4 * flag_bytes);
+        float *qband = reinterpret_cast<float *>(base + cand_bytes + cnt_bytes + 4 * flag_bytes);
+        unsigned long long *glist = reinterpret_cast<unsigned long long *>(base + cand_bytes + cnt_bytes + 5 * flag_bytes);
         // (kept 1 KB aligned: bulk copies need 16-byte aligned sources)
-        unsigned char *qt = base + ((cand_bytes + cnt_bytes + 4 * flag_bytes + glist_bytes + 1023) & ~(size_t)1023);
+        unsigned char *qt = base + ((cand_bytes + cnt_bytes + 5 * flag_bytes + glist_bytes + 1023) & ~(size_t)1023);
         e = cudaMemsetAsync(qflags, 0, flag_bytes, st);
         if (e != cudaSuccess) return e;
 
@@ -1346,7 +1370,9 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             const char *dbg = kDbg ? getenv("VROD_BATCHED_DEBUG") : nullptr;
             const bool nocand = dbg && (strstr(dbg, "nocand") || strstr(dbg, "noepi") || strstr(dbg, "nomma") || strstr(dbg, "ldonly"));
             const uint32_t slots = groups * BN;
-            prep<<<(slots + 7) / 8, 256, 0, st>>>(qw, bq, slots, s.ld, kd, T, s.maxnorm_bits, qt, gthr, qcap, nocand ? -1.f : 1.f);
+            const float acc_eps_f = (float)((double)(ld_h / UMMA_K_H + 2) * ldexp(1.0, -23));
+            prep<<<(slots + 7) / 8, 256, 0, st>>>(qw, bq, slots, s.ld, kd, T, s.maxnorm_bits, qt, gthr, qcap, nocand ? -1.f : 1.f,
+                                                  band ? qband : nullptr, (float)eps_dot, acc_eps_f);
             if (stats) stats->launches += 1;
         } else if (!make_map(&tmX, s.rows, s.n, s.ld, BM) || !make_map(&tmQ, qw, bq, s.ld, BN / psz)) {
             return cudaErrorInvalidValue;
@@ -1364,7 +1390,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         p.cand = cand;
         p.cnt_out = cnt;
         p.qflags = qflags;
-        p.kprime = kprime;
+        p.kprime = band ? CAP : kprime;   // band mode: a list may need more than kprime entries, nothing may be pruned away
         if (kDbg) {
             const char *dbg = getenv("VROD_BATCHED_DEBUG");
             p.debug_nocand = dbg && (strcmp(dbg, "nocand") == 0 || strstr(dbg, "noepi") || strstr(dbg, "nomma") || strstr(dbg, "ldonly"));
@@ -1451,6 +1477,9 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         f.k = k;
         f.id_base = s.id_base;
         f.kprime = kprime;
+        f.need = band ? (int)k : kprime;
+        f.keep = keep;
+        f.qband = band ? qband : nullptr;
         f.cap = kFinCap;
         f.water = f.cap - kScanThreads;
         f.qgroups = groups;

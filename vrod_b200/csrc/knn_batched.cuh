@@ -29,9 +29,12 @@ bool batched_supported(const ShardView &s, uint32_t b, uint32_t k);
 // device buffer the callee may grow.  status[qi] = 1 marks a query whose guard failed (the caller
 // rescans it); out receives b x k hits and, when out_ids/out_dist are not null, the final ids / distances as well
 // (single-GPU contexts: no merge kernel needed).  ev_start/ev_stop, when given, bracket the tile kernels.
+// band_mode: keep every candidate within the approximate surrogate's error band above the k-th best one (up to 1024 per
+// query) instead of a fixed k' of them -- for collections whose neighbours the bf16 contraction cannot tell apart (tight
+// clusters under the Euclidean metric), where the fixed-k' proof fails for every query.
 cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t b, uint32_t k, int sm_count,
                                   void **scratch, size_t *scratch_bytes, int *status, Hit *out, unsigned long long *out_ids,
                                   float *out_dist, cudaStream_t st, BatchedStats *stats, cudaEvent_t ev_start = nullptr,
-                                  cudaEvent_t ev_stop = nullptr);
+                                  cudaEvent_t ev_stop = nullptr, bool band_mode = false);
 
 }  // namespace vrod

@@ -247,12 +247,27 @@ __device__ __forceinline__ void block_prune(CandCtl *ctl, unsigned long long *bu
 // (3-4 passes on real lists, 8 at most).  ~5x fewer instructions than the 1024-key bitonic sort that dominated
 // batched_finish_kernel in round 1.  `hist` is 256 + 4 ints of shared memory.  All threads call it after a
 // __syncthreads(); cnt <= cap <= MAXPER * kScanThreads.
+// BAND mode (keep_max > 0): T is the kprime-th smallest key as before, but everything up to T + band survives (at most
+// keep_max keys; more than that raises ctl->overflow) and the threshold becomes T + band: the caller keeps every
+// candidate whose approximate key lies within the error band above the k-th best one instead of a fixed number of them.
+__device__ __forceinline__ unsigned long long band_key(unsigned long long T, float band) {
+    if (T == kKeyMax) return kKeyMax;
+    return make_key(__fadd_ru(ord2f((uint32_t)(T >> 32)), band), 0xffffffffu);
+}
 template <int MAXPER>
-__device__ __forceinline__ void block_select(CandCtl *ctl, unsigned long long *buf, int kprime, int cap, int tid, int *hist) {
+__device__ __forceinline__ void block_select(CandCtl *ctl, unsigned long long *buf, int kprime, int cap, int tid, int *hist, float band = 0.f,
+                                             int keep_max = 0) {
     int cnt = ctl->cnt;
     if (cnt > cap) cnt = cap;
     if (cnt <= kprime) {   // uniform: nothing to drop (short lists are cheap to sort)
         block_prune(ctl, buf, kprime, cap, tid);
+        if (keep_max > 0) {
+            if (tid == 0 && ctl->thrkey != kKeyMax) {
+                ctl->thrkey = band_key(ctl->thrkey, band);
+                ctl->thr_f = ord2f((uint32_t)(ctl->thrkey >> 32));
+            }
+            __syncthreads();
+        }
         return;
     }
     unsigned long long key[MAXPER];
@@ -326,6 +341,28 @@ __device__ __forceinline__ void block_select(CandCtl *ctl, unsigned long long *b
     }
     __syncthreads();
     const unsigned long long T = *tkey;
+    if (keep_max > 0) {
+        // band mode: everything at or below T + band survives
+        const unsigned long long Tb = band_key(T, band);
+#pragma unroll
+        for (int e = 0; e < MAXPER; ++e)
+            if (tid + e * kScanThreads < cnt && key[e] <= Tb) {
+                const int pos = atomicAdd(&ctl->cnt, 1);
+                if (pos < keep_max) buf[pos] = key[e];
+            }
+        __syncthreads();
+        if (tid == 0) {
+            if (ctl->cnt > keep_max) {
+                ctl->overflow = 1;   // the band holds more rows than the list: the query cannot be proven from here
+                ctl->cnt = keep_max;
+            }
+            ctl->thrkey = Tb;
+            ctl->thr_f = ord2f((uint32_t)(Tb >> 32));
+            ctl->prune_req = 0;
+        }
+        __syncthreads();
+        return;
+    }
     // compaction: keys below T all survive; keys equal to T fill up to kprime (keys are unique in practice)
 #pragma unroll
     for (int e = 0; e < MAXPER; ++e)

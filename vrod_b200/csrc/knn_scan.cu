@@ -179,6 +179,7 @@ __device__ __forceinline__ bool finish_and_merge(CandCtl *ctl, unsigned long lon
     }
     __syncthreads();
     const unsigned long long t0key = ctl->thrkey;    // kKeyMax: fewer than kprime non-empty lists
+    const int ov_before = ctl->overflow;             // (this CTA's own scan; the gather below may raise the flag for its own reasons)
     if (kDbg && p.dbg && tid == 0) p.dbg[6] = gtimer();
     const int room = p.cap - nlists - 2;
     auto keep = [&](unsigned long long key) {
@@ -219,13 +220,27 @@ __device__ __forceinline__ bool finish_and_merge(CandCtl *ctl, unsigned long lon
     }
     __syncthreads();
     if (kDbg && p.dbg && tid == 0) p.dbg[7] = gtimer();
-    if (ctl->cnt > room) {   // (uniform) more survivors than the buffer holds next to the staged heads: give the query up
-        if (tid == 0) ctl->cnt = room;
+    // The depth walk: the lists are read one level at a time and pruned on the way, so that the buffer never has to hold
+    // more than a level.  It takes over (a) when there is no finite T0 -- fewer non-empty lists than kprime: large k on a
+    // small grid, tiny collections -- and (b) when more keys lie at or below T0 than the buffer holds: T0 is only as
+    // tight as the heads are spread, and thousands of rows at exactly the same distance (sparse rows under the cosine
+    // metric: half the collection at distance 1, ordered by id alone) put thousands of keys below any head-based bound.
+    bool walk = t0key == kKeyMax;
+    if (!walk && ctl->cnt > room) {   // (uniform)
+        walk = true;
         __syncthreads();
+        if (tid == 0) {
+            cand_reset(ctl);
+            ctl->overflow = ov_before;   // (what the gather could not hold raised the flag; nothing is lost, it starts over)
+        }
+        __syncthreads();
+#pragma unroll
+        for (int li = 0; li < kMaxListsPerThread; ++li)
+            if (head[li] != kKeyMax) buf[atomicAdd(&ctl->cnt, 1)] = head[li];   // nlists <= cap
+        __syncthreads();
+        block_prune(ctl, buf, p.kprime, p.cap, tid);
     }
-    // Fewer non-empty lists than kprime (large k on a small grid, tiny collections): no finite T0.  Walk the lists by
-    // depth instead, pruning on the way, so that the buffer never has to hold all of them.
-    if (t0key == kKeyMax) {
+    if (walk) {
         const int water = p.cap - nlists;
         unsigned int active = 0;
 #pragma unroll

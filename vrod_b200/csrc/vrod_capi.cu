@@ -266,6 +266,10 @@ struct vrod_collection {
     // automatic path choice discounts the batched pass by it, so that data the tensor-core pass cannot resolve
     // (tight clusters under the Euclidean metric) stops paying for a pass that proves nothing
     double rescan_share = 0.0;
+    // the batched pass keeps every candidate inside the approximate surrogate's error band (knn_batched.cuh: band_mode)
+    // instead of a fixed k' of them: switched on, for good, by the first batch whose fixed-k' proofs fail for more than
+    // 5 % of the queries (tight clusters under the Euclidean metric)
+    bool band_mode = false;
     std::vector<vrod_collection *> parts;   // collection of a multi-GPU parent context: one part per device, in id order
 };
 
@@ -1187,6 +1191,57 @@ static ScanScratch scan_scratch(vrod_ctx *ctx, int *d_status) {
                        d_status, ctx->dev_counters};
 }
 
+// The batched (tensor-core) pass of this rank's shard: mirror upkeep, the phased tile / finish launches.  The guard flags
+// land in d_status; the caller reads them back (batched_fetch_status) and re-answers the flagged queries (batched_rescans).
+static vrod_status enqueue_batched(vrod_collection *c, const float *d_q, uint32_t b, uint32_t k, uint64_t *d_ids, float *d_dist,
+                                   int *d_status) {
+    vrod_ctx *ctx = c->ctx;
+    const ShardView s = shard_view(c);
+    Hit *local = reinterpret_cast<Hit *>(ctx->hits_local.p);
+    const bool direct = ctx->world == 1;
+    ShardView sb = s;
+    if (c->path != 4 && !c->mirror_failed) {
+        // bf16 operand mirror: allocate once for the shard's capacity, convert the rows appended since the last time
+        if (!c->rows_h) {
+            // VROD_NO_MIRROR=1 behaves like a failed allocation (tests of the fallback; memory-tight deployments)
+            static const bool no_mirror = getenv("VROD_NO_MIRROR") != nullptr;
+            const cudaError_t me = no_mirror ? cudaErrorMemoryAllocation : cudaMalloc(&c->rows_h, mirror_bytes(c->shard_rows, c->dim));
+            if (me != cudaSuccess) {
+                cudaGetLastError();
+                c->rows_h = nullptr;
+                c->mirror_failed = true;
+            }
+            c->mirror_rows = 0;
+        }
+        if (c->rows_h) {
+            if (c->mirror_rows < c->local) {
+                VROD_CUDA(launch_build_mirror(s, c->rows_h, (uint32_t)c->mirror_rows, (uint32_t)(c->local - c->mirror_rows), ctx->stream));
+                ctx->stats.kernel_launches++;
+                c->mirror_rows = c->local;
+            }
+            sb.rows_h = c->rows_h;
+        }
+    }
+    BatchedStats bs{};
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool sample = false;
+    if (ctx->profiling) {
+        e0 = ctx->prof_event();
+        e1 = ctx->prof_event();
+    } else if (ctx->cost.want_sample()) {
+        sample = ctx->cost.events(&e0, &e1);
+    }
+    cudaError_t e = launch_batched_search(sb, d_q, b, k, ctx->sms, &ctx->batched.p, &ctx->batched.bytes, d_status, local,
+                                          direct ? reinterpret_cast<unsigned long long *>(d_ids) : nullptr, direct ? d_dist : nullptr,
+                                          ctx->stream, &bs, e0, e1, c->band_mode);
+    if (e != cudaSuccess) return fail(VROD_ECUDA, std::string("batched search: ") + cudaGetErrorString(e));
+    if (sample)
+        ctx->cost.pending(2, (double)((b + 255) / 256) * ((double)s.n / 128.0) * ((double)mirror_ld(s.dim) / 144.0) / (double)ctx->sms);
+    ctx->stats.kernel_launches += bs.launches;
+    ctx->stats.batched_tiles += bs.tiles;
+    return VROD_OK;
+}
+
 // Stage 1.  Queries already on the device as [b x ld]; enqueue the local pass, no synchronisation.  On a single-GPU
 // context the kernels write d_ids / d_dist themselves; otherwise the local hits land in ctx->hits_local.
 // d_status: per-query guard flags (device).  host_checks: the caller reads d_status after synchronising and rescans the
@@ -1233,46 +1288,8 @@ static vrod_status local_enqueue(vrod_collection *c, const float *d_q, uint32_t 
     auto oid = [&](uint32_t qi) { return direct ? reinterpret_cast<unsigned long long *>(d_ids) + (size_t)qi * k : nullptr; };
     auto odd = [&](uint32_t qi) { return direct ? d_dist + (size_t)qi * k : nullptr; };
     if (batched) {
-        ShardView sb = s;
-        if (c->path != 4 && !c->mirror_failed) {
-            // bf16 operand mirror: allocate once for the shard's capacity, convert the rows appended since the last time
-            if (!c->rows_h) {
-                // VROD_NO_MIRROR=1 behaves like a failed allocation (tests of the fallback; memory-tight deployments)
-                static const bool no_mirror = getenv("VROD_NO_MIRROR") != nullptr;
-                const cudaError_t me = no_mirror ? cudaErrorMemoryAllocation
-                                                 : cudaMalloc(&c->rows_h, mirror_bytes(c->shard_rows, c->dim));
-                if (me != cudaSuccess) {
-                    cudaGetLastError();
-                    c->rows_h = nullptr;
-                    c->mirror_failed = true;
-                }
-                c->mirror_rows = 0;
-            }
-            if (c->rows_h) {
-                if (c->mirror_rows < c->local) {
-                    VROD_CUDA(launch_build_mirror(s, c->rows_h, (uint32_t)c->mirror_rows, (uint32_t)(c->local - c->mirror_rows), ctx->stream));
-                    ctx->stats.kernel_launches++;
-                    c->mirror_rows = c->local;
-                }
-                sb.rows_h = c->rows_h;
-            }
-        }
-        BatchedStats bs{};
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        bool sample = false;
-        if (ctx->profiling) {
-            e0 = ctx->prof_event();
-            e1 = ctx->prof_event();
-        } else if (ctx->cost.want_sample()) {
-            sample = ctx->cost.events(&e0, &e1);
-        }
-        cudaError_t e = launch_batched_search(sb, d_q, b, k, ctx->sms, &ctx->batched.p, &ctx->batched.bytes, d_status,
-                                              local, oid(0), odd(0), ctx->stream, &bs, e0, e1);
-        if (e != cudaSuccess) return fail(VROD_ECUDA, std::string("batched search: ") + cudaGetErrorString(e));
-        if (sample)
-            ctx->cost.pending(2, (double)((b + 255) / 256) * ((double)s.n / 128.0) * ((double)mirror_ld(s.dim) / 144.0) / (double)ctx->sms);
-        ctx->stats.kernel_launches += bs.launches;
-        ctx->stats.batched_tiles += bs.tiles;
+        vrod_status bst = enqueue_batched(c, d_q, b, k, d_ids, d_dist, d_status);
+        if (bst != VROD_OK) return bst;
         lp->batched = true;
     } else if (exact_only) {
         const ScanPlan xp = make_scan_plan(s, k, ctx->sms, true);
@@ -1363,6 +1380,18 @@ static vrod_status batched_rescans(vrod_collection *c, const float *d_q, uint32_
     const ScanScratch scr = scan_scratch(ctx, d_status);
     uint32_t flagged = 0;
     for (uint32_t qi = 0; qi < b; ++qi) flagged += hs[qi] ? 1u : 0u;
+    if (flagged * 20u > b && !c->band_mode && c->rows_h && c->path != 4) {
+        // more than 5 % of the fixed-k' proofs failed: this collection holds neighbours the bf16 contraction cannot tell
+        // apart.  From now on its batched passes keep every candidate inside the error band (up to 1024 per query) -- and
+        // this batch is answered that way at once: one more tensor-core pass instead of `flagged` single-query scans.
+        c->band_mode = true;
+        vrod_status st = enqueue_batched(c, d_q, b, k, d_ids, d_dist, d_status);
+        if (st == VROD_OK) st = batched_fetch_status(c, b, d_status);
+        if (st != VROD_OK) return st;
+        VROD_CUDA(cudaEventSynchronize(ctx->ev_status));
+        flagged = 0;
+        for (uint32_t qi = 0; qi < b; ++qi) flagged += hs[qi] ? 1u : 0u;
+    }
     {   // rises at once, falls slowly
         const double share = (double)flagged / (double)b, ema = 0.5 * c->rescan_share + 0.5 * share;
         c->rescan_share = share > ema ? share : ema;
