@@ -15,7 +15,7 @@ def main():
     from oracle import oracle as O
     from tests.util import assert_same
     from vrod_b200 import ffi
-    from vrod_b200.dist import share_comm_id, shard_range
+    from vrod_b200.dist import SHARD_BLOCK, share_comm_id, shard_ids
 
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -28,11 +28,11 @@ def main():
         c = ctx.create(f"s{n}_{d}", d, metric, n)
         c.fill_synthetic(n, 41)
         base, rows_here = c.shard()
-        lo, hi = shard_range(n, rank, world)
-        assert (base, rows_here) == (lo if hi > lo else base, hi - lo), (base, rows_here, lo, hi)
+        mine = shard_ids(n, rank, world)                  # block-cyclic deal: blocks of SHARD_BLOCK ids, round robin
+        assert (base, rows_here) == (rank * SHARD_BLOCK, len(mine)), (base, rows_here, len(mine))
         X = O.fill(n, d, 41)
         if rows_here:
-            assert np.array_equal(c.read_rows(0, rows_here), X[lo:hi])
+            assert np.array_equal(c.read_rows(0, rows_here), X[mine.astype(np.int64)])
         Q = O.fill(5, d, 42)
         Q[4] = X[n - 1]                                   # an exact hit on the last shard
         ids, dd = c.search(Q, k)                          # collective; every rank gets the global answer
@@ -58,20 +58,45 @@ def main():
         ctx.drop(c.name)
 
     # INSERT: every rank passes the same rows; ties across the shard boundary break by id
-    n, d = 30_000, 96
+    n, d = 9 * SHARD_BLOCK + 777, 96
     X = O.fill(n, d, 43)
-    lo1, _ = shard_range(n, world - 1, world)
-    X[lo1] = X[3]                                         # same vector in the first and the last shard
-    c = ctx.create("ins", d, 0, n)
+    lo1 = (world - 1) * SHARD_BLOCK + 5                   # a row of the last rank's first block
+    X[lo1] = X[3]                                         # same vector on the first and the last rank
+    X[world * SHARD_BLOCK + 9] = X[3]                     # ... and again on the first rank, one deal later
+    c = ctx.create("ins", d, 0, n // 3)                   # a third of what will arrive: the shards grow, twice
     c.insert(X[:12_345])
     c.insert(X[12_345:])
+    assert c.info()["count"] == n and c.info()["capacity"] >= n
+    assert c.shard()[1] == len(shard_ids(n, rank, world))
     ids, dd = c.search(X[3], 5)
-    assert ids[0, 0] == 3 and ids[0, 1] == lo1 and dd[0, 0] == 0 and dd[0, 1] == 0
+    assert ids[0].tolist()[:3] == [3, lo1, world * SHARD_BLOCK + 9] and not dd[0, :3].any()   # ties: by id, across interleaved shards
     assert_same(ids, dd, *O.search(X, X[3], 5, 0))
     ctx.drop("ins")
 
+    # persistence, collectively: every rank writes / reads only the blocks it holds (one file, block offsets)
+    path = f"/tmp/vrod_sharded_{os.environ.get('MASTER_PORT', '0')}.vrc"
+    c = ctx.create("sv", d, 1, n)
+    c.insert(X)
+    Qs = O.fill(3, d, 60)
+    want = O.search(X, Qs, 7, 1)
+    assert_same(*c.search(Qs, 7), *want, "before save")
+    c.save(path)
+    ctx.drop("sv")
+    c2 = ctx.load("sv2", path)
+    assert c2.info()["count"] == n and c2.shard()[1] == len(shard_ids(n, rank, world))
+    assert_same(*c2.search(Qs, 7), *want, "after the collective load")
+    ctx.drop("sv2")
+    if rank == 0:                                         # the same file in a plain single-GPU context
+        with ffi.Context(local) as one:
+            assert_same(*one.load("sv3", path).search(Qs, 7), *want, "sharded file, single-GPU load")
+    dist.barrier()
+    if rank == 0:
+        os.remove(path)
+
     # a batch with ONE non-finite value lands on one rank only: every rank must reject it (and keep its count), or the
     # ranks' ids drift apart for every later insert
+    n = 30_000
+    X = X[:n]
     c = ctx.create("bad", d, 0, n)
     c.insert(X[:1000])
     bad = X[1000:1100].copy()

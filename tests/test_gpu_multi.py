@@ -81,11 +81,13 @@ def test_batched_path_fused_and_gathered_exchange(mctx, oracle):
 
 def test_insert_ties_across_devices_and_rejects_bad_rows(mctx, oracle):
     from vrod_b200 import ffi
-    n, d = 30_000, 96
+    from vrod_b200.dist import SHARD_BLOCK
+    W = mctx.devices
+    n, d = 9 * SHARD_BLOCK + 777, 96
     X = oracle.fill(n, d, 43)
-    last_lo = (n + mctx.devices - 1) // mctx.devices * (mctx.devices - 1)
+    last_lo = (W - 1) * SHARD_BLOCK + 5                             # a row of the last device's first block
     X[last_lo] = X[3]                                               # the same vector on the first and the last device
-    c = mctx.create("mins", d, 0, n)
+    c = mctx.create("mins", d, 0, n // 3)                           # the shards grow as the rows arrive
     assert c.insert(X[:12_345]) == 0
     bad = X[12_345:12_400].copy()
     bad[-1, 5] = np.nan                                             # lands on ONE device: all of them must reject the batch
@@ -96,9 +98,8 @@ def test_insert_ties_across_devices_and_rejects_bad_rows(mctx, oracle):
     ids, dd = c.search(X[3], 5)
     assert ids[0, 0] == 3 and ids[0, 1] == last_lo and dd[0, 0] == 0 and dd[0, 1] == 0
     assert_same(ids, dd, *oracle.search(X, X[3], 5, 0))
-    with pytest.raises(ffi.VrodError) as e:
-        c.insert(X[:1])                                             # full: sharded collections do not grow (yet)
-    assert e.value.status == ffi.ENOMEM
+    assert c.info()["count"] == n and c.info()["capacity"] >= n     # grown in place: every device continues its own deal
+    assert np.array_equal(c.read_rows(0, n), X)
     mctx.drop("mins")
 
 

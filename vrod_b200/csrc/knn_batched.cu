@@ -984,7 +984,7 @@ struct FinishParams {
     const float4 *rows4;
     const float4 *q4;       // [b][ld4]
     uint32_t n, ld4, b, k;
-    unsigned long long id_base;
+    uint32_t rank, world;   // shard coordinates (row_id)
     int kprime, cap, water;
     uint32_t qgroups, units, psz;   // list layout of the tile kernel: unit u = g + m*qgroups, CTA = u*psz + r
     const unsigned long long *cand;
@@ -1174,7 +1174,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
     for (int i = tid; i < (int)p.k; i += kScanThreads) {
         Hit h;
         if (i < ncand) {
-            h.id = p.id_base + (uint32_t)buf[i];
+            h.id = row_id((uint32_t)buf[i], p.rank, p.world);
             h.dist = ord2f((uint32_t)(buf[i] >> 32));
         } else {
             h.id = kKeyMax;
@@ -1475,7 +1475,8 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         f.ld4 = s.ld / 4;
         f.b = bq;
         f.k = k;
-        f.id_base = s.id_base;
+        f.rank = s.rank;
+        f.world = s.world ? s.world : 1;
         f.kprime = kprime;
         f.need = band ? (int)k : kprime;
         f.keep = keep;

@@ -31,7 +31,7 @@ struct ScanParams {
     const float *inv_norm;
     const float4 *q4;
     uint32_t n, ld4;
-    unsigned long long id_base;
+    uint32_t rank, world;      // shard coordinates: global id of a local row by row_id()
     uint32_t k;
     int kprime, cap, water;
     uint32_t iters;
@@ -280,7 +280,7 @@ __device__ __forceinline__ void write_hits(const unsigned long long *buf, int nc
     for (int i = tid; i < (int)p.k; i += kScanThreads) {
         Hit h;
         if (i < ncand) {
-            h.id = p.id_base + (uint32_t)buf[i];
+            h.id = row_id((uint32_t)buf[i], p.rank, p.world);
             h.dist = ord2f((uint32_t)(buf[i] >> 32));
         } else {
             h.id = kKeyMax;
@@ -613,13 +613,13 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const float4 *rows4, uin
 }
 
 __global__ void __launch_bounds__(256) fill_synthetic_kernel(float4 *rows4, uint32_t row0, uint32_t n, uint32_t dim,
-                                                             uint32_t ld4, unsigned long long g0, uint32_t k0,
+                                                             uint32_t ld4, uint32_t rank, uint32_t world, uint32_t k0,
                                                              uint32_t k1) {
     const unsigned long long total = (unsigned long long)n * ld4;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
         const uint32_t r = (uint32_t)(t / ld4), c = (uint32_t)(t % ld4);
-        const unsigned long long e = (g0 + r) * dim + 4ull * c;  // first element of this float4
+        const unsigned long long e = row_id(row0 + r, rank, world) * dim + 4ull * c;  // first element of this float4
         float v[4];
         if ((dim & 3u) == 0) {
             const uint4 w = philox4x32_10((uint32_t)(e >> 2), (uint32_t)(e >> 34), k0, k1);
@@ -649,41 +649,53 @@ __global__ void pad_queries_kernel(const float *src, float *dst, uint32_t b, uin
     }
 }
 
-// One CTA per query: sort g*k (dist, shard, slot) keys; shards hold ascending id ranges and each list
-// is already (dist, id)-sorted, so (dist, shard, slot) order IS (dist, id) order.
-__global__ void __launch_bounds__(kScanThreads) merge_hits_kernel(const Hit *lists, uint32_t g, uint32_t b, uint32_t k,
-                                                                  unsigned long long *out_ids, float *out_dist) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem);
-    const int tid = threadIdx.x;
-    const uint32_t qi = blockIdx.x;
-    const int total = (int)(g * k);
-    int P = 32;
-    while (P < total) P <<= 1;
-    for (int i = tid; i < P; i += kScanThreads) {
-        unsigned long long key = kKeyMax;
-        if (i < total) {
-            const uint32_t s = i / k, j = i % k;
-            const Hit h = lists[((size_t)s * b + qi) * k + j];
-            if (h.id != kKeyMax) key = ((unsigned long long)f2ord(h.dist) << 32) | (s << 16) | j;
-        }
-        buf[i] = key;
+// Merge g lists of k hits, each sorted by (dist, id), into the k best under the same order.  No sort: every entry finds its
+// rank -- its index in its own list plus, by binary search, the number of entries of every other list that precede it
+// (ids are unique, so no two entries compare equal) -- and the entries ranked below k go straight to their slot.  Shards
+// interleave in id space (block-cyclic sharding), so the order has to be the full (dist, id) one.  `list_of(s)` returns
+// list s (global memory, possibly written by a peer: read volatile).  All threads of the CTA; ends with a barrier.
+template <typename ListOf>
+__device__ __forceinline__ void ranked_merge(ListOf list_of, uint32_t g, uint32_t k, unsigned long long *out_ids, float *out_dist, int tid) {
+    for (uint32_t i = tid; i < k; i += kScanThreads) {
+        out_ids[i] = kKeyMax;
+        out_dist[i] = __int_as_float(0x7f800000);
     }
     __syncthreads();
-    block_bitonic(buf, P, tid);
-    for (int i = tid; i < (int)k; i += kScanThreads) {
-        const unsigned long long key = buf[i];
-        unsigned long long id = kKeyMax;
-        float dist = __int_as_float(0x7f800000);
-        if (key != kKeyMax) {
-            const uint32_t s = ((uint32_t)key >> 16) & 0xffffu, j = (uint32_t)key & 0xffffu;
-            const Hit h = lists[((size_t)s * b + qi) * k + j];
-            id = h.id;
-            dist = h.dist;
+    for (uint32_t e = tid; e < g * k; e += kScanThreads) {
+        const uint32_t s = e / k, j = e % k;
+        const Hit *mine = list_of(s) + j;
+        const unsigned long long id = *(volatile const unsigned long long *)&mine->id;
+        if (id == kKeyMax) continue;   // padding (a shard with fewer than k rows)
+        const float dist = *(volatile const float *)&mine->dist;
+        uint32_t rank = j;
+        for (uint32_t t = 0; t < g && rank < k; ++t) {
+            if (t == s) continue;
+            const Hit *lt = list_of(t);
+            uint32_t lo = 0, hi = k;       // entries of list t before (dist, id): lower bound
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const unsigned long long oid = *(volatile const unsigned long long *)&lt[mid].id;
+                const float od = *(volatile const float *)&lt[mid].dist;
+                const bool before = oid != kKeyMax && (od < dist || (od == dist && oid < id));
+                if (before) lo = mid + 1;
+                else hi = mid;
+            }
+            rank += lo;
         }
-        out_ids[(size_t)qi * k + i] = id;
-        out_dist[(size_t)qi * k + i] = dist;
+        if (rank < k) {
+            out_ids[rank] = id;
+            out_dist[rank] = dist;
+        }
     }
+    __syncthreads();
+}
+
+// One CTA per query: merge the g gathered lists under (dist, id).
+__global__ void __launch_bounds__(kScanThreads) merge_hits_kernel(const Hit *lists, uint32_t g, uint32_t b, uint32_t k,
+                                                                  unsigned long long *out_ids, float *out_dist) {
+    const uint32_t qi = blockIdx.x;
+    ranked_merge([&](uint32_t s) { return lists + ((size_t)s * b + qi) * k; }, g, k, out_ids + (size_t)qi * k, out_dist + (size_t)qi * k,
+                 threadIdx.x);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -694,7 +706,7 @@ __global__ void __launch_bounds__(kScanThreads) merge_hits_kernel(const Hit *lis
 // One CTA per query: (1) PUSH this rank's k hits of the query into slot [seq&1][rank] of EVERY rank's window with
 // plain stores through the peer mappings (NVLink P2P), fence at system scope, then publish flag = seq in every
 // window; (2) WAIT until all `world` flags of the query in the LOCAL window carry seq (the peers' pushes);
-// (3) MERGE the world lists from the local window by (dist, shard, slot) and write the final ids / distances.
+// (3) MERGE the world lists from the local window under (dist, id) (ranked_merge) and write the final ids / distances.
 // This replaces ncclAllGather + merge_hits_kernel (two launches, ~20-30 us of latency at 8 GPUs).  For single-query
 // scans it is not even a launch: the last CTA of fast_scan_kernel / exact_scan_kernel runs it right after it has written
 // the rank's k hits (exchange_device below), so a sharded search is ONE kernel per rank.
@@ -759,38 +771,12 @@ __device__ __forceinline__ int exchange_device(const XchgArgs &x, const Hit *loc
     }
     __syncthreads();
     __threadfence_system();
-    // (3) merge: (dist, shard, slot) order IS (dist, id) order (shards own ascending id ranges, lists are sorted)
-    const int total = (int)(world * k);
-    int P = 32;
-    while (P < total) P <<= 1;
+    // (3) merge under (dist, id); the ranks' guard flags ride in hit[0].pad
     int flagged = 0;
-    for (int i = tid; i < P; i += kScanThreads) {
-        unsigned long long key = kKeyMax;
-        if (i < total) {
-            const uint32_t s = i / k, j = i % k;
-            const Hit *h = data_of(mine, s) + j;
-            const unsigned long long id = *(volatile const unsigned long long *)&h->id;
-            const float dist = *(volatile const float *)&h->dist;
-            if (j == 0) flagged |= (int)*(volatile const uint32_t *)&h->pad;
-            if (id != kKeyMax) key = ((unsigned long long)f2ord(dist) << 32) | (s << 16) | j;
-        }
-        buf[i] = key;
-    }
+    if (tid < (int)world) flagged = (int)*(volatile const uint32_t *)&data_of(mine, tid)->pad;
     flagged = __syncthreads_or(flagged);
-    block_bitonic(buf, P, tid);
-    for (int i = tid; i < (int)k; i += kScanThreads) {
-        const unsigned long long key = buf[i];
-        unsigned long long id = kKeyMax;
-        float dist = __int_as_float(0x7f800000);
-        if (key != kKeyMax) {
-            const uint32_t s = ((uint32_t)key >> 16) & 0xffffu, j = (uint32_t)key & 0xffffu;
-            const Hit *h = data_of(mine, s) + j;
-            id = *(volatile const unsigned long long *)&h->id;
-            dist = *(volatile const float *)&h->dist;
-        }
-        out_ids[i] = id;
-        out_dist[i] = dist;
-    }
+    ranked_merge([&](uint32_t s) { return data_of(mine, s); }, world, k, out_ids, out_dist, tid);
+    (void)buf;
     return flagged;
 }
 
@@ -913,7 +899,8 @@ static ScanParams make_params(const ShardView &s, const float *q, uint32_t k, co
     p.q4 = reinterpret_cast<const float4 *>(q);
     p.n = s.n;
     p.ld4 = s.ld / 4;
-    p.id_base = s.id_base;
+    p.rank = s.rank;
+    p.world = s.world ? s.world : 1;
     p.k = k;
     p.kprime = plan.kprime;
     p.cap = plan.cap;
@@ -971,10 +958,10 @@ cudaError_t launch_row_norms(const float *rows, uint32_t row0, uint32_t n, uint3
     return cudaGetLastError();
 }
 
-cudaError_t launch_fill_synthetic(float *rows, uint32_t row0, uint32_t n, uint32_t dim, uint32_t ld, uint64_t g0,
+cudaError_t launch_fill_synthetic(float *rows, uint32_t row0, uint32_t n, uint32_t dim, uint32_t ld, uint32_t rank, uint32_t world,
                                   uint64_t seed, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    fill_synthetic_kernel<<<148 * 16, 256, 0, st>>>(reinterpret_cast<float4 *>(rows), row0, n, dim, ld / 4, g0,
+    fill_synthetic_kernel<<<148 * 16, 256, 0, st>>>(reinterpret_cast<float4 *>(rows), row0, n, dim, ld / 4, rank, world ? world : 1,
                                                     (uint32_t)seed, (uint32_t)(seed >> 32));
     return cudaGetLastError();
 }
@@ -988,12 +975,7 @@ cudaError_t launch_pad_queries(const float *src, float *dst, uint32_t b, uint32_
 cudaError_t launch_merge_hits(const Hit *lists, uint32_t g, uint32_t b, uint32_t k, unsigned long long *out_ids,
                               float *out_dist, cudaStream_t st) {
     if (b == 0) return cudaSuccess;
-    size_t smem = (size_t)next_pow2((int)(g * k) < 32 ? 32 : (int)(g * k)) * sizeof(unsigned long long);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(merge_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    merge_hits_kernel<<<b, kScanThreads, smem, st>>>(lists, g, b, k, out_ids, out_dist);
+    merge_hits_kernel<<<b, kScanThreads, 0, st>>>(lists, g, b, k, out_ids, out_dist);
     return cudaGetLastError();
 }
 

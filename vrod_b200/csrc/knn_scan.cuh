@@ -14,8 +14,25 @@ struct ShardView {
     uint32_t n;              // local rows (< 2^32)
     uint32_t dim, ld;
     int metric;              // 0 Euclidean, 1 cosine
-    uint64_t id_base;        // global id of local row 0
+    uint32_t rank, world;    // which shard of how many: ids are dealt to the shards in blocks of kShardBlock rows (row_id)
 };
+
+// Row sharding: BLOCK-CYCLIC.  Global ids are dealt out in blocks of kShardBlock consecutive rows, block j to shard j mod G;
+// a shard stores its blocks back to back.  Every shard then holds the same number of rows (within one block) at ANY fill
+// level, so a half-filled collection scans as fast as a full one, and it grows on its own: more rows just continue the
+// deal, no row ever moves between shards (round 1 cut the id space into G contiguous ranges sized by the capacity: a
+// collection filled shard 0 first and could not grow without re-dealing everything).  Inside a shard local order is id
+// order; across shards ids interleave, so lists are merged under the full (dist, id) order, not by shard number.
+constexpr uint32_t kShardBlock = 4096;
+__host__ __device__ inline uint64_t row_id(uint64_t local_row, uint32_t rank, uint32_t world) {
+    return ((local_row / kShardBlock) * world + rank) * kShardBlock + local_row % kShardBlock;
+}
+// rows shard `rank` holds when the collection holds `count` rows
+inline uint64_t shard_rows_at(uint64_t count, uint32_t rank, uint32_t world) {
+    const uint64_t cycle = (uint64_t)kShardBlock * world, full = count / cycle, rem = count % cycle;
+    const uint64_t lo = (uint64_t)rank * kShardBlock;
+    return full * kShardBlock + (rem <= lo ? 0 : (rem - lo < kShardBlock ? rem - lo : kShardBlock));
+}
 
 // Per-launch scratch owned by the collection (sized by scan_scratch_bytes()).
 struct ScanScratch {
@@ -76,8 +93,8 @@ cudaError_t launch_exact_scan(const ShardView &s, const float *q, uint32_t k, co
 // |= 2 if a value or norm is outside the range the f32 scan's error bound covers.
 cudaError_t launch_row_norms(const float *rows, uint32_t row0, uint32_t n, uint32_t ld, float *inv_norm,
                              float *sq_norm, int *flags, cudaStream_t st);
-// synthetic rows (global row index g0 + local) into rows[row0 ..]
-cudaError_t launch_fill_synthetic(float *rows, uint32_t row0, uint32_t n, uint32_t dim, uint32_t ld, uint64_t g0,
+// synthetic rows into the local rows [row0, row0 + n) of shard `rank` of `world` (their global ids by row_id)
+cudaError_t launch_fill_synthetic(float *rows, uint32_t row0, uint32_t n, uint32_t dim, uint32_t ld, uint32_t rank, uint32_t world,
                                   uint64_t seed, cudaStream_t st);
 // [b x dim] -> [b x ld] zero padded
 cudaError_t launch_pad_queries(const float *src, float *dst, uint32_t b, uint32_t dim, uint32_t ld, cudaStream_t st);

@@ -211,7 +211,7 @@ struct vrod_ctx {
     ncclComm_t comm = nullptr;
     std::map<std::string, vrod_collection *> colls;
     // scratch shared by every collection of the context
-    DevBuf blk_cand, small, q_pad, q_dev, hits_local, hits_all, out_ids, out_dist, batched;
+    DevBuf blk_cand, small, q_pad, q_dev, hits_local, hits_all, out_ids, out_dist, batched, agree;
     PinBuf q_host, ids_host, dist_host, status_host;
     unsigned long long *dev_counters = nullptr;  // [0] exact rescans (counted on the device)
     vrod_stats stats{};
@@ -537,7 +537,7 @@ extern "C" void vrod_ctx_destroy(vrod_ctx *ctx) {
     cudaFree(ctx->d_xchg_err);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf *dev[] = {&ctx->blk_cand, &ctx->small, &ctx->q_pad, &ctx->q_dev, &ctx->hits_local,
-                     &ctx->hits_all, &ctx->out_ids, &ctx->out_dist, &ctx->batched};
+                     &ctx->hits_all, &ctx->out_ids, &ctx->out_dist, &ctx->batched, &ctx->agree};
     for (DevBuf *b : dev) b->release();
     PinBuf *pin[] = {&ctx->q_host, &ctx->ids_host, &ctx->dist_host, &ctx->status_host};
     for (PinBuf *b : pin) b->release();
@@ -733,9 +733,11 @@ static vrod_status vrod_collection_create_impl(vrod_ctx *ctx, const char *name, 
     c->ld = (dim + 3u) & ~3u;
     c->metric = metric;
     c->capacity = capacity_rows;
-    c->shard_rows = (capacity_rows + ctx->world - 1) / ctx->world;
+    // block-cyclic sharding (knn_scan.cuh: row_id): this rank's capacity is what it holds when the collection is full
+    c->shard_rows = shard_rows_at(capacity_rows, (uint32_t)ctx->rank, (uint32_t)ctx->world);
     if (c->shard_rows >= 0xFFFFFFFFull) return fail(VROD_EINVAL, "more than 2^32-1 rows per GPU");
-    c->id_base = c->shard_rows * (uint64_t)ctx->rank;
+    if (c->shard_rows == 0) c->shard_rows = 1;      // (a rank beyond the last block of a small collection: keep the buffers real)
+    c->id_base = (uint64_t)ctx->rank * kShardBlock;  // global id of local row 0
     const size_t row_bytes = (size_t)c->shard_rows * c->ld * sizeof(float);
     cudaError_t e = cudaMalloc(&c->rows, row_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&c->inv_norm, (size_t)c->shard_rows * sizeof(float));
@@ -851,18 +853,20 @@ static vrod_status vrod_collection_set_path_impl(vrod_collection *c, int path) {
     return VROD_OK;
 }
 
-// rows [g0, g0+n) of the global sequence: which part lands on this rank?  Returns local start / count / source offset.
-static void shard_overlap(const vrod_collection *c, uint64_t g0, uint64_t n, uint64_t *loc0, uint64_t *cnt, uint64_t *src_off) {
-    const uint64_t lo = c->id_base, hi = c->id_base + c->shard_rows;
-    const uint64_t a = g0 > lo ? g0 : lo;
-    const uint64_t b = (g0 + n) < hi ? (g0 + n) : hi;
-    if (b <= a) {
-        *loc0 = 0; *cnt = 0; *src_off = 0;
-        return;
+// Rows [g0, g0 + n) of the global sequence, block by block: calls f(local_row, source_offset, rows) for every piece that
+// is dealt to this rank (knn_scan.cuh: block-cyclic sharding).  Appends arrive in id order, so the pieces of one call are
+// back to back in the shard.
+template <typename F>
+static vrod_status for_my_pieces(const vrod_collection *c, uint64_t g0, uint64_t n, F &&f) {
+    const uint64_t G = (uint64_t)c->ctx->world, r = (uint64_t)c->ctx->rank, B = kShardBlock;
+    for (uint64_t blk = g0 / B; blk * B < g0 + n; ++blk) {
+        if (blk % G != r) continue;
+        const uint64_t a = blk * B > g0 ? blk * B : g0;
+        const uint64_t e = (blk + 1) * B < g0 + n ? (blk + 1) * B : g0 + n;
+        vrod_status st = f((blk / G) * B + (a - blk * B), a - g0, e - a);
+        if (st != VROD_OK) return st;
     }
-    *loc0 = a - lo;
-    *cnt = b - a;
-    *src_off = a - g0;
+    return VROD_OK;
 }
 
 // after new rows landed in [loc0, loc0+cnt): norms + validation
@@ -894,23 +898,29 @@ static bool host_rows_finite(const float *rows, size_t n) {
     return bad == 0;
 }
 
-// single-GPU collections: make room for at least `need` rows (capacity at least doubles)
+// Make room for at least `need` rows in all (the global capacity at least doubles).  Every shard grows on its own: the
+// block-cyclic deal just continues, no row changes its shard, so a sharded collection needs no communication here.
 static vrod_status collection_grow(vrod_collection *c, uint64_t need) {
     vrod_ctx *ctx = c->ctx;
-    uint64_t cap = c->capacity * 2 > need ? c->capacity * 2 : need;
-    if (cap >= 0xFFFFFFFFull) cap = 0xFFFFFFFEull;
-    if (cap < need) return fail(VROD_ENOMEM, "more than 2^32-2 rows on one GPU");
+    const uint32_t rk = (uint32_t)ctx->rank, G = (uint32_t)ctx->world;
+    uint64_t gcap = c->capacity * 2 > need ? c->capacity * 2 : need;      // global
+    if (shard_rows_at(gcap, 0, G) >= 0xFFFFFFFFull) gcap = need;
+    if (shard_rows_at(gcap, 0, G) >= 0xFFFFFFFFull) return fail(VROD_ENOMEM, "more than 2^32-2 rows on one GPU");
+    uint64_t cap = shard_rows_at(gcap, rk, G);                            // this shard
+    if (cap == 0) cap = 1;
+    const uint64_t need_local = shard_rows_at(need, rk, G) ? shard_rows_at(need, rk, G) : 1;
     float *rows = nullptr, *inv = nullptr, *sq = nullptr;
     cudaError_t e = cudaSuccess;
     for (int attempt = 0; attempt < 2; ++attempt) {   // doubled capacity first, exactly `need` rows if that does not fit
         e = cudaMalloc(&rows, (size_t)cap * c->ld * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&inv, (size_t)cap * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&sq, (size_t)cap * sizeof(float));
-        if (e != cudaErrorMemoryAllocation || cap == need) break;
+        if (e != cudaErrorMemoryAllocation || cap == need_local) break;
         cudaGetLastError();
         cudaFree(rows); cudaFree(inv); cudaFree(sq);
         rows = inv = sq = nullptr;
-        cap = need;
+        cap = need_local;
+        gcap = need;
     }
     if (e == cudaSuccess && c->local) {
         e = cudaMemcpyAsync(rows, c->rows, (size_t)c->local * c->ld * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
@@ -929,7 +939,7 @@ static vrod_status collection_grow(vrod_collection *c, uint64_t need) {
     c->mirror_rows = 0;
     c->mirror_failed = false;
     c->rows = rows; c->inv_norm = inv; c->sq_norm = sq;
-    c->capacity = cap;
+    c->capacity = gcap;
     c->shard_rows = cap;
     return VROD_OK;
 }
@@ -956,7 +966,6 @@ static vrod_status vrod_collection_insert_impl(vrod_collection *c, const float *
     if (!c->parts.empty()) {
         // every device takes the rows of its own id range; accept or reject is decided once, here, for all of them
         if (!host_rows_finite(rows, (size_t)n * c->dim)) return fail(VROD_EINVAL, "rows contain NaN or infinity");
-        if (c->count + n > c->capacity) return fail(VROD_ENOMEM, "collection capacity exceeded (sharded collections do not grow)");
         for (vrod_collection *part : c->parts) {
             vrod_status st = vrod_collection_insert_impl(part, rows, n, first_id, true);
             if (st != VROD_OK) return st;
@@ -966,23 +975,23 @@ static vrod_status vrod_collection_insert_impl(vrod_collection *c, const float *
         return VROD_OK;
     }
     VROD_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->world > 1 && !validated && !host_rows_finite(rows, (size_t)n * c->dim))
+        return fail(VROD_EINVAL, "rows contain NaN or infinity");   // decided identically on every rank (same rows)
     if (c->count + n > c->capacity) {
-        if (ctx->world > 1) return fail(VROD_ENOMEM, "collection capacity exceeded (sharded collections do not grow)");
         vrod_status gs = collection_grow(c, c->count + n);
         if (gs != VROD_OK) return gs;
     }
-    if (ctx->world > 1 && !validated && !host_rows_finite(rows, (size_t)n * c->dim))
-        return fail(VROD_EINVAL, "rows contain NaN or infinity");   // decided identically on every rank (same rows)
-    uint64_t loc0, cnt, off;
-    shard_overlap(c, c->count, n, &loc0, &cnt, &off);
-    if (cnt) {
+    const uint64_t loc0 = c->local, cnt = shard_rows_at(c->count + n, (uint32_t)ctx->rank, (uint32_t)ctx->world) - c->local;
+    vrod_status st = for_my_pieces(c, c->count, n, [&](uint64_t lrow, uint64_t off, uint64_t m) -> vrod_status {
         const float *src = rows + (size_t)off * c->dim;
-        float *dst = c->rows + (size_t)loc0 * c->ld;
-        if (c->ld != c->dim) VROD_CUDA(cudaMemsetAsync(dst, 0, (size_t)cnt * c->ld * sizeof(float), ctx->stream));
+        float *dst = c->rows + (size_t)lrow * c->ld;
+        if (c->ld != c->dim) VROD_CUDA(cudaMemsetAsync(dst, 0, (size_t)m * c->ld * sizeof(float), ctx->stream));
         VROD_CUDA(cudaMemcpy2DAsync(dst, (size_t)c->ld * sizeof(float), src, (size_t)c->dim * sizeof(float),
-                                    (size_t)c->dim * sizeof(float), (size_t)cnt, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    vrod_status st = finish_append(c, loc0, cnt, true);
+                                    (size_t)c->dim * sizeof(float), (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        return VROD_OK;
+    });
+    if (st != VROD_OK) return st;
+    st = finish_append(c, loc0, cnt, true);
     if (st != VROD_OK) return st;  // rejected rows are not counted: the next insert overwrites them
     if (first_id) *first_id = c->count;
     c->count += n;
@@ -1008,10 +1017,9 @@ static vrod_status vrod_collection_fill_synthetic_impl(vrod_collection *c, uint6
         return VROD_OK;
     }
     VROD_CUDA(cudaSetDevice(ctx->device));
-    uint64_t loc0, cnt, off;
-    shard_overlap(c, c->count, n, &loc0, &cnt, &off);
+    const uint64_t loc0 = c->local, cnt = shard_rows_at(c->count + n, (uint32_t)ctx->rank, (uint32_t)ctx->world) - c->local;
     if (cnt) {
-        VROD_CUDA(launch_fill_synthetic(c->rows, (uint32_t)loc0, (uint32_t)cnt, c->dim, c->ld, c->id_base + loc0, seed,
+        VROD_CUDA(launch_fill_synthetic(c->rows, (uint32_t)loc0, (uint32_t)cnt, c->dim, c->ld, (uint32_t)ctx->rank, (uint32_t)ctx->world, seed,
                                         ctx->stream));
         ctx->stats.kernel_launches++;
     }
@@ -1032,12 +1040,11 @@ static vrod_status vrod_collection_read_rows_impl(vrod_collection *c, uint64_t r
     if (row0 + n > c->local) return fail(VROD_EINVAL, "row range outside this rank's shard");
     if (n == 0) return VROD_OK;
     vrod_ctx *ctx = c->ctx;
-    if (!c->parts.empty()) {   // global row indices: every part returns its piece of the range
+    if (!c->parts.empty()) {   // global row indices: every part returns its blocks of the range
         for (vrod_collection *part : c->parts) {
-            const uint64_t lo = part->id_base, hi = part->id_base + part->local;
-            const uint64_t a = row0 > lo ? row0 : lo, b = row0 + n < hi ? row0 + n : hi;
-            if (b <= a) continue;
-            vrod_status st = vrod_collection_read_rows_impl(part, a - lo, b - a, out + (size_t)(a - row0) * c->dim);
+            vrod_status st = for_my_pieces(part, row0, n, [&](uint64_t lrow, uint64_t off, uint64_t m) -> vrod_status {
+                return vrod_collection_read_rows_impl(part, lrow, m, out + (size_t)off * c->dim);
+            });
             if (st != VROD_OK) return st;
         }
         VROD_CUDA(cudaSetDevice(ctx->device));
@@ -1054,6 +1061,25 @@ static vrod_status vrod_collection_read_rows_impl(vrod_collection *c, uint64_t r
 // -------------------------------------------------------------------------------------------------
 // persistence
 // -------------------------------------------------------------------------------------------------
+// Collective over the ranks of a process-per-GPU context: *all_ok is true on every rank iff `ok` was true on every rank
+// (and nobody gets past it before everybody has arrived: it doubles as a barrier).  One byte per rank through NCCL.
+static vrod_status ranks_agree(vrod_ctx *ctx, bool ok, bool *all_ok) {
+    *all_ok = ok;
+    if (ctx->world <= 1 || !ctx->comm) return VROD_OK;
+    const int W = ctx->world;
+    VROD_CUDA(cudaSetDevice(ctx->device));
+    VROD_CUDA(ctx->agree.ensure((size_t)W + 16));
+    unsigned char *d = reinterpret_cast<unsigned char *>(ctx->agree.p);
+    const unsigned char mine = ok ? 1 : 0;
+    std::vector<unsigned char> all(W);
+    VROD_CUDA(cudaMemcpyAsync(d + W, &mine, 1, cudaMemcpyHostToDevice, ctx->stream));
+    VROD_NCCL(g_nccl.AllGather(d + W, d, 1, ncclChar, ctx->comm, ctx->stream));
+    VROD_CUDA(cudaMemcpyAsync(all.data(), d, W, cudaMemcpyDeviceToHost, ctx->stream));
+    VROD_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (unsigned char v : all) *all_ok = *all_ok && v;
+    return VROD_OK;
+}
+
 struct ColFileHeader {
     char magic[8];        // "VRODCOL1"
     uint32_t dim, metric;
@@ -1070,7 +1096,43 @@ extern "C" vrod_status vrod_collection_save(vrod_collection *c, const char *path
 static vrod_status vrod_collection_save_impl(vrod_collection *c, const char *path) {
     if (!c || !path) return fail(VROD_EINVAL, "NULL argument");
     vrod_ctx *ctx = c->ctx;
-    if (ctx->world > 1) return fail(VROD_EINVAL, "vrod_collection_save: single-GPU contexts only");
+    if (ctx->world > 1) {
+        // process-per-GPU context (collective): rank 0 lays the file out, then every rank writes the blocks it holds at their
+        // offsets -- each row crosses one PCIe link once and nobody holds more than a block on the host
+        if (ctx->parent) return fail(VROD_EINVAL, "vrod_collection_save: use the multi-GPU context's own collection handle");
+        VROD_CUDA(cudaSetDevice(ctx->device));
+        bool ok = true, all_ok = true;
+        if (ctx->rank == 0) {
+            FILE *f0 = fopen(path, "wb");
+            ColFileHeader h{};
+            memcpy(h.magic, "VRODCOL1", 8);
+            h.dim = c->dim;
+            h.metric = (uint32_t)c->metric;
+            h.count = c->count;
+            ok = f0 && fwrite(&h, sizeof(h), 1, f0) == 1;
+            if (f0) ok = (fclose(f0) == 0) && ok;
+        }
+        vrod_status st = ranks_agree(ctx, ok, &all_ok);
+        if (st != VROD_OK) return st;
+        if (!all_ok) return fail(VROD_EINVAL, std::string("cannot create '") + path + "'");
+        FILE *f = fopen(path, "r+b");
+        ok = f != nullptr;
+        std::vector<float> buf((size_t)kShardBlock * c->dim);
+        if (ok) {
+            st = for_my_pieces(c, 0, c->count, [&](uint64_t lrow, uint64_t off, uint64_t m) -> vrod_status {
+                vrod_status rs = vrod_collection_read_rows(c, lrow, m, buf.data());
+                if (rs != VROD_OK) return rs;
+                if (fseeko(f, (off_t)(sizeof(ColFileHeader) + off * c->dim * sizeof(float)), SEEK_SET) != 0 ||
+                    fwrite(buf.data(), sizeof(float) * c->dim, m, f) != m)
+                    ok = false;
+                return VROD_OK;
+            });
+            ok = (fclose(f) == 0) && ok && st == VROD_OK;
+        }
+        st = ranks_agree(ctx, ok, &all_ok);
+        if (st != VROD_OK) return st;
+        return all_ok ? VROD_OK : fail(VROD_EINVAL, std::string("short write to '") + path + "'");
+    }
     VROD_CUDA(cudaSetDevice(ctx->device));
     FILE *f = fopen(path, "wb");
     if (!f) return fail(VROD_EINVAL, std::string("cannot open '") + path + "' for writing");
@@ -1118,8 +1180,49 @@ static vrod_status vrod_collection_load_impl(vrod_ctx *ctx, const char *name, co
         fclose(f);
         return st;
     }
-    // every rank appends the whole file in chunks; vrod_collection_insert keeps the rows of its own range
-    // (a sharded rank still reads the whole file: simple, and the file is read once)
+    if (ctx->world > 1 && !ctx->parent && ctx->subs.empty()) {
+        // process-per-GPU context (collective): every rank reads only the blocks that are dealt to it
+        bool ok = true, all_ok = true;
+        std::string err;
+        std::vector<float> blk((size_t)kShardBlock * h.dim);
+        const uint64_t mine = shard_rows_at(h.count, (uint32_t)ctx->rank, (uint32_t)ctx->world);
+        st = for_my_pieces(c, 0, h.count, [&](uint64_t lrow, uint64_t off, uint64_t m) -> vrod_status {
+            if (!ok) return VROD_OK;
+            if (fseeko(f, (off_t)(sizeof(ColFileHeader) + off * h.dim * sizeof(float)), SEEK_SET) != 0 ||
+                fread(blk.data(), sizeof(float) * h.dim, m, f) != m) {
+                ok = false;
+                err = std::string("'") + path + "' is truncated";
+                return VROD_OK;
+            }
+            float *dst = c->rows + (size_t)lrow * c->ld;
+            if (c->ld != c->dim) VROD_CUDA(cudaMemsetAsync(dst, 0, (size_t)m * c->ld * sizeof(float), ctx->stream));
+            VROD_CUDA(cudaMemcpy2DAsync(dst, (size_t)c->ld * sizeof(float), blk.data(), (size_t)c->dim * sizeof(float),
+                                        (size_t)c->dim * sizeof(float), (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+            VROD_CUDA(cudaStreamSynchronize(ctx->stream));   // (the staging block is reused)
+            return VROD_OK;
+        });
+        fclose(f);
+        if (st == VROD_OK && ok) {
+            st = finish_append(c, 0, mine, true);
+            if (st != VROD_OK) {
+                ok = false;
+                err = g_last_error;
+                st = VROD_OK;
+            }
+        }
+        if (st != VROD_OK) ok = false;
+        vrod_status as = ranks_agree(ctx, ok, &all_ok);
+        if (as != VROD_OK || !all_ok) {
+            vrod_collection_drop(ctx, name);
+            if (as != VROD_OK) return as;
+            return fail(VROD_EINVAL, !err.empty() ? err : std::string("loading '") + path + "' failed on another rank");
+        }
+        c->count = h.count;
+        c->local = mine;
+        if (out) *out = c;
+        return VROD_OK;
+    }
+    // single GPU, or the single-process multi-GPU context: the file is read once, in chunks, and appended
     std::vector<float> buf((size_t)kIoChunkRows * h.dim);
     for (uint64_t r0 = 0; r0 < h.count; r0 += kIoChunkRows) {
         const uint64_t n = h.count - r0 < kIoChunkRows ? h.count - r0 : kIoChunkRows;
@@ -1154,7 +1257,8 @@ static ShardView shard_view(const vrod_collection *c) {
     s.dim = c->dim;
     s.ld = c->ld;
     s.metric = (int)c->metric;
-    s.id_base = c->id_base;
+    s.rank = (uint32_t)c->ctx->rank;
+    s.world = (uint32_t)c->ctx->world;
     return s;
 }
 
@@ -1266,7 +1370,7 @@ static vrod_status local_enqueue(vrod_collection *c, const float *d_q, uint32_t 
         const bool sharded = ctx->world > 1;
         const CostModel seeds;
         const CostModel &cm = sharded ? seeds : ctx->cost;
-        const double rows = sharded ? (double)c->shard_rows : (double)s.n;
+        const double rows = sharded ? (double)c->capacity / (double)ctx->world : (double)s.n;
         const double share = sharded ? 0.0 : c->rescan_share;
         const double t_scan = cm.scan_seconds(rows * s.ld * 4.0);
         const double groups = (double)((b + 255) / 256);

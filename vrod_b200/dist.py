@@ -1,19 +1,34 @@
 """Multi-rank plumbing around the C ABI: one process per GPU (torchrun), torch.distributed only for
 the rendezvous (shipping the communicator id, barriers, max-over-ranks timing).  The data path -- the
-per-rank scan and the ncclAllGather + merge of the top-k lists -- is inside libvrod_knn.so.
+per-rank scan and the exchange + merge of the top-k lists -- is inside libvrod_knn.so.
 
-shard_range() restates the library's partition rule (vrod_capi.cu: vrod_collection_create) so host
-code and tests can reason about which rank owns which ids.
+shard_ids() / shard_rows_at() restate the library's partition rule (knn_scan.cuh: row_id, block-cyclic
+sharding) so host code and tests can reason about which rank owns which ids:
+global ids are dealt out in blocks of SHARD_BLOCK consecutive rows, block j to rank j mod world; a rank
+stores its blocks back to back, so its local order is id order.
 """
 import os
 
+import numpy as np
 
-def shard_range(capacity, rank, world):
-    """Global id range [lo, hi) owned by `rank`: contiguous blocks of ceil(capacity/world) rows."""
-    per = (capacity + world - 1) // world
-    lo = min(capacity, per * rank)
-    hi = min(capacity, per * (rank + 1))
-    return lo, hi
+SHARD_BLOCK = 4096
+
+
+def shard_rows_at(count, rank, world, block=SHARD_BLOCK):
+    """Rows rank `rank` holds when the collection holds `count` rows."""
+    cycle = block * world
+    full, rem = divmod(count, cycle)
+    return full * block + min(max(rem - rank * block, 0), block)
+
+
+def shard_ids(count, rank, world, block=SHARD_BLOCK):
+    """Global ids of rank `rank`'s rows, in local order (ascending)."""
+    ids = np.arange(count, dtype=np.uint64)
+    return ids[(ids // block) % world == rank]
+
+
+def row_id(local_row, rank, world, block=SHARD_BLOCK):
+    return ((local_row // block) * world + rank) * block + local_row % block
 
 
 def env_rank_world():
