@@ -64,6 +64,7 @@ typedef enum { VROD_EUCLIDEAN = 0, VROD_COSINE = 1 } vrod_metric;
 #define VROD_MAX_K 1024u          /* largest k a search accepts */
 #define VROD_COMM_ID_BYTES 128u   /* size of the opaque communicator id (an ncclUniqueId) */
 #define VROD_PAD_ID UINT64_MAX
+#define VROD_SHARD_BLOCK 4096u    /* rows per block of the block-cyclic deal of a sharded collection */
 
 /* Counters of one context, for benches and tests (monotonic since ctx creation). */
 typedef struct {
@@ -85,16 +86,20 @@ VROD_API vrod_status vrod_ctx_create(int device, vrod_ctx **out);
  * bytes to the other ranks by any means (the benches use torch.distributed). */
 VROD_API vrod_status vrod_comm_unique_id(void *out);
 
-/* One process per GPU: this rank holds shard `rank` of `world` of every collection (contiguous row
- * ranges).  Collective: all ranks call it with the same id.  Searches
- * merge the per-rank top-k lists with one ncclAllGather on the context's stream. */
+/* One process per GPU: this rank holds shard `rank` of `world` of every collection.
+ * Rows are dealt to the shards BLOCK-CYCLICALLY: ids in blocks of VROD_SHARD_BLOCK consecutive rows, block j to
+ * shard j mod world, a shard's blocks stored back to back -- every shard holds the same number of rows (within one
+ * block) at any fill level, and a collection grows without moving a row between shards.  Collective: all ranks call
+ * it with the same id.  A search scans every shard and merges the per-rank top-k lists under (dist, id) -- inside the
+ * scan kernels' last CTA over NVLink peer memory for single queries, a fused push + merge kernel after the batched
+ * pass, ncclAllGather + merge for calls too large for the exchange windows. */
 VROD_API vrod_status vrod_ctx_create_sharded(int device, int rank, int world, const void *comm_id,
                                              vrod_ctx **out);
 
 /* ONE process, n_devices GPUs: the shape the reference's caller needs -- a single-threaded
  * process holding Rc<RefCell<Database>> (src/command/types.rs:10; fn main, src/main.rs:42).  Every collection of
- * the context is row-sharded over the devices (device i of the list holds shard i, contiguous id ranges); the
- * calling thread drives all devices (one stream per device), the per-device top-k lists meet on the first device
+ * the context is row-sharded over the devices (device i of the list holds shard i of the block-cyclic deal, see
+ * vrod_ctx_create_sharded); the calling thread drives all devices (one stream per device), the per-device top-k lists meet on the first device
  * through direct NVLink peer access (fused push + merge kernel; peer copies for large batches or when the devices
  * have no peer access) and only that device is read by the host.  All collection calls work on such a context
  * with GLOBAL meaning (read_rows takes global row indices, shard reports base 0 and every row); the device-pointer
@@ -119,8 +124,8 @@ VROD_API int vrod_ctx_world(vrod_ctx *ctx);
 
 /* ---- collections (Database surface) ---------------------------------------------------- */
 
-/* CREATE: `capacity_rows` is the GLOBAL row capacity; a sharded context keeps ceil(capacity/world)
- * rows per rank.  dim >= 1.  Names are 1..200 characters of [A-Za-z0-9_.-], not "." or ".." (they become file
+/* CREATE: `capacity_rows` is the GLOBAL row capacity (an initial size: collections grow); a sharded context keeps
+ * about capacity/world rows per rank.  dim >= 1.  Names are 1..200 characters of [A-Za-z0-9_.-], not "." or ".." (they become file
  * names and whitespace-delimited config tokens in the Database layer). */
 VROD_API vrod_status vrod_collection_create(vrod_ctx *ctx, const char *name, uint32_t dim, vrod_metric metric,
                                             uint64_t capacity_rows, vrod_collection **out);
@@ -135,15 +140,17 @@ VROD_API vrod_status vrod_collection_info(vrod_collection *c, uint32_t *dim, vro
 
 /* INSERT / BULKINSERT: append n rows (row-major n x dim f32).  Ids are insertion indices; the id of
  * the first appended row is written to *first_id (may be NULL).  In a sharded context every rank
- * passes the same rows and keeps the part that falls into its range.  A single-GPU collection that is full
- * grows (capacity doubles, rows are moved device-to-device); a sharded one returns VROD_ENOMEM. */
+ * passes the same rows and keeps the blocks that are dealt to it; a batch with a NaN / infinity is rejected by every
+ * rank alike.  A collection that is full grows: the capacity at least doubles, every shard re-allocates on its own
+ * (device-to-device move), no row changes its shard. */
 VROD_API vrod_status vrod_collection_insert(vrod_collection *c, const float *rows, uint64_t n, uint64_t *first_id);
 
 /* Persistence (the step after INSERT; the reference's Database::load is a todo!(), src/database/mod.rs:19-21).
  * vrod_collection_save writes this collection to `path`: a 64-byte header ("VRODCOL1", dim, metric, count)
- * followed by count x dim f32 rows, row-major, unpadded, little-endian.  Single-GPU contexts only.
- * vrod_collection_load creates collection `name` from such a file; capacity_rows = 0 means "as many as the
- * file holds".  In a sharded context every rank reads only the rows of its own id range. */
+ * followed by count x dim f32 rows in id order, row-major, unpadded, little-endian -- the same file whatever the
+ * context.  vrod_collection_load creates collection `name` from such a file; capacity_rows = 0 means "as many as
+ * the file holds".  In a process-per-GPU context both are collective (same path on every rank, a shared file
+ * system): rank 0 lays the file out and every rank writes / reads only the blocks it holds. */
 VROD_API vrod_status vrod_collection_save(vrod_collection *c, const char *path);
 VROD_API vrod_status vrod_collection_load(vrod_ctx *ctx, const char *name, const char *path, uint64_t capacity_rows,
                                           vrod_collection **out);
@@ -153,9 +160,11 @@ VROD_API vrod_status vrod_collection_load(vrod_ctx *ctx, const char *name, const
  * i is the global row index.  The CPU oracle replays it bit for bit. */
 VROD_API vrod_status vrod_collection_fill_synthetic(vrod_collection *c, uint64_t n, uint64_t seed);
 
-/* Copy rows [row0, row0+n) of THIS RANK's shard (local indices) back to the host (n x dim). */
+/* Copy rows [row0, row0+n) of THIS RANK's shard (local indices; a single-GPU or multi-GPU context: global row
+ * indices) back to the host (n x dim). */
 VROD_API vrod_status vrod_collection_read_rows(vrod_collection *c, uint64_t row0, uint64_t n, float *out);
-/* Global id of this rank's local row 0 and the number of rows it holds. */
+/* Global id of this rank's local row 0 (rank * VROD_SHARD_BLOCK) and the number of rows it holds; local row l has
+ * id ((l / VROD_SHARD_BLOCK) * world + rank) * VROD_SHARD_BLOCK + l % VROD_SHARD_BLOCK. */
 VROD_API vrod_status vrod_collection_shard(vrod_collection *c, uint64_t *id_base, uint64_t *local_rows);
 
 /* ---- SEARCH ----------------------------------------------------------------------------- */
