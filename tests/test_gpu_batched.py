@@ -250,6 +250,50 @@ def test_clustered_data_stays_on_the_tensor_cores(ctx, oracle):
     ctx.drop("learn")
 
 
+def test_rows_sorted_by_distance_defeat_the_guessed_thresholds_once(ctx, oracle):
+    """The batched pass filters each phase at a GUESSED threshold: the rank among the keys seen so far below which the phase
+    should find its k' keys if the rows to come resemble the rows already seen.  Rows inserted nearest-first break that
+    assumption: every guess is too tight, the finish kernels notice (fewer than k' keys under the threshold the rows were
+    filtered with) and flag the queries.  The first such batch is answered again at the k'-th best key (no assumption),
+    the collection stops guessing, later batches run one plain pass -- and every answer is the oracle's throughout."""
+    rng = np.random.default_rng(11)
+    n, d, b, k = 400_000, 64, 64, 10
+    X = oracle.fill(n, d, 93)
+    q0 = oracle.fill(1, d, 94)[0]
+    X = X[np.argsort(((X.astype(np.float64) - q0) ** 2).sum(axis=1), kind="stable")]   # nearest to q0 first
+    Q = (q0 + 0.01 * rng.standard_normal((b, d))).astype(np.float32)
+    c = ctx.create("sorted", d, 0, n)
+    c.insert(X)
+    c.set_path(3)
+    want = oracle.search(X, Q, k, 0)
+    tiles, rescans = [], []
+    for _ in range(3):
+        s0 = ctx.stats()
+        assert_same(*c.search(Q, k), *want, "rows sorted by distance")
+        s1 = ctx.stats()
+        tiles.append(s1["batched_tiles"] - s0["batched_tiles"])
+        rescans.append(s1["fast_scans"] - s0["fast_scans"])
+    assert tiles[0] == 2 * tiles[1] == 2 * tiles[2], f"the first batch runs twice (guessed, then plain), later ones once: {tiles}"
+    assert rescans[1] == rescans[2] == 0, f"no single-query rescans once the collection has stopped guessing: {rescans}"
+    ctx.drop("sorted")
+
+
+def test_guessed_thresholds_hold_on_exchangeable_rows(ctx, oracle):
+    """Rows in random order (the synthetic fill): the guesses hold, no query is rescanned, one pass per batch."""
+    n, d, b, k = 1_000_000, 64, 300, 100
+    c = ctx.create("guess_ok", d, 0, n)
+    c.fill_synthetic(n, 91)
+    c.set_path(3)
+    Q = oracle.fill(b, d, 92)
+    s0 = ctx.stats()
+    ids, dist = c.search(Q, k)
+    s1 = ctx.stats()
+    assert s1["fast_scans"] == s0["fast_scans"], "a guessed threshold failed on rows in random order"
+    assert s1["batched_tiles"] - s0["batched_tiles"] == ((n + 127) // 128) * ((b + 255) // 256)
+    assert_same(ids[:16], dist[:16], *oracle.search(oracle.fill(n, d, 91), Q[:16], k, 0), "guessed thresholds, random order")
+    ctx.drop("guess_ok")
+
+
 @pytest.mark.parametrize("metric", [0, 1])
 def test_many_queries_few_rows_keeps_the_tensor_core_answers(ctx, oracle, metric):
     """b >= 8192 with k ~ 100 on ~100k rows: few row tiles per CTA and 8x phase growth make the per-(CTA, query) lists

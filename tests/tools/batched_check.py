@@ -32,7 +32,7 @@ cases = [(1000, 128, 0, 10, 4), (50000, 128, 0, 10, 300), (50000, 128, 1, 100, 2
          (20000, 100, 1, 10, 64), (30000, 32, 0, 100, 100), (200000, 128, 0, 100, 1024), (300000, 96, 1, 10, 1000)]
 if len(sys.argv) > 1 and sys.argv[1] == "first":
     cases = cases[:1]
-if len(sys.argv) > 1 and sys.argv[1].startswith("prof"):
+if len(sys.argv) > 1 and (sys.argv[1].startswith("prof") or sys.argv[1] == "one"):
     cases = []
 for cs in cases:
     check(*cs)
@@ -56,6 +56,8 @@ def timeit(n, d, metric, k, b, iters=3):
     ctx.drop("t")
 if len(sys.argv) > 1 and sys.argv[1] == "prof":
     timeit(1000000, 128, 0, 100, 1024, iters=2)
+elif len(sys.argv) > 1 and sys.argv[1] == "one":      # one n d metric k b
+    timeit(*[int(a) for a in sys.argv[2:7]])
 elif len(sys.argv) > 1 and sys.argv[1] == "prof10":
     timeit(10000000, 128, 0, 100, 1024, iters=1)
 elif bad == 0 and not (len(sys.argv) > 1 and sys.argv[1] == "first"):

@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
         const int ew = warp - 2;                     // 0..15
         const int part = ew >> 2;                    // which 64 of the 256 query columns
         unsigned long long *cand = p.cand + (size_t)blockIdx.x * BN * CAP;
-        long long w_tfull = 0, w_prune = 0, n_slow = 0;
+        long long w_tfull = 0, w_prune = 0, n_slow = 0, w_park = 0, w_flush = 0, w_bar = 0;
         const long long tstart = kDbg ? clock64() : 0;
         // per-row factor of the NEXT tile is fetched one tile ahead (its global-load latency would otherwise
         // sit on the critical path of every tile)
@@ -754,6 +754,11 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 tc_ld32(taddr, ra);
                 tc_ld32(taddr + 32, rb);
                 tc_wait_ld();
+                // the scores are in registers: the accumulator stage goes back to the MMA warp NOW, before the filter, the
+                // parking and the flush -- a warp with candidates is late for its next tile, not for the tensor core
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->tempty[acc]);
                 float wa = H ? block_max_h(ra) : block_max<COS>(ra, thr_p, hx, ninf);
                 float wb = H ? block_max_h(rb) : block_max<COS>(rb, thr_p + 32, hx, ninf);
                 if (kDbg && (p.debug_skip & 4)) {   // ldonly: no scan of the blocks
@@ -762,31 +767,35 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 }
                 const bool hita = (H ? wa > 0.f : cand_hit<COS>(wa, hx)) && rowok;
                 const bool hitb = (H ? wb > 0.f : cand_hit<COS>(wb, hx)) && rowok;
-                if (__builtin_expect(__any_sync(kFull, hita || hitb), 0)) {
+                if (__builtin_expect(__any_sync(kFull, hita || hitb), 0) && !(kDbg && (p.debug_skip & 16))) {
                     if (kDbg) n_slow++;
+                    const long long tp = kDbg ? clock64() : 0;
                     if (__any_sync(kFull, hita)) on_hit(ra, hita, col0);
                     if (__any_sync(kFull, hitb)) on_hit(rb, hitb, col0 + 32);
+                    if (kDbg) w_park += clock64() - tp;
                 }
             }
-            // accumulator stage drained: hand it back to the MMA warp (of the leader CTA)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (leader) mbar_arrive(&ctl->tempty[acc]);
-                else mbar_arrive_leader(&ctl->tempty[acc]);
+            if (DENSE || (kDbg && (p.debug_skip & 1))) {   // (the hot path above has released its stage already)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->tempty[acc]);
             }
 
             // the stage is back with the MMA warp: now the parked candidates
-            if (nst) {
+            if (nst && !(kDbg && (p.debug_skip & 8))) {
+                const long long tf = kDbg ? clock64() : 0;
                 __syncwarp();
                 stash_flush<COS, H>(0, nst, slots, ctl, cand, p.qflags, g * BN, p.b, lane);
+                if (kDbg) w_flush += clock64() - tf;
             }
             // list maintenance every kCheckEvery tiles, per 64-column part: the four warps that append to the lists of a
             // part (one per lane quadrant) meet at the part's own named barrier -- not all sixteen, so a warp that is late
             // after a flush holds up three others, not the whole epilogue.  The lists have room for the appends of the
             // tiles in between (PRUNE_AT).
             if (DENSE || (i + 1) % kCheckEvery != 0) continue;
+            const long long tb = kDbg ? clock64() : 0;
             asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
+            if (kDbg) w_bar += clock64() - tb;
             if (*(volatile int *)&ctl->pflag[part]) {
                 t0 = kDbg ? clock64() : 0;
                 for (int q = col0 + quad; q < col0 + BN / 4; q += 4) {
@@ -807,6 +816,9 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
             p.dbg[blockIdx.x * 16 + 2] = tot;
             p.dbg[blockIdx.x * 16 + 3] = w_tfull;
             p.dbg[blockIdx.x * 16 + 4] = w_prune;
+            p.dbg[blockIdx.x * 16 + 10] = w_park;
+            p.dbg[blockIdx.x * 16 + 11] = w_flush;
+            p.dbg[blockIdx.x * 16 + 12] = w_bar;
 
         }
         asm volatile("bar.sync 5, 512;" ::: "memory");   // all epilogue warps (ids 1..4 are the parts' own barriers)
@@ -1011,6 +1023,11 @@ struct FinishParams {
     // construction (tight clusters: whatever the contraction cannot tell apart becomes a candidate, up to `keep` of them)
     int need, keep;         // rank of the key the threshold hangs on (kprime, band mode: k); stride and capacity of glist
     const float *qband;     // [b] band width per query (nullptr: classic mode)
+    // GUESSED thresholds (launch_batched_search): the next phase does not filter at the kprime-th best key seen so far but
+    // at the guess_rank-th (< kprime), the rank below which the next phase is expected to find its kprime keys.  The finish
+    // of a phase that ran under a guess checks that it did (prev_guess): the new kprime-th key must not lie above the
+    // threshold the rows were filtered with, or rows between the two were lost and the query is flagged (qflags bit 2).
+    int guess_rank, prev_guess;
 };
 
 constexpr int kFinCtl = 128;
@@ -1135,14 +1152,25 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
     block_select<kFinPer>(ctl, buf, p.need, p.cap, tid, hist, band, p.qband ? p.keep : 0);
 
     const int ncand = ctl->cnt;
+    if (p.prev_guess && tid == 0) {
+        // the phase just merged was filtered at a guessed threshold: it holds if at least `need` keys lie at or below it
+        const float kth = ctl->thrkey != kKeyMax ? ord2f((uint32_t)(ctl->thrkey >> 32)) : __int_as_float(0x7f800000);
+        if (!(kth <= p.gthr[qi])) atomicOr(p.qflags + qi, 2);
+    }
     if (!p.final_phase) {
         for (int i = tid; i < ncand; i += kScanThreads) p.glist[(size_t)qi * p.keep + i] = buf[i];
+        const bool guess = p.guess_rank > 0 && p.guess_rank < ncand && ctl->thrkey != kKeyMax;   // uniform
+        if (guess) {
+            // the list is stored; the buffer may now be cut down to the guess_rank best keys to find the guess_rank-th
+            __syncthreads();
+            block_select<kFinPer>(ctl, buf, p.guess_rank, p.cap, tid, hist);
+        }
         if (tid == 0) {
             p.gcnt[qi] = ncand;
             // a merge that could not hold everything it had to keep (band mode: more rows inside the error band than the list
             // has room for) has dropped keys: the flag must outlive this launch, the last phase cannot know
             if (ctl->overflow) atomicOr(p.qflags + qi, 1);
-            // (the kept keys are unsorted: the kprime-th one is the select's threshold key)
+            // (the kept keys are unsorted: the kprime-th one -- or the guess_rank-th -- is the select's threshold key)
             float thr = ctl->thrkey != kKeyMax ? ord2f((uint32_t)(ctl->thrkey >> 32)) : __int_as_float(0x7f800000);
             if (p.qt) {   // bf16 mode: finite thresholds only, folded into the query mirror as three exact parts
                 const float cap = p.qcap[qi];
@@ -1188,7 +1216,9 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
         }
     }
     if (tid == 0) {
-        int bad = (ctl->overflow | (p.qflags[qi] & 1)) ? 1 : 0;
+        const int qf = p.qflags[qi];   // (this thread's own atomicOr above included)
+        int bad = (ctl->overflow | (qf & 1)) ? 1 : 0;
+        if (qf & 2) bad |= 16;
         if (p.n > (uint32_t)ncand) {
             const int kk = (int)p.k < ncand ? (int)p.k : ncand;
             // (no candidate at all -- e.g. a query the tensor-core pass could not represent: flagged below, kk < k)
@@ -1219,7 +1249,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
                 printf("[finish dbg] q %u: bad %d (1 overflow/flag, 4 bound, 8 short) ncand %d u %.6g lb %.6g T %.6g nq %.6g xn_max %.6g\n", qi, bad,
                        ncand, u, (double)lb, (double)T, nq, xn_max);
         }
-        p.status[qi] = bad ? 1 : 0;
+        p.status[qi] = bad ? ((bad & 16) ? 2 : 1) : 0;   // 2: a guessed threshold did not hold (the caller counts those)
     }
 }
 
@@ -1288,9 +1318,52 @@ bool batched_supported(const ShardView &s, uint32_t b, uint32_t k) {
     return encode_fn() != nullptr;
 }
 
+// Guessed thresholds.  After a phase the kprime best keys of the n0 rows seen so far are known exactly.  If the next phase
+// takes the rows seen to g * n0 and the new rows resemble the old ones (exchangeable row order), the key of rank r among
+// the old ones is a threshold below which the new rows contribute NB(r, 1/g) keys (negative binomial: Poisson counts
+// whose rate has the Gamma(r) uncertainty of an r-th order statistic).  The guess holds when r + that count >= kprime.
+// guess_rank returns the smallest r whose failure probability is below 1e-9 per query and phase, plus a margin for rows
+// that are only roughly exchangeable; 0 when guessing gains nothing.  (kprime = 256, g = 8: r = 72 -- the phase collects
+// ~500 candidates per query where the kprime-th best key as threshold lets ~1800 through.)
+static double nb_cdf(int m, int r, double pr) {   // P(NB(r, pr) <= m), in the log domain
+    if (m < 0) return 0.0;
+    const double lq = log1p(-pr);
+    double lt = (double)r * log(pr), top = lt, acc = 1.0;   // the sum so far = exp(top) * acc
+    for (int i = 0; i < m; ++i) {
+        lt += log((double)(i + r) / (double)(i + 1)) + lq;
+        if (lt > top) {
+            acc = acc * exp(top - lt) + 1.0;
+            top = lt;
+        } else {
+            acc += exp(lt - top);
+        }
+    }
+    return exp(top) * acc;
+}
+static int guess_rank(int kprime, double g) {
+    if (!(g > 1.25)) return 0;
+    struct Memo { int kprime; double g; int r; };
+    static thread_local Memo memo[8] = {};
+    static thread_local int memo_next = 0;
+    for (const Memo &m : memo)
+        if (m.kprime == kprime && m.g == g) return m.r;
+    int lo = 1, hi = kprime;   // smallest r with P(r + NB(r, 1/g) < kprime) < tol; the probability falls with r
+    while (lo < hi) {
+        const int mid = (lo + hi) / 2;
+        if (nb_cdf(kprime - mid - 1, mid, 1.0 / g) < 1e-9) hi = mid;
+        else lo = mid + 1;
+    }
+    int r = lo + lo / 16 + 2;
+    if (r * 10 > kprime * 9) r = 0;   // nearly the kprime-th key anyway
+    memo[memo_next] = Memo{kprime, g, r};
+    memo_next = (memo_next + 1) % 8;
+    return r;
+}
+
 cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t b, uint32_t k, int sm_count, void **scratch,
                                   size_t *scratch_bytes, int *status, Hit *out, unsigned long long *out_ids, float *out_dist,
-                                  cudaStream_t st, BatchedStats *stats, cudaEvent_t ev_start, cudaEvent_t ev_stop, bool band_mode) {
+                                  cudaStream_t st, BatchedStats *stats, cudaEvent_t ev_start, cudaEvent_t ev_stop, bool band_mode,
+                                  bool guess_mode) {
     // operand mode: bf16 mirrors with folded thresholds when the collection has a mirror, else the stored f32 rows as tf32
     const bool H = s.rows_h != nullptr;
     const uint32_t kd = mirror_kd(s.dim), ld_h = mirror_ld(s.dim);
@@ -1394,7 +1467,8 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         if (kDbg) {
             const char *dbg = getenv("VROD_BATCHED_DEBUG");
             p.debug_nocand = dbg && (strcmp(dbg, "nocand") == 0 || strstr(dbg, "noepi") || strstr(dbg, "nomma") || strstr(dbg, "ldonly"));
-            p.debug_skip = dbg ? ((strstr(dbg, "noepi") ? 1 : 0) | (strstr(dbg, "nomma") ? 2 : 0) | (strstr(dbg, "ldonly") ? 4 : 0)) : 0;
+            p.debug_skip = dbg ? ((strstr(dbg, "noepi") ? 1 : 0) | (strstr(dbg, "nomma") ? 2 : 0) | (strstr(dbg, "ldonly") ? 4 : 0) |
+                                  (strstr(dbg, "noflush") ? 8 : 0) | (strstr(dbg, "nopark") ? 16 : 0)) : 0;
             static long long *dbg_buf = nullptr;
             if (dbg && !dbg_buf) cudaMalloc(&dbg_buf, 1024 * 16 * sizeof(long long));
             p.dbg = dbg ? dbg_buf : nullptr;
@@ -1513,9 +1587,28 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         // the candidate rate of a phase is ~k'/rows_seen instead of ~k'/rows_seen_by_one_CTA.
         uint32_t t_begin = 0, t_end = cpg_max * psz < ntiles ? cpg_max * psz : ntiles;
         bool first = true;
+        static const bool no_guess_env = getenv("VROD_BATCHED_NO_GUESS") != nullptr;
+        const bool guess = guess_mode && !band && !no_guess_env;
+        int prev_guess = 0;
         if (ev_start && g0 == 0) cudaEventRecord(ev_start, st);
         while (true) {
             const bool last = t_end >= ntiles;
+            // The next phase's extent is fixed now: the finish kernel of this phase publishes the threshold it filters with.
+            // 3.5x the rows seen so far per phase at the kprime-th key (measured best of 2.5 / 3.5 / 5 / 7 / 10 at configs[2]: new +
+            // carried keys fit the 2048-key select); short scans (few tiles per unit) take bigger steps: there every
+            // extra phase costs a tile launch and a finish kernel (~50 us) that the tiles cannot amortise.  Guessed
+            // thresholds let through ~kprime * 2 keys per phase whatever its length, so the steps are 8x.
+            uint32_t t_next = t_end;
+            if (!last) {
+                static const double growth_env = getenv("VROD_BATCHED_GROWTH") ? atof(getenv("VROD_BATCHED_GROWTH")) : 0.0;
+                const double growth = growth_env > 1.0 ? growth_env : ((guess || (super_tiles / cpg_max) < 256) ? 8.0 : 3.5);
+                unsigned long long nxt = (unsigned long long)((double)t_end * growth);
+                if (nxt <= t_end) nxt = t_end + psz;
+                nxt -= nxt % psz;
+                t_next = nxt >= ntiles ? ntiles : (uint32_t)nxt;
+                // a short rest is not worth a phase of its own
+                if (guess && ntiles - t_next < t_next / 2) t_next = ntiles;
+            }
             p.tile_begin = t_begin;
             p.tile_end = t_end;
             p.thr_init = (first && !H) ? nullptr : gthr;   // bf16 mode starts from the finite caps of prep_queries_kernel
@@ -1523,6 +1616,13 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             if (e != cudaSuccess) return e;
             f.first_phase = first ? 1 : 0;
             f.final_phase = last ? 1 : 0;
+            f.prev_guess = prev_guess;
+            f.guess_rank = 0;
+            if (guess && !last) {
+                const double rows_seen = (double)t_end * BM, rows_next = (double)(t_next < ntiles ? (unsigned long long)t_next * BM : s.n);
+                if (rows_seen >= 8.0 * kprime) f.guess_rank = guess_rank(kprime, rows_next / rows_seen);
+            }
+            prev_guess = f.guess_rank > 0 ? 1 : 0;
             fin_fn<<<bq, kScanThreads, fsmem, st>>>(f);
             e = cudaGetLastError();
             if (e != cudaSuccess) return e;
@@ -1531,9 +1631,9 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
                 static long long h[1024 * 16];
                 cudaStreamSynchronize(st);
                 cudaMemcpy(h, g_dbg_buf, sizeof(long long) * grid * 16, cudaMemcpyDeviceToHost);
-                double a[8] = {0};
+                double a[13] = {0};
                 for (uint32_t c = 0; c < grid; ++c)
-                    for (int jx = 0; jx < 8; ++jx) a[jx] += (double)h[c * 16 + jx] / grid;
+                    for (int jx = 0; jx < 13; ++jx) a[jx] += (double)h[c * 16 + jx] / grid;
                 if (psz == 2) {
                     double le = 0, pe = 0, wf = 0, wpf = 0, mt = 0;
                     for (uint32_t c = 0; c < grid; c += 2) {
@@ -1545,22 +1645,13 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
                             mt / np, wf / np, wpf / np, le / np, pe / np);
                 }
                 fprintf(stderr, "[batched dbg] tiles [%u,%u) avg/CTA: warp2 slow entries %.0f, mma total %.0f, candidates %.0f | epi wait_tfull %.0f prune %.0f | mma wait_tempty %.0f wait_full %.0f "
-                                "| epi total %.0f | tiles/CTA %u\n",
-                        t_begin, t_end, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], (t_end - t_begin + cpg_max * psz - 1) / (cpg_max * psz));
+                                "| epi total %.0f (warp2: park %.0f flush %.0f part barrier %.0f) | tiles/CTA %u\n",
+                        t_begin, t_end, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[10], a[11], a[12], (t_end - t_begin + cpg_max * psz - 1) / (cpg_max * psz));
             }
             if (last) break;
             first = false;
             t_begin = t_end;
-            // 3.5x per phase (measured best of 3.5 / 5 / 7 / 10 at configs[2]: new + carried keys fit the 2048-key
-            // select); short scans (few tiles per unit) take bigger steps: there every extra phase costs a tile launch
-            // and a finish kernel (~60 us) that the tiles cannot amortise.  (8x steps only while the phases are tiny,
-            // 3.5x afterwards, measured the same as plain 3.5x at configs[2].)
-            static const double growth_env = getenv("VROD_BATCHED_GROWTH") ? atof(getenv("VROD_BATCHED_GROWTH")) : 0.0;
-            const double growth = growth_env > 1.0 ? growth_env : ((super_tiles / cpg_max) < 256 ? 8.0 : 3.5);
-            unsigned long long nxt = (unsigned long long)((double)t_end * growth);
-            if (nxt <= t_end) nxt = t_end + psz;
-            nxt -= nxt % psz;
-            t_end = nxt >= ntiles ? ntiles : (uint32_t)nxt;
+            t_end = t_next;
         }
         if (ev_stop && g0 + groups >= qgroups) cudaEventRecord(ev_stop, st);
         if (stats) stats->tiles += (uint64_t)ntiles * groups;

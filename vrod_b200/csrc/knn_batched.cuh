@@ -32,9 +32,13 @@ bool batched_supported(const ShardView &s, uint32_t b, uint32_t k);
 // band_mode: keep every candidate within the approximate surrogate's error band above the k-th best one (up to 1024 per
 // query) instead of a fixed k' of them -- for collections whose neighbours the bf16 contraction cannot tell apart (tight
 // clusters under the Euclidean metric), where the fixed-k' proof fails for every query.
+// guess: filter every phase at a GUESSED threshold -- the rank of the keys seen so far below which the phase is expected
+// to find its k' keys if the rows still to come resemble the rows already seen -- instead of the k'-th best key so far
+// (2-3x fewer candidates, half as many phases).  A guess that did not hold is detected (status[qi] = 2: the caller
+// rescans the query, and stops guessing for a collection whose row order defeats it).
 cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t b, uint32_t k, int sm_count,
                                   void **scratch, size_t *scratch_bytes, int *status, Hit *out, unsigned long long *out_ids,
                                   float *out_dist, cudaStream_t st, BatchedStats *stats, cudaEvent_t ev_start = nullptr,
-                                  cudaEvent_t ev_stop = nullptr, bool band_mode = false);
+                                  cudaEvent_t ev_stop = nullptr, bool band_mode = false, bool guess = false);
 
 }  // namespace vrod

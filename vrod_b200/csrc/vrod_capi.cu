@@ -270,6 +270,9 @@ struct vrod_collection {
     // instead of a fixed k' of them: switched on, for good, by the first batch whose fixed-k' proofs fail for more than
     // 5 % of the queries (tight clusters under the Euclidean metric)
     bool band_mode = false;
+    // the batched pass filters its phases at guessed thresholds (knn_batched.cuh: guess) until a batch shows that this
+    // collection's row order defeats the guesses (rows inserted cluster by cluster, sorted rows)
+    bool guess_off = false;
     std::vector<vrod_collection *> parts;   // collection of a multi-GPU parent context: one part per device, in id order
 };
 
@@ -1337,7 +1340,7 @@ static vrod_status enqueue_batched(vrod_collection *c, const float *d_q, uint32_
     }
     cudaError_t e = launch_batched_search(sb, d_q, b, k, ctx->sms, &ctx->batched.p, &ctx->batched.bytes, d_status, local,
                                           direct ? reinterpret_cast<unsigned long long *>(d_ids) : nullptr, direct ? d_dist : nullptr,
-                                          ctx->stream, &bs, e0, e1, c->band_mode);
+                                          ctx->stream, &bs, e0, e1, c->band_mode, !c->guess_off);
     if (e != cudaSuccess) return fail(VROD_ECUDA, std::string("batched search: ") + cudaGetErrorString(e));
     if (sample)
         ctx->cost.pending(2, (double)((b + 255) / 256) * ((double)s.n / 128.0) * ((double)mirror_ld(s.dim) / 144.0) / (double)ctx->sms);
@@ -1482,8 +1485,27 @@ static vrod_status batched_rescans(vrod_collection *c, const float *d_q, uint32_
     const bool direct = ctx->world == 1;
     Hit *local = reinterpret_cast<Hit *>(ctx->hits_local.p);
     const ScanScratch scr = scan_scratch(ctx, d_status);
-    uint32_t flagged = 0;
-    for (uint32_t qi = 0; qi < b; ++qi) flagged += hs[qi] ? 1u : 0u;
+    uint32_t flagged = 0, misguessed = 0;
+    for (uint32_t qi = 0; qi < b; ++qi) {
+        flagged += hs[qi] ? 1u : 0u;
+        misguessed += hs[qi] == 2 ? 1u : 0u;
+    }
+    static const bool verbose = getenv("VROD_VERBOSE") != nullptr;
+    if (verbose && flagged)
+        fprintf(stderr, "[vrod] batched pass of %u queries on '%s': %u flagged (%u by a guessed threshold); band mode %d, guessing %d\n", b,
+                c->name.c_str(), flagged, misguessed, (int)c->band_mode, (int)!c->guess_off);
+    if (misguessed > 2u + b / 64u && !c->guess_off) {
+        // Guessed thresholds failed for more than a stray query: the rows of this collection do not arrive in an order in
+        // which the rows seen so far predict the rows to come.  Its batched passes filter at the k'-th best key from now
+        // on (more candidates, more phases, no assumption) -- starting with this batch.
+        c->guess_off = true;
+        vrod_status st = enqueue_batched(c, d_q, b, k, d_ids, d_dist, d_status);
+        if (st == VROD_OK) st = batched_fetch_status(c, b, d_status);
+        if (st != VROD_OK) return st;
+        VROD_CUDA(cudaEventSynchronize(ctx->ev_status));
+        flagged = 0;
+        for (uint32_t qi = 0; qi < b; ++qi) flagged += hs[qi] ? 1u : 0u;
+    }
     if (flagged * 20u > b && !c->band_mode && c->rows_h && c->path != 4) {
         // more than 5 % of the fixed-k' proofs failed: this collection holds neighbours the bf16 contraction cannot tell
         // apart.  From now on its batched passes keep every candidate inside the error band (up to 1024 per query) -- and
