@@ -111,6 +111,7 @@ struct CandCtl {
     float u_val;                // value part of the kprime-th approximate key (guard)
     int ncand;
     unsigned long long thrkey2; // last-CTA merge: the warps' offers for the bound T0
+    float dq2;                  // batched finish: ||bf16(q) - q||^2 (guard of the bf16 operand mode)
 };
 
 __device__ __forceinline__ void cand_reset(CandCtl *ctl) {

@@ -10,6 +10,7 @@ struct ShardView {
     const float *inv_norm;   // n f32: 1/||x|| (0 for a zero row)               [cosine fast scan]
     const float *sq_norm;    // n f32: ||x||^2                                  [batched L2 path]
     const unsigned int *maxnorm_bits;  // f32 bits of max ||x||^2 over the shard [batched guard]
+    unsigned int *mirror_stats;        // [2] f32 bits of max ||x~ - x||^2 and max ||x~||^2 over the mirrored rows (x~: the bf16 mirror row) [bf16 guard]
     const unsigned short *rows_h;      // tiled bf16 mirror of the rows (knn_batched.cu: mirror_bytes), nullptr if none [batched bf16 mode]
     uint32_t n;              // local rows (< 2^32)
     uint32_t dim, ld;

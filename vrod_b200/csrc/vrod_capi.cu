@@ -1256,6 +1256,7 @@ static ShardView shard_view(const vrod_collection *c) {
     s.inv_norm = c->inv_norm;
     s.sq_norm = c->sq_norm;
     s.maxnorm_bits = reinterpret_cast<const unsigned int *>(c->flags) + 1;
+    s.mirror_stats = reinterpret_cast<unsigned int *>(c->flags) + 2;
     s.n = (uint32_t)c->local;
     s.dim = c->dim;
     s.ld = c->ld;
