@@ -1117,6 +1117,9 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
     int *hist = reinterpret_cast<int *>(buf + p.cap);   // [kFinHist] block_select scratch
     const float band = p.qband ? p.qband[qi] : 0.f;
     int *offs = hist + kFinHist;                        // [nlists + 2]
+    // (all threads fetch the counts -- one memory latency --, warp 0 turns them into offsets)
+    for (uint32_t m = tid; m < nlists; m += kScanThreads) offs[m + 2] = p.cnt_in[(size_t)cta_of(m) * BN + ql];
+    __syncthreads();
     if (warp == 0) {
         int carry = p.first_phase ? 0 : p.gcnt[qi];
         if (lane == 0) {
@@ -1125,7 +1128,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
         }
         for (uint32_t m0 = 0; m0 < nlists; m0 += 32) {
             const uint32_t m = m0 + lane;
-            int v = m < nlists ? p.cnt_in[(size_t)cta_of(m) * BN + ql] : 0;
+            int v = m < nlists ? offs[m + 2] : 0;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(kFull, v, o);
@@ -1188,20 +1191,35 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
             }
             const bool optimistic = all_at_once && thr != kKeyMax && lo < nlists;
             const uint32_t m1 = optimistic ? nlists : lo;
-            for (uint32_t m = m0 + warp; m < m1; m += kScanWarps) {
-                const int n_m = offs[m + 2] - offs[m + 1];
-                const unsigned long long *src = p.cand + ((size_t)cta_of(m) * BN + ql) * CAP;
-                for (int j0 = lane; j0 < n_m; j0 += 128) {
-                    unsigned long long keys[4];
+            // a warp takes FOUR lists at a time, two keys of each per lane and step: 8 independent loads in flight per
+            // lane (one list at a time left the warp waiting out a memory latency per list: 17 in a row for the 148 lists
+            // of a single query group's start phase)
+            constexpr int kLists = 4;
+            for (uint32_t mb = m0 + warp; mb < m1; mb += kLists * kScanWarps) {
+                int n_m[kLists], longest = 0;
+                const unsigned long long *src[kLists];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) keys[e] = j0 + 32 * e < n_m ? __ldcg(src + j0 + 32 * e) : kKeyMax;
+                for (int e = 0; e < kLists; ++e) {
+                    const uint32_t m = mb + e * kScanWarps;
+                    n_m[e] = m < m1 ? offs[m + 2] - offs[m + 1] : 0;
+                    src[e] = p.cand + ((size_t)cta_of(m < m1 ? m : mb) * BN + ql) * CAP;
+                    longest = n_m[e] > longest ? n_m[e] : longest;
+                }
+                for (int j0 = lane; j0 < longest; j0 += 64) {
+                    unsigned long long keys[kLists][2];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (keys[e] < thr) {
-                            const int pos = atomicAdd(&ctl->cnt, 1);
-                            if (pos < p.cap) buf[pos] = keys[e];
-                        }
+                    for (int e = 0; e < kLists; ++e) {
+                        keys[e][0] = j0 < n_m[e] ? __ldcg(src[e] + j0) : kKeyMax;
+                        keys[e][1] = j0 + 32 < n_m[e] ? __ldcg(src[e] + j0 + 32) : kKeyMax;
                     }
+#pragma unroll
+                    for (int e = 0; e < kLists; ++e)
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+                            if (keys[e][u] < thr) {
+                                const int pos = atomicAdd(&ctl->cnt, 1);
+                                if (pos < p.cap) buf[pos] = keys[e][u];
+                            }
                 }
             }
             __syncthreads();
