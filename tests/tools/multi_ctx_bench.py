@@ -2,7 +2,7 @@
 the host-buffer call a vRod SearchCommand would make (one thread, host query in, host ids / distances out), parity-checked
 against a full oracle replay; then the same collection with 1024-query batches.  Prints one JSON line."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from oracle import oracle as O

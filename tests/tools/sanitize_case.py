@@ -2,7 +2,7 @@
 exact scan, a generic dimension), the batched tcgen05 path in bf16 and tf32 operand modes (dense start phase, stash,
 finish kernels, band mode), inserts with growth.  Answers are checked against the oracle."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import oracle as O
 from vrod_b200 import ffi

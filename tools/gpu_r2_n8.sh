@@ -14,4 +14,4 @@ for e in d.get("extra", []):
     print(" extra", e["workload"], "value %.0f e2e %.0f ms/step %.3f roofline %s %.3f parity %s" % (e["value"], e["e2e"]["value"], e["ms_per_step"], e["roofline"]["bound"], e["roofline"]["frac"], e["parity"]["ok"]))
 print("wall", d.get("bench_wall_s"))
 PY
-timeout 600 python tools/multi_ctx_bench.py > gpurun_out/multi_ctx_n8.json 2> gpurun_out/multi_ctx_n8.err; tail -1 gpurun_out/multi_ctx_n8.json | cut -c1-900; tail -3 gpurun_out/multi_ctx_n8.err
+timeout 600 python tests/tools/multi_ctx_bench.py > gpurun_out/multi_ctx_n8.json 2> gpurun_out/multi_ctx_n8.err; tail -1 gpurun_out/multi_ctx_n8.json | cut -c1-900; tail -3 gpurun_out/multi_ctx_n8.err
