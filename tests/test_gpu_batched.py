@@ -245,7 +245,7 @@ def test_clustered_data_stays_on_the_tensor_cores(ctx, oracle):
         tiles.append(s1["batched_tiles"] - s0["batched_tiles"])
         rescans.append(s1["fast_scans"] - s0["fast_scans"])
     assert all(t > 0 for t in tiles), f"every batch should go through the tensor cores: {tiles}"
-    assert tiles[0] > tiles[1], "the first batch runs the pass twice (fixed k', then the band)"
+    assert tiles[0] > tiles[1], "the first batch runs the pass again with the wide margin and then in band mode"
     assert max(rescans) <= b // 20, f"at most 5 % of a batch may fall back to single-query scans: {rescans}"
     ctx.drop("learn")
 

@@ -1451,7 +1451,7 @@ static int guess_rank(int kprime, double g) {
 cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t b, uint32_t k, int sm_count, void **scratch,
                                   size_t *scratch_bytes, int *status, Hit *out, unsigned long long *out_ids, float *out_dist,
                                   cudaStream_t st, BatchedStats *stats, cudaEvent_t ev_start, cudaEvent_t ev_stop, bool band_mode,
-                                  bool guess_mode) {
+                                  bool guess_mode, bool wide_margin) {
     // operand mode: bf16 mirrors with folded thresholds when the collection has a mirror, else the stored f32 rows as tf32
     const bool H = s.rows_h != nullptr;
     const uint32_t kd = mirror_kd(s.dim), ld_h = mirror_ld(s.dim);
@@ -1466,7 +1466,13 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
     // (the bf16 surrogate cannot order rows closer than its error bound).  Round 1 used pow2 >= 2k + 16 (256 for k = 100)
     // with the worst-case operand error; with the measured one (operand_error) 160 already proves every query of
     // configs[2] and of the 1M-row sweep, 128 does not (27 of 256 fail at 1M x 128): 192 it is, and 32 for k = 10.
+    // Collections whose proofs fail at that margin (distances that concentrate: 1M x 1536) get round 1's wider one
+    // (wide_margin: the caller switches per collection) before they fall back to band mode.
     int kprime = ((int)(k + k / 2 + 16) + 31) / 32 * 32;
+    if (wide_margin) {
+        kprime = 64;
+        while (kprime < (int)(2 * k + 16)) kprime <<= 1;
+    }
     {   // tuning knob (any value in [k + 8, 1024] is correct: a k' that is too small only makes more proofs fail)
         static const int kp_env = getenv("VROD_BATCHED_KPRIME") ? atoi(getenv("VROD_BATCHED_KPRIME")) : 0;
         if (kp_env >= (int)k + 8 && kp_env <= CAP) kprime = kp_env;

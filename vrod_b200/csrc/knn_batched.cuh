@@ -36,9 +36,11 @@ bool batched_supported(const ShardView &s, uint32_t b, uint32_t k);
 // to find its k' keys if the rows still to come resemble the rows already seen -- instead of the k'-th best key so far
 // (2-3x fewer candidates, half as many phases).  A guess that did not hold is detected (status[qi] = 2: the caller
 // rescans the query, and stops guessing for a collection whose row order defeats it).
+// wide_margin: k' = pow2 >= 2k + 16 (round 1's rule) instead of 1.5k + 16: the first thing to try when the proofs of a
+// collection fail (high-dimensional data whose distances concentrate), before band mode.
 cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t b, uint32_t k, int sm_count,
                                   void **scratch, size_t *scratch_bytes, int *status, Hit *out, unsigned long long *out_ids,
                                   float *out_dist, cudaStream_t st, BatchedStats *stats, cudaEvent_t ev_start = nullptr,
-                                  cudaEvent_t ev_stop = nullptr, bool band_mode = false, bool guess = false);
+                                  cudaEvent_t ev_stop = nullptr, bool band_mode = false, bool guess = false, bool wide_margin = false);
 
 }  // namespace vrod
