@@ -15,7 +15,7 @@ LIB       := vrod_b200/libvrod_knn$(SUF).so
 
 all: $(LIB) oracle host
 
-$(CSRC)/%$(SUF).o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/vrod_knn.h
+$(CSRC)/%$(SUF).o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) include/vrod_knn.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 debug:

@@ -24,6 +24,7 @@
 // Stands for the reference's SearchCommand::execute (src/command/types.rs:114-119, empty) when the
 // argument carries many queries; nothing of it exists upstream.
 #include "knn_batched.cuh"
+#include "guess_rank.hpp"
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -1404,48 +1405,6 @@ bool batched_supported(const ShardView &s, uint32_t b, uint32_t k) {
     if (s.ld > 4096) return false;
     if (k > 120) return false;                            // k' = 1.5k + 16 (rounded up to 32s) must stay <= 256 (CAP / 4)
     return encode_fn() != nullptr;
-}
-
-// Guessed thresholds.  After a phase the kprime best keys of the n0 rows seen so far are known exactly.  If the next phase
-// takes the rows seen to g * n0 and the new rows resemble the old ones (exchangeable row order), the key of rank r among
-// the old ones is a threshold below which the new rows contribute NB(r, 1/g) keys (negative binomial: Poisson counts
-// whose rate has the Gamma(r) uncertainty of an r-th order statistic).  The guess holds when r + that count >= kprime.
-// guess_rank returns the smallest r whose failure probability is below 1e-9 per query and phase, plus a margin for rows
-// that are only roughly exchangeable; 0 when guessing gains nothing.  (kprime = 256, g = 8: r = 72 -- the phase collects
-// ~500 candidates per query where the kprime-th best key as threshold lets ~1800 through.)
-static double nb_cdf(int m, int r, double pr) {   // P(NB(r, pr) <= m), in the log domain
-    if (m < 0) return 0.0;
-    const double lq = log1p(-pr);
-    double lt = (double)r * log(pr), top = lt, acc = 1.0;   // the sum so far = exp(top) * acc
-    for (int i = 0; i < m; ++i) {
-        lt += log((double)(i + r) / (double)(i + 1)) + lq;
-        if (lt > top) {
-            acc = acc * exp(top - lt) + 1.0;
-            top = lt;
-        } else {
-            acc += exp(lt - top);
-        }
-    }
-    return exp(top) * acc;
-}
-static int guess_rank(int kprime, double g) {
-    if (!(g > 1.25)) return 0;
-    struct Memo { int kprime; double g; int r; };
-    static thread_local Memo memo[8] = {};
-    static thread_local int memo_next = 0;
-    for (const Memo &m : memo)
-        if (m.kprime == kprime && m.g == g) return m.r;
-    int lo = 1, hi = kprime;   // smallest r with P(r + NB(r, 1/g) < kprime) < tol; the probability falls with r
-    while (lo < hi) {
-        const int mid = (lo + hi) / 2;
-        if (nb_cdf(kprime - mid - 1, mid, 1.0 / g) < 1e-9) hi = mid;
-        else lo = mid + 1;
-    }
-    int r = lo + lo / 16 + 2;
-    if (r * 10 > kprime * 9) r = 0;   // nearly the kprime-th key anyway
-    memo[memo_next] = Memo{kprime, g, r};
-    memo_next = (memo_next + 1) % 8;
-    return r;
 }
 
 cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t b, uint32_t k, int sm_count, void **scratch,
