@@ -146,7 +146,7 @@ struct PinBuf {
 // completed (polled at a later search, never waited for) the elapsed time is folded into the matching term.  The
 // boxes of this pool differed by 1537..1965 MHz under load, which the seeds alone would not follow.
 struct CostModel {
-    double scan_fixed = 25e-6, hbm_bps = 6.5e12, batched_fixed = 200e-6, tile_seconds = 1.45e-6;
+    double scan_fixed = 20e-6, hbm_bps = 6.5e12, batched_fixed = 150e-6, tile_seconds = 1.2e-6;   // seeds: round-2 measurements
     uint32_t calls = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int pending_kind = 0;      // 0 none, 1 scan, 2 batched
@@ -186,11 +186,11 @@ struct CostModel {
             if (pending_kind == 1) {
                 const double stream_t = pending_work / hbm_bps;
                 if (stream_t > 4.0 * scan_fixed) hbm_bps = blend(hbm_bps, pending_work / (t > scan_fixed ? t - scan_fixed : t), 6.5e12);
-                else if (stream_t < scan_fixed) scan_fixed = blend(scan_fixed, t - stream_t, 25e-6);
+                else if (stream_t < scan_fixed) scan_fixed = blend(scan_fixed, t - stream_t, 20e-6);
             } else {
                 const double tiles_t = pending_work * tile_seconds;
-                if (tiles_t > 4.0 * batched_fixed) tile_seconds = blend(tile_seconds, (t > batched_fixed ? t - batched_fixed : t) / pending_work, 1.45e-6);
-                else if (tiles_t < batched_fixed) batched_fixed = blend(batched_fixed, t - tiles_t, 200e-6);
+                if (tiles_t > 4.0 * batched_fixed) tile_seconds = blend(tile_seconds, (t > batched_fixed ? t - batched_fixed : t) / pending_work, 1.2e-6);
+                else if (tiles_t < batched_fixed) batched_fixed = blend(batched_fixed, t - tiles_t, 150e-6);
             }
         } else {
             cudaGetLastError();
