@@ -1,25 +1,29 @@
-// knn_batched.cu -- batched-query path on the 5th-gen tensor cores (sm_100a: tcgen05 + TMEM + TMA).
+// knn_batched.cu -- batched-query path on the 5th-gen tensor cores (sm_100a: tcgen05 + TMEM + bulk copies / TMA).
 //
 // For a batch of queries the scan IS a dense contraction: S = X . Q^T (rows x queries).  One CTA per SM
-// owns a fixed group of BN = 256 queries (resident in shared memory, 128B-swizzled, loaded once by TMA)
-// and streams its share of the collection's row tiles (BM = 128 rows) through a multi-stage TMA ->
-// mbarrier -> tcgen05.mma pipeline into a double-buffered TMEM accumulator (2 x 256 columns).  Eight
-// epilogue warps read the accumulator with tcgen05.ld and NEVER materialise the rows x queries score
-// matrix: a branch-free maximum over each thread's 32 scores tells whether its row beats any query's
-// running threshold, and the rare survivors are appended -- straight from the registers -- to a
+// owns a fixed group of BN = 256 queries (resident in shared memory, loaded once) and streams its share of
+// the collection's row tiles (BM = 128 rows) through a multi-stage copy -> mbarrier -> tcgen05.mma pipeline
+// into a double-buffered TMEM accumulator (2 x 256 columns).  Sixteen epilogue warps read the accumulator
+// with tcgen05.ld, hand the stage back at once, and NEVER materialise the rows x queries score matrix: a
+// branch-free maximum over each thread's 32 scores tells whether its row beats any query's threshold, the
+// rare blocks with a candidate are parked in a small per-warp stash and appended after the tile to a
 // per-(CTA, query) candidate list in global memory.
 //
-// Two operand modes.  Default: bf16 mirrors of the rows and of the query batch (kind::f16) whose 16 aux
-// columns fold the threshold and the row-norm term into the contraction, so the accumulator holds
-// D = dot + thr_q - ||x||^2/2 and "candidate" is D > 0.  Fallback / set_path(4): the stored f32 rows as
-// tf32 operands (kind::tf32, no second copy), thresholds applied in the epilogue.
+// Two operand modes.  Default: TILED bf16 mirrors of the rows and of the query batch (kind::f16; every
+// (tile, K step) block is 4 KB / 8 KB of contiguous memory in the no-swizzle K-major UMMA layout, moved by
+// plain bulk copies) whose 16 aux columns fold the threshold and the row-norm term into the contraction,
+// so the accumulator holds D = dot + thr_q - ||x||^2/2 and "candidate" is D > 0.  Fallback / set_path(4):
+// the stored f32 rows as tf32 operands (kind::tf32 through TMA tensor maps, 128-byte swizzle, no second
+// copy), thresholds applied in the epilogue.
 //
 // The row tiles are processed in phases; between phases batched_finish_kernel merges the lists of all
-// CTAs of a query (radix select) into the exact global k'-th surrogate = every CTA's next threshold.
-// In the last phase it re-evaluates the best k' candidates in canonical f64 (the same arithmetic as the
-// oracle), sorts them by (dist, id) and PROVES with the operand-rounding error bound that no dropped row
-// can belong to the top k; a query whose proof fails is flagged and answered by the single-query scan
-// (knn_scan.cu).
+// CTAs of a query (radix select) into its best k' keys and publishes the next phase's threshold: the
+// k'-th key, or a GUESS (guess_rank.hpp) that the following finish verifies.  In the last phase it
+// re-evaluates the best k' candidates in canonical f64 (the same arithmetic as the oracle), sorts them by
+// (dist, id) and PROVES -- with the rounding error of the operands as measured while the mirrors were
+// built -- that no dropped row can belong to the top k; a query whose proof fails is flagged and answered
+// by the single-query scan (knn_scan.cu).  Collections whose proofs fail escalate: wider margin k', then
+// BAND mode (every candidate within the error band above the k-th best is kept and reranked).
 //
 // Stands for the reference's SearchCommand::execute (src/command/types.rs:114-119, empty) when the
 // argument carries many queries; nothing of it exists upstream.
