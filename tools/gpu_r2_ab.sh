@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B on one box: the committed library (libvrod_knn_head.so) against the working tree's
+# A/B on one box: the committed library (libvrod_knn_head.so) against the working tree's.
+# Build the former first:  git stash && make && cp vrod_b200/libvrod_knn.so vrod_b200/libvrod_knn_head.so && git stash pop && make
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,power.limit,temperature.gpu --format=csv > gpurun_out/ab.log
 {
