@@ -30,12 +30,36 @@ def test_three_bf16_parts_rebuild_an_f32_exactly():
         assert torch.equal(part.to(torch.bfloat16).float(), part)
 
 
+def tiled_offset(r, chunk, R):
+    """knn_batched.cu tiled_offset: byte offset of 8-column chunk `chunk` of row r inside a tile of R rows."""
+    return (chunk >> 1) * R * 32 + (r >> 3) * 256 + (chunk & 1) * 128 + (r & 7) * 16
+
+
 def test_mirror_geometry_matches_the_library():
-    """kd = dim rounded up to 16 data columns + 16 aux columns; rows of 2*ld_h bytes keep TMA's 16-byte stride rule."""
+    """kd = dim rounded up to 16 data columns + 16 aux columns = T K steps of 16 columns.  The mirrors are TILED: a (tile of
+    R rows, K step) block is R * 32 contiguous bytes in the no-swizzle K-major UMMA layout -- 8-row x 16-byte core
+    matrices of 128 contiguous bytes, the two 8-column halves of a K step 128 bytes apart (the descriptor's leading byte
+    offset), consecutive 8-row groups 256 bytes apart (its stride byte offset) -- so a whole tile is ONE contiguous piece
+    that a single bulk copy moves and the MMA descriptor only advances by R * 32 bytes per K step."""
     for dim in (1, 8, 15, 16, 17, 64, 100, 128, 130, 768, 1536):
         kd = (dim + 15) // 16 * 16
         ld_h = kd + 16
-        assert kd >= dim and ld_h % 16 == 0 and (ld_h * 2) % 16 == 0
-        nslab = (ld_h + 63) // 64
-        ksteps_last = (ld_h - (nslab - 1) * 64) // 16
-        assert 1 <= ksteps_last <= 4 and (nslab - 1) * 4 + ksteps_last == ld_h // 16
+        assert kd >= dim and ld_h % 16 == 0
+        T = ld_h // 16
+        for R in (128, 256):                      # row tiles (BM) and query groups (BN)
+            offs = {tiled_offset(r, ch, R) for r in range(R) for ch in range(2 * T)}
+            assert len(offs) == R * 2 * T, "two (row, chunk) pairs share a slot"
+            assert offs == set(range(0, T * R * 32, 16)), "the tile is not one dense piece of T * R * 32 bytes"
+        R = 128
+        for step in range(T):                     # every K step is its own contiguous R * 32-byte block
+            block = {tiled_offset(r, 2 * step + h, R) for r in range(R) for h in (0, 1)}
+            assert min(block) == step * R * 32 and max(block) == (step + 1) * R * 32 - 16
+        for g in range(R // 8):                   # core matrices: 8 rows x 16 bytes, contiguous; LBO 128, SBO 256
+            base = tiled_offset(8 * g, 0, R)
+            assert [tiled_offset(8 * g + i, 0, R) - base for i in range(8)] == [16 * i for i in range(8)]
+            assert tiled_offset(8 * g, 1, R) - base == 128
+            if g + 1 < R // 8:
+                assert tiled_offset(8 * (g + 1), 0, R) - base == 256
+    # shared-memory budget at dim 128: 9 K steps -> 72 KB of queries + 4 stages of 36 KB + the control block = 227 KB
+    T = (128 + 16) // 16
+    assert T * 256 * 32 + 4 * T * 128 * 32 + 11264 == 227 * 1024
