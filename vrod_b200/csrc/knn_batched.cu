@@ -56,7 +56,7 @@ constexpr int kThreads = 64 + 32 * kEpiWarps + 32;
 constexpr int kIssuer2 = kThreads / 32 - 1;
 constexpr int SLAB_A_BYTES = BM * KS * 4;   // 16 KB: 128 rows x 128 B
 // query slab of one CTA: all BN queries (32 KB) alone, its half (16 KB) in a CTA pair
-__host__ __device__ constexpr int slab_b_bytes(int psz) { return BN / psz * KS * 4; }
+constexpr int SLAB_B_BYTES = BN * KS * 4;   // 32 KB: 256 queries x 128 B
 constexpr int MAX_SLABS = 4;                // tf32, dim <= 128: the query group stays resident (128 KB)
 // bf16 operand mode ("H"): a K slab is 64 bf16 = the same 128-byte swizzle row, one MMA covers K = 16.  The mirror of
 // a row / a query is [kd data columns | 16 aux columns] (kd = dim rounded up to 16): the aux columns fold the query's
@@ -78,7 +78,7 @@ constexpr uint32_t kPlainLBO = 128, kPlainSBO = 256;   // chunk-to-chunk and gro
 struct BatchedParams {
     const float *sq_norm, *inv_norm;
     uint32_t n, b, nslab, stages;
-    uint32_t qgroups, units;         // units = CTAs (PSZ = 1) or CTA pairs (PSZ = 2); unit u serves query group u % qgroups
+    uint32_t qgroups, units;         // units = CTAs; unit u serves query group u % qgroups
     uint32_t tile_begin, tile_end;   // this launch (phase) covers row tiles [tile_begin, tile_end)
     const float *thr_init;      // [b] thresholds carried over from the previous phase (nullptr: +inf)
     unsigned long long *cand;   // [grid][BN][CAP]
@@ -127,37 +127,6 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
             smem_u32(dst)),
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
-}
-// CTA-pair (cta_group::2) forms.  The leader (rank 0 of the pair) owns the tmem-empty barriers and the
-// peer-full barriers; the peer's warps arrive there through the cluster-mapped address.
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {   // arrive on CTA rank 0's copy of `bar`
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {        // arrives on the barrier in BOTH CTAs
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     smem_u32(bar)),
-                 "h"((unsigned short)3)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -229,8 +198,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return d;
 }
 // kind::tf32, f32 accumulate, A and B K-major, N = 256, M = 128 (one CTA) or 256 (CTA pair: 128 rows per CTA)
-__host__ __device__ constexpr uint32_t idesc_tf32(int psz) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * psz) >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_tf32() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 // kind::f16 with bf16 A and B, f32 accumulate, both K-major, N = 256, M = 128
@@ -247,25 +216,23 @@ __host__ __device__ constexpr uint32_t idesc_bf16() {
 // indices) and the warp empties the stash after it has handed the stage back.  A warp may then be late by two tile
 // times minus twice its own work before the MMA warp notices.
 constexpr int kStash = 4;                 // parked blocks per warp; fuller blocks (the dense early phases) go in rounds
-struct StashSlot {      // 140 bytes: 16 warps x 4 slots make the control block 11264 bytes, which leaves EXACTLY four 36 KB
-    float score[32];    // stages next to the 72 KB query operand at dim = 128 (227 KB of shared memory)
+struct StashSlot {      // 140 bytes: 16 warps x 4 slots make the control block 11200 bytes, which just leaves four 36 KB
+    float score[32];    // stages next to the 72 KB query operand at dim = 128 (227 KB of shared memory; asserted below)
     uint32_t row, colbase;
     float hx;
 };
 static_assert(sizeof(StashSlot) == 140, "stash slot size");
 struct BatchCtl {
     uint64_t full[8], empty[8], tfull[2], tempty[2], qfull;
-    union {
-        uint64_t pfull[8];       // leader's view of the PEER's slabs (CTA pairs only; not instantiated any more)
-        int pflag[4];            // per 64-column part: one of its lists is long, prune at the next maintenance point
-    };
-    uint64_t pqfull;
+    int pflag[4];                // per 64-column part: one of its lists is long, prune at the next maintenance point
     uint32_t tmem_base;
     int flag;
     alignas(16) float thr[BN];
     int cnt[BN];
     StashSlot stash[kEpiWarps][kStash];
 };
+static_assert(9 * KB_B + 4 * 9 * KB_A + sizeof(BatchCtl) <= 227 * 1024,
+              "dim 128 (9 K steps): the resident query group, four whole-tile stages and the control block must fit 227 KB");
 
 // ---- epilogue: prune one (CTA, query) list with one warp ------------------------------------------
 // Keep the entries <= t where t is the smallest sampled key with at least kprime entries at or below
@@ -406,22 +373,18 @@ __device__ __noinline__ void stash_flush(int first, int nst, const StashSlot *sl
     __syncwarp();
 }
 
-// PSZ = 1 (default): one CTA per unit (tcgen05 cta_group::1, M = 128).  PSZ = 2 (experiment, VROD_BATCHED_PAIR=1):
-// a CTA pair per unit (cluster of 2, cta_group::2, M = 256): each CTA streams its own 128-row tile and keeps
-// only HALF of the query group in shared memory; only the leader CTA issues MMAs, both run TMA and epilogue, the
-// peer's idle MMA warp forwards "slab landed" to the leader.  The 1-CTA kernel spends ~2600 instead of 2048
-// cycles per tile in the MMA (12 KB of shared-memory operands per K=8 step); the pair was meant to cut that to
-// 8 KB per CTA but measured slower in round 1.
-// H = bf16 operand mode (PSZ = 1 only): operands are the bf16 mirrors with the folded aux columns, MMA kind::f16.
+// One CTA per unit (tcgen05 cta_group::1, M = 128).  (A CTA-pair variant of the tf32 kernel -- cluster of 2, cta_group::2,
+// M = 256, half of the query group per CTA -- passed parity in round 1, measured slower and was removed in round 2:
+// tools/mma_probe.cu shows one CTA already issues at the tensor core's full rate.)
+// H = bf16 operand mode: operands are the bf16 mirrors with the folded aux columns, MMA kind::f16.
 // DENSE = the start phase (one tile per CTA, every threshold still above every surrogate): the epilogue writes all 128
 // rows of the tile as candidates of all 256 queries, no test, position = row inside the tile, 256-byte coalesced stores.
-template <bool COS, int PSZ, bool H, bool DENSE>
+template <bool COS, bool H, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                    const __grid_constant__ CUtensorMap tmQ,
                                                                    const BatchedParams p) {
-    static_assert(!(H && PSZ == 2), "the bf16 mode has no CTA-pair variant");
     extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr int SLAB_B = slab_b_bytes(PSZ);
+    constexpr int SLAB_B = SLAB_B_BYTES;
     constexpr int KSE = KS;   // f32 elements per K slab (tf32 mode)
     // resident mode: [query operand of the group][stages x row operand]; streamed mode: [stages x (row + query operand)]
     // (tf32: 128-byte-swizzled slabs written by TMA; bf16: S K-step blocks of the tiled mirrors per stage)
@@ -431,31 +394,26 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
     BatchCtl *ctl = reinterpret_cast<BatchCtl *>(a_s + (size_t)p.stages * stage_bytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (smem_u32(smem) & 1023u) __trap();          // the 128-byte swizzle needs a 1024-byte aligned base
-    const uint32_t rank = PSZ == 2 ? cluster_ctarank() : 0;   // position in the pair
-    const bool leader = rank == 0;
-    const uint32_t unit = blockIdx.x / PSZ;
+    const uint32_t unit = blockIdx.x;
     const uint32_t g = unit % p.qgroups;           // query group of this unit
     const uint32_t member = unit / p.qgroups;
     const uint32_t cpg = (p.units - g + p.qgroups - 1) / p.qgroups;        // units serving this group
-    const uint32_t span = (p.tile_end - p.tile_begin + PSZ - 1) / PSZ;     // super-tiles (PSZ row tiles) of the phase
+    const uint32_t span = p.tile_end - p.tile_begin;                        // row tiles of the phase
     const uint32_t my_tiles = member < span ? (span - member + cpg - 1) / cpg : 0;
-    auto tile_of = [&](uint32_t i) { return p.tile_begin + (member + i * cpg) * PSZ + rank; };
+    auto tile_of = [&](uint32_t i) { return p.tile_begin + member + i * cpg; };
 
     if (tid == 0) {
         for (uint32_t s = 0; s < p.stages; ++s) {
             mbar_init(&ctl->full[s], 1);             // this CTA's own TMA (local transaction bytes)
-            if (PSZ == 2) mbar_init(&ctl->pfull[s], 1);   // pair leader only: the peer's forwarder arrives here
             mbar_init(&ctl->empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&ctl->tfull[a], 1);
-            mbar_init(&ctl->tempty[a], kEpiWarps * PSZ);
+            mbar_init(&ctl->tempty[a], kEpiWarps);
         }
         mbar_init(&ctl->qfull, 1);
-        mbar_init(&ctl->pqfull, 1);
         ctl->flag = 0;
-        if (PSZ == 1)
-            for (int w = 0; w < 4; ++w) ctl->pflag[w] = 0;
+        for (int w = 0; w < 4; ++w) ctl->pflag[w] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < BN; i += kThreads) {
@@ -465,25 +423,17 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
         ctl->cnt[i] = 0;
     }
     if (warp == 1) {
-        if constexpr (PSZ == 2) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(512u)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-        } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(512u)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        }
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
-    if constexpr (PSZ == 2) cluster_sync_all();    // both CTAs' barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem = ctl->tmem_base;
-    const int q_row0 = (int)(g * BN + rank * (BN / PSZ));   // first query row of this CTA's (half of the) group
+    const int q_row0 = (int)(g * BN);   // first query row of this CTA's group
 
     if (warp == 0) {
-        // ===== TMA producer (both CTAs of a pair: each loads its own row tile and its share of the queries) =====
+        // ===== producer =====
         if (H) {
             // ===== bf16 mode: contiguous bulk copies of the tiled mirrors (one per stage and operand) =====
             if (lane == 0) {
@@ -512,8 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                 }
             }
         } else if (lane == 0) {
-            // every CTA completes its TMA bytes on its OWN barrier (completing the peer's bytes on the leader's
-            // barrier through the cluster made the loads ~2x slower); the peer's forwarder warp tells the leader
+            // ===== tf32 mode: 128-byte-wide TMA boxes out of the stored f32 rows =====
             auto load = [&](void *dst, const CUtensorMap *m, int c0, int c1, uint64_t *bar) { tma_load_2d(dst, m, c0, c1, bar); };
             auto arm = [&](uint64_t *bar, uint32_t bytes) { mbar_expect_tx(bar, bytes); };
             if (!p.stream_q) {
@@ -606,28 +555,11 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
     } else if (warp == kIssuer2) {
         // (tf32 mode: the second issuer warp of the bf16 mode has nothing to do)
     } else if (warp == 1) {
-        // ===== peer CTA of a pair: forward "my slab has landed" to the leader, one remote arrive per slab =====
-        if (lane == 0 && !leader) {
-            if (!p.stream_q) {
-                mbar_wait(&ctl->qfull, 0);
-                mbar_arrive_leader(&ctl->pqfull);
-            }
+        // ===== tf32 mode: MMA issuer (one thread) =====
+        if (lane == 0) {
+            if (!p.stream_q) mbar_wait(&ctl->qfull, 0);
             uint32_t stage = 0, phase = 0;
-            for (uint32_t i = 0; i < my_tiles; ++i)
-                for (uint32_t s = 0; s < p.nslab; ++s) {
-                    mbar_wait(&ctl->full[stage], phase);
-                    mbar_arrive_leader(&ctl->pfull[stage]);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                }
-        }
-        // ===== MMA issuer (one thread of the leader CTA) =====
-        if (lane == 0 && leader) {
-            if (!p.stream_q) {
-                mbar_wait(&ctl->qfull, 0);
-                if constexpr (PSZ == 2) mbar_wait(&ctl->pqfull, 0);
-            }
-            uint32_t stage = 0, phase = 0;
-            long long w_tempty = 0, w_full = 0, w_pfull = 0;
+            long long w_tempty = 0, w_full = 0;
             const long long tstart = kDbg ? clock64() : 0;
             for (uint32_t i = 0; i < my_tiles; ++i) {
                 const uint32_t acc = i & 1, aphase = (i >> 1) & 1;
@@ -640,11 +572,6 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                     t0 = (kDbg && p.dbg) ? clock64() : 0;
                     mbar_wait(&ctl->full[stage], phase);
                     if (kDbg && p.dbg) w_full += clock64() - t0;
-                    if constexpr (PSZ == 2) {
-                        t0 = (kDbg && p.dbg) ? clock64() : 0;
-                        mbar_wait(&ctl->pfull[stage], phase);
-                        if (kDbg && p.dbg) w_pfull += clock64() - t0;
-                    }
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(a_s + (size_t)stage * stage_bytes);
                     const uint32_t b_addr = p.stream_q ? a_addr + SLAB_A_BYTES : smem_u32(q_s + (size_t)s * SLAB_B);
@@ -654,22 +581,16 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
                         if ((kDbg && (p.debug_skip & 2)) || kk >= nk) break;
                         const uint64_t ad = umma_desc_sw128(a_addr + kk * 32), bd = umma_desc_sw128(b_addr + kk * 32);
                         const uint32_t accum = (s | kk) != 0 ? 1u : 0u;
-                        if constexpr (PSZ == 2) tc_mma_tf32_pair(d_tmem, ad, bd, idesc_tf32(2), accum);
-                        else tc_mma_tf32(d_tmem, ad, bd, idesc_tf32(1), accum);
+                        tc_mma_tf32(d_tmem, ad, bd, idesc_tf32(), accum);
                     }
-                    // frees the slab (in both CTAs) when these MMAs have read it
-                    if constexpr (PSZ == 2) tc_commit_pair(&ctl->empty[stage]);
-                    else tc_commit(&ctl->empty[stage]);
+                    tc_commit(&ctl->empty[stage]);   // frees the slab when these MMAs have read it
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                // accumulator complete (each CTA's epilogue waits on its own copy of the barrier)
-                if constexpr (PSZ == 2) tc_commit_pair(&ctl->tfull[acc]);
-                else tc_commit(&ctl->tfull[acc]);
+                tc_commit(&ctl->tfull[acc]);         // accumulator complete
             }
             if (kDbg && p.dbg) {
                 p.dbg[blockIdx.x * 16 + 5] = w_tempty;
                 p.dbg[blockIdx.x * 16 + 6] = w_full;
-                p.dbg[blockIdx.x * 16 + 8] = w_pfull;
                 p.dbg[blockIdx.x * 16 + 1] = clock64() - tstart;
             }
         }
@@ -834,11 +755,9 @@ __global__ void __launch_bounds__(kThreads, 1) batched_tile_kernel(const __grid_
     }
     tc_fence_before();
     __syncthreads();
-    if constexpr (PSZ == 2) cluster_sync_all();    // the peer's TMEM and barriers stay alive until the leader is done
     if (warp == 1) {
         tc_fence_after();
-        if constexpr (PSZ == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
 
@@ -1048,7 +967,7 @@ struct FinishParams {
     uint32_t n, ld4, b, k;
     uint32_t rank, world;   // shard coordinates (row_id)
     int kprime, cap, water;
-    uint32_t qgroups, units, psz;   // list layout of the tile kernel: unit u = g + m*qgroups, CTA = u*psz + r
+    uint32_t qgroups, units;        // list layout of the tile kernel: CTA u = g + m*qgroups serves query group g
     const unsigned long long *cand;
     const int *cnt_in;
     int *qflags;                        // [b] |= 1: the query cannot be proven from its lists (in: tile kernels; out: a merge that overran)
@@ -1096,8 +1015,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) batched_finish_kernel(const F
     const uint32_t qi = blockIdx.x;
     const uint32_t g = qi / BN, ql = qi % BN;
     const float4 *q4 = p.q4 + (size_t)qi * p.ld4;
-    const uint32_t nlists = (p.units - g + p.qgroups - 1) / p.qgroups * p.psz;   // CTAs that scanned rows for this query
-    auto cta_of = [&](uint32_t l) { return (g + (l / p.psz) * p.qgroups) * p.psz + (l % p.psz); };
+    const uint32_t nlists = (p.units - g + p.qgroups - 1) / p.qgroups;   // CTAs that scanned rows for this query
+    auto cta_of = [&](uint32_t l) { return g + l * p.qgroups; };
     if (tid == 0) {
         cand_reset(ctl);
         ctl->overflow = 0;
@@ -1448,18 +1367,13 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
     // then only covers the accumulation.
     const double eps_dot = H ? (double)ld_h * ldexp(1.0, -22) : ldexp(1.0, -9) * 1.01 + (double)s.ld * ldexp(1.0, -22);
 
-    // One CTA per unit (cta_group::1).  The CTA-pair form of the tf32 kernel (cta_group::2, M = 256; the template's
-    // PSZ = 2 paths) passed parity but measured slower in round 1 and is no longer instantiated: tools/mma_probe.cu
-    // shows a single CTA already issues its M = 128 x N = 256 MMAs at the tensor core's full rate (128.0 cycles each)
-    // with the operand copies and the accumulator reads running, so pairing has nothing to give here.
-    const uint32_t psz = 1u;
     // band mode (bf16 operand mode only): every key within the error band above the k-th best approximate key is kept, up to
     // kBandKeep per query
     constexpr int kBandKeep = 1024;
     const bool band = band_mode && H && (int)k <= kBandKeep / 2;
     const int keep = band ? kBandKeep : kprime;
-    const uint32_t max_units = (uint32_t)sm_count / psz;
-    const uint32_t super_tiles = (ntiles + psz - 1) / psz;
+    const uint32_t max_units = (uint32_t)sm_count;   // one CTA (= one unit) per SM
+    const uint32_t super_tiles = ntiles;
 
     for (uint32_t g0 = 0; g0 < qgroups; g0 += max_units) {
         const uint32_t groups = qgroups - g0 < max_units ? qgroups - g0 : max_units;
@@ -1468,7 +1382,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         uint32_t units = groups * (max_units / groups);
         if ((unsigned long long)groups * super_tiles < units) units = groups * super_tiles;   // no more units than work
         const uint32_t cpg_max = (units + groups - 1) / groups;
-        const uint32_t grid = units * psz;
+        const uint32_t grid = units;
         const uint32_t bq = b - g0 * BN < groups * BN ? b - g0 * BN : groups * BN;   // queries in this wave
         const float *qw = d_q + (size_t)g0 * BN * s.ld;
 
@@ -1513,7 +1427,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             prep<<<(slots + 7) / 8, 256, 0, st>>>(qw, bq, slots, s.ld, kd, T, s.maxnorm_bits, qt, gthr, qcap, nocand ? -1.f : 1.f,
                                                   band ? qband : nullptr, (float)eps_dot, acc_eps_f, s.mirror_stats);
             if (stats) stats->launches += 1;
-        } else if (!make_map(&tmX, s.rows, s.n, s.ld, BM) || !make_map(&tmQ, qw, bq, s.ld, BN / psz)) {
+        } else if (!make_map(&tmX, s.rows, s.n, s.ld, BM) || !make_map(&tmQ, qw, bq, s.ld, BN)) {
             return cudaErrorInvalidValue;
         }
 
@@ -1571,7 +1485,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
             // tf32 mode, dim <= 128: the query group is resident (nslab x 32 KB) and only row slabs stream; larger dims
             // stream the query slab next to every row slab (48 KB stages, L2-bandwidth bound: DESIGN.md)
             p.stream_q = nslab > (uint32_t)MAX_SLABS ? 1 : 0;
-            const size_t slab_b = (size_t)slab_b_bytes((int)psz);
+            const size_t slab_b = (size_t)SLAB_B_BYTES;
             resident = p.stream_q ? 0 : (size_t)nslab * slab_b;
             stage_bytes = p.stream_q ? (SLAB_A_BYTES + slab_b) : SLAB_A_BYTES;
         }
@@ -1587,11 +1501,11 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         p.stages = (uint32_t)stages;
         const size_t smem = resident + stages * stage_bytes + sizeof(BatchCtl);
         typedef void (*TileFn)(const CUtensorMap, const CUtensorMap, const BatchedParams);
-        const TileFn tile_fn = H ? (s.metric ? batched_tile_kernel<true, 1, true, false> : batched_tile_kernel<false, 1, true, false>)
-                                 : (s.metric ? batched_tile_kernel<true, 1, false, false> : batched_tile_kernel<false, 1, false, false>);
+        const TileFn tile_fn = H ? (s.metric ? batched_tile_kernel<true, true, false> : batched_tile_kernel<false, true, false>)
+                                 : (s.metric ? batched_tile_kernel<true, false, false> : batched_tile_kernel<false, false, false>);
         // the start phase (one tile per CTA, everything passes) has its own epilogue
-        const TileFn tile_fn_first = H ? (s.metric ? batched_tile_kernel<true, 1, true, true> : batched_tile_kernel<false, 1, true, true>)
-                                       : (s.metric ? batched_tile_kernel<true, 1, false, true> : batched_tile_kernel<false, 1, false, true>);
+        const TileFn tile_fn_first = H ? (s.metric ? batched_tile_kernel<true, true, true> : batched_tile_kernel<false, true, true>)
+                                       : (s.metric ? batched_tile_kernel<true, false, true> : batched_tile_kernel<false, false, true>);
         e = cudaFuncSetAttribute(tile_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_fn_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1602,7 +1516,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cattr[0].id = cudaLaunchAttributeClusterDimension;
-        cattr[0].val.clusterDim.x = psz;
+        cattr[0].val.clusterDim.x = 1;   // (the kernels address shared memory through the cluster window: a cluster of one)
         cattr[0].val.clusterDim.y = 1;
         cattr[0].val.clusterDim.z = 1;
         cfg.attrs = cattr;
@@ -1625,7 +1539,6 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         f.water = f.cap - kScanThreads;
         f.qgroups = groups;
         f.units = units;
-        f.psz = psz;
         f.cand = cand;
         f.cnt_in = cnt;
         f.qflags = qflags;
@@ -1645,14 +1558,14 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
         f.T = T;
         f.qcap = qcap;
         f.acc_eps = H ? (double)(ld_h / UMMA_K_H + 2) * ldexp(1.0, -23) : 0.0;
-        const size_t fsmem = kFinCtl + (size_t)f.cap * sizeof(unsigned long long) + ((size_t)kFinHist + (size_t)cpg_max * psz + 2) * sizeof(int);
+        const size_t fsmem = kFinCtl + (size_t)f.cap * sizeof(unsigned long long) + ((size_t)kFinHist + (size_t)cpg_max + 2) * sizeof(int);
         auto fin_fn = s.metric ? batched_finish_kernel<true> : batched_finish_kernel<false>;
 
         // Phases over the row tiles: 1 tile per CTA first, then each phase 3.5x the rows seen so far (phase
         // boundaries are multiples of the pair size).  Between
         // phases the finish kernel merges all CTA lists of a query into its exact global k'-th threshold, so
         // the candidate rate of a phase is ~k'/rows_seen instead of ~k'/rows_seen_by_one_CTA.
-        uint32_t t_begin = 0, t_end = cpg_max * psz < ntiles ? cpg_max * psz : ntiles;
+        uint32_t t_begin = 0, t_end = cpg_max < ntiles ? cpg_max : ntiles;
         bool first = true;
         static const bool no_guess_env = getenv("VROD_BATCHED_NO_GUESS") != nullptr;
         const bool guess = guess_mode && !band && !no_guess_env;
@@ -1670,8 +1583,7 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
                 static const double growth_env = getenv("VROD_BATCHED_GROWTH") ? atof(getenv("VROD_BATCHED_GROWTH")) : 0.0;
                 const double growth = growth_env > 1.0 ? growth_env : ((guess || (super_tiles / cpg_max) < 256) ? 8.0 : 3.5);
                 unsigned long long nxt = (unsigned long long)((double)t_end * growth);
-                if (nxt <= t_end) nxt = t_end + psz;
-                nxt -= nxt % psz;
+                if (nxt <= t_end) nxt = t_end + 1;
                 t_next = nxt >= ntiles ? ntiles : (uint32_t)nxt;
                 // a short rest is not worth a phase of its own
                 if (guess && ntiles - t_next < t_next / 2) t_next = ntiles;
@@ -1705,19 +1617,9 @@ cudaError_t launch_batched_search(const ShardView &s, const float *d_q, uint32_t
                 double a[13] = {0};
                 for (uint32_t c = 0; c < grid; ++c)
                     for (int jx = 0; jx < 13; ++jx) a[jx] += (double)h[c * 16 + jx] / grid;
-                if (psz == 2) {
-                    double le = 0, pe = 0, wf = 0, wpf = 0, mt = 0;
-                    for (uint32_t c = 0; c < grid; c += 2) {
-                        le += (double)h[c * 16 + 9]; pe += (double)h[(c + 1) * 16 + 9];
-                        wf += (double)h[c * 16 + 6]; wpf += (double)h[c * 16 + 8]; mt += (double)h[c * 16 + 1];
-                    }
-                    const double np = grid / 2.0;
-                    fprintf(stderr, "[batched dbg pair] leader: mma total %.0f wait_full(own) %.0f wait_pfull(peer) %.0f | producer wait_empty leader %.0f peer %.0f\n",
-                            mt / np, wf / np, wpf / np, le / np, pe / np);
-                }
                 fprintf(stderr, "[batched dbg] tiles [%u,%u) avg/CTA: warp2 slow entries %.0f, mma total %.0f, candidates %.0f | epi wait_tfull %.0f prune %.0f | mma wait_tempty %.0f wait_full %.0f "
                                 "| epi total %.0f (warp2: park %.0f flush %.0f part barrier %.0f) | tiles/CTA %u\n",
-                        t_begin, t_end, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[10], a[11], a[12], (t_end - t_begin + cpg_max * psz - 1) / (cpg_max * psz));
+                        t_begin, t_end, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[10], a[11], a[12], (t_end - t_begin + cpg_max - 1) / cpg_max);
             }
             if (last) break;
             first = false;
