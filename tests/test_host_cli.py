@@ -69,3 +69,23 @@ def test_script_describe_mode():
     assert r.stdout.splitlines() == ['CreateCollectionCommand{collection_name=Some("words;4;cosine"),arg=None}',
                                      'SearchCommand{collection_name=Some("words"),arg=Some("3;1,2,3,4")}',
                                      "ListCollectionsCommand{collection_name=None,arg=None}"]
+
+
+def test_devices_flag_is_validated_before_anything_runs():
+    """--devices A,B,.. selects the single-process multi-GPU context (vrod_ctx_create_multi); a malformed list is a usage
+    error, and --describe never touches a GPU whatever the list says."""
+    r = run("--describe", "--devices", "0,1,2,3", "-c", "C", "-e", "SEARCH", "-a", "3;1,2")
+    assert r.returncode == 0 and r.stdout.strip() == 'SearchCommand{collection_name=Some("C"),arg=Some("3;1,2")}'
+    for bad in ("0,x", "1;2", "a"):
+        r = run("--describe", "--devices", bad, "-e", "LISTCOLLECTIONS")
+        assert r.returncode == 2 and "--devices takes a comma-separated list" in r.stderr, (bad, r.stderr)
+
+
+def test_executing_without_a_gpu_fails_loudly():
+    """There is no CPU path: a command that needs the library's context reports the CUDA error and exits non-zero (on a
+    GPU box the same command succeeds -- tests/test_gpu_host_cli.py)."""
+    import shutil
+    if shutil.which("nvidia-smi") and subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0:
+        pytest.skip("a GPU is visible")
+    r = run("-e", "LISTCOLLECTIONS")
+    assert r.returncode != 0 and r.stderr.strip(), (r.returncode, r.stdout, r.stderr)
