@@ -62,7 +62,7 @@ def _worker(rank, world, port, n, d, k, metric, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,metric", [(2, 0), (2, 1), (3, 0)])
+@pytest.mark.parametrize("world,metric", [(2, 0), (2, 1), (3, 0), (4, 1)])
 def test_gloo_sharded_equals_unsharded(tmp_path, oracle, world, metric):
     n, d, k = 3 * SHARD_BLOCK + 1001, 48, 12
     s = socket.socket()
